@@ -1,0 +1,145 @@
+// common.cuh -- device-side model description, Philox4x32-10 streams and the draw
+// primitives shared by every kernel of the B200 ensemble-MCMC engine (sm_100a).
+//
+// Randomness replaces numpy's Generator calls on the reference hot path
+// (cobaya/samplers/mcmc/proposal.py:54,79-82,90; cobaya/functions.py:36;
+// cobaya/samplers/mcmc/mcmc.py:683) with counter-based streams, so that any
+// thread can produce any draw and the CPU oracle consumes identical values
+// (layout: DESIGN.md section 4).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "../../include/cobaya_b200.h"
+
+#define CB2_TAG_STEP 0u
+#define CB2_TAG_ACCEPT 1u
+#define CB2_TAG_BASIS 2u
+#define CB2_TAG_CYCLER 3u
+#define CB2_TAG_STEP2 4u
+
+#define CB2_LOG_2PI 1.8378770664093453
+
+struct LikeDev {
+    int32_t kind, dim, n_modes, derived;
+    int32_t idx_off;     // into Model.ipool
+    int32_t means_off;   // into Model.dpool: [m*dim]
+    int32_t linvT_off;   // [m][dim*dim], element (row i, col j) at j*dim + i
+    int32_t c0_off;      // [m]  dim*log(2pi) + logdet_k
+    int32_t w_off;       // [m]
+    int32_t der_off;     // offset of this likelihood's derived params in the row
+    double scale;        // rosenbrock
+};
+
+struct ModelDev {
+    int32_t D, n_like, n_der, width;
+    // prior
+    const int32_t *prior_kind;  // [D]
+    const double *lower, *upper, *loc, *pscale;
+    const int32_t *periodic;
+    int32_t any_periodic, any_normal;
+    double uniform_logp;
+    // likelihoods
+    LikeDev likes[CB2_MAX_LIKES];
+    const double *dpool;
+    const int32_t *ipool;
+    // blocking
+    int32_t n_blocks;
+    int32_t bsize[CB2_MAX_BLOCKS], jstart[CB2_MAX_BLOCKS], oversamp[CB2_MAX_BLOCKS];
+    const int32_t *i_of_j;  // [D]
+    int32_t drag, last_slow, drag_steps, n_slow, n_fast;
+    // proposal: TT[k*D + j] = T[j][k]  (column k contiguous over rows j)
+    const double *TT;
+    double proposal_scale;
+    // options
+    double temperature;
+    int64_t max_tries;
+    int32_t output_thin;
+    // rng
+    uint32_t key0, key1;
+    uint64_t chain_id0;
+};
+
+// ---------------------------------------------------------------- Philox4x32-10
+struct u32x4 {
+    uint32_t x, y, z, w;
+};
+
+__host__ __device__ __forceinline__ u32x4 philox4x32_10(uint32_t k0, uint32_t k1,
+                                                         uint32_t c0, uint32_t c1,
+                                                         uint32_t c2, uint32_t c3) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+#ifdef __CUDA_ARCH__
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+#else
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+        uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+#endif
+        uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    u32x4 o;
+    o.x = c0; o.y = c1; o.z = c2; o.w = c3;
+    return o;
+}
+
+// 52-bit uniform strictly inside (0,1)
+__host__ __device__ __forceinline__ double u52(uint32_t a, uint32_t b) {
+    uint64_t k = ((uint64_t)(a >> 6) << 26) | (uint64_t)(b >> 6);
+    return ((double)k + 0.5) * 2.220446049250313e-16;
+}
+
+// radial part of a proposal: propose_r / RandProposer1D (proposal.py:71-93)
+__device__ __forceinline__ void draw_radial(const ModelDev &M, uint64_t gid, uint64_t t,
+                                            uint32_t sub, int n_block, double &r,
+                                            double &sign) {
+    u32x4 w = philox4x32_10(M.key0, M.key1, (uint32_t)t, (uint32_t)(t >> 32),
+                            (uint32_t)gid, CB2_TAG_STEP | (sub << 8));
+    double u_mix = ((double)w.x + 0.5) * 2.3283064365386963e-10;
+    double u_r = u52(w.z, w.w);
+    sign = (w.y & 1u) ? 1.0 : -1.0;
+    if (u_mix < 0.33) {
+        r = -log(u_r);
+    } else if (n_block >= 2) {
+        r = sqrt(-2.0 * log(u_r));
+    } else {
+        u32x4 w2 = philox4x32_10(M.key0, M.key1, (uint32_t)t, (uint32_t)(t >> 32),
+                                 (uint32_t)gid, CB2_TAG_STEP2 | (sub << 8));
+        double u2 = u52(w2.x, w2.y);
+        r = fabs(sqrt(-2.0 * log(u_r)) * cospi(2.0 * u2));
+    }
+}
+
+// Exp(1) draw of metropolis_accept (mcmc.py:683)
+__device__ __forceinline__ double draw_accept_exp(const ModelDev &M, uint64_t gid,
+                                                  uint64_t t, uint32_t sub) {
+    u32x4 w = philox4x32_10(M.key0, M.key1, (uint32_t)t, (uint32_t)(t >> 32),
+                            (uint32_t)gid, CB2_TAG_ACCEPT | (sub << 8));
+    return -log(u52(w.x, w.y));
+}
+
+// pair p of the standard normals consumed by random_SO_N (functions.py:36)
+__device__ __forceinline__ void draw_normal_pair(uint32_t k0, uint32_t k1, uint64_t gid,
+                                                 int block, uint32_t epoch, uint32_t p,
+                                                 double &z0, double &z1) {
+    u32x4 w = philox4x32_10(k0, k1, p, epoch, (uint32_t)gid,
+                            CB2_TAG_BASIS | ((uint32_t)block << 8));
+    double u1 = u52(w.x, w.y), u2 = u52(w.z, w.w);
+    double rad = sqrt(-2.0 * log(u1));
+    double s, c;
+    sincospi(2.0 * u2, &s, &c);
+    z0 = rad * c;
+    z1 = rad * s;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}

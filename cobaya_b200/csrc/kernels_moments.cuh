@@ -1,0 +1,189 @@
+// kernels_moments.cuh -- per-GPU sufficient statistics of the convergence check
+// (MCMC.check_convergence_and_learn_proposal, mcmc.py:773-889) and small reductions.
+#pragma once
+#include "common.cuh"
+
+// A "task" is one (virtual) chain of the R-1 computation: rows [first, last) of a
+// stored chain, counted with weight N in the mean of covariances (mcmc.py:791-822).
+struct MomentTask {
+    int64_t chain, first, last;
+    double N;
+};
+
+// mode HALVES: task c = rows [n_c/2, n_c) of chain c, N = n_c   (mcmc.py:787-793)
+__global__ void k_tasks_halves(const int64_t *__restrict__ n_rows, int64_t n_chains,
+                               MomentTask *__restrict__ tasks) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= n_chains) return;
+    int64_t n = n_rows[c];
+    MomentTask t;
+    t.chain = c;
+    t.first = n / 2;  // int(self.n() / 2)
+    t.last = n;
+    t.N = (double)n;
+    tasks[c] = t;
+}
+
+// Per task: Sw = sum w, mean m = sum w x / Sw over rows [first,last)
+// (SampleCollection.mean, collection.py:893-935).  One warp per task.
+__global__ void k_task_means(const double *__restrict__ rows, int64_t cap, int width, int D,
+                             const MomentTask *__restrict__ tasks, int64_t n_tasks,
+                             double *__restrict__ means, double *__restrict__ sw_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t t = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (t >= n_tasks) return;
+    const MomentTask T = tasks[t];
+    const double *base = rows + (size_t)T.chain * cap * width;
+    double sw = 0.0;
+    for (int64_t r = T.first; r < T.last; ++r) sw += base[(size_t)r * width];
+    for (int d = lane; d < D; d += 32) {
+        double acc = 0.0;
+        for (int64_t r = T.first; r < T.last; ++r) {
+            const double *row = base + (size_t)r * width;
+            acc += row[0] * row[2 + d];
+        }
+        means[t * D + d] = acc / sw;
+    }
+    if (lane == 0) sw_out[t] = sw;
+}
+
+// Accumulate, over the tasks assigned to this CTA, the partial sums
+//   P[0]=M, P[1]=sum N, P[2]=sum N*a, P[3..3+D)=sum (m-shift),
+//   P[3+D..+D^2) = sum (m-shift)(m-shift)^T,  P[3+D+D^2..) = sum N * C
+// with C = sum_r w_r (x_r-m)(x_r-m)^T / Sw  (np.cov(ddof=0, fweights), collection.py:968)
+// and a = (#rows)/Sw (get_acceptance_rate, mcmc.py:311-318).
+// Each thread owns a fixed set of (i,j) entries -> deterministic summation order.
+// PER > 0: entries live in registers (PER per thread); PER == 0: in the global partial.
+template <int PER>
+__global__ void __launch_bounds__(256)
+k_task_accumulate(const double *__restrict__ rows, int64_t cap, int width, int D,
+                  const MomentTask *__restrict__ tasks, int64_t n_tasks,
+                  const double *__restrict__ means, const double *__restrict__ sw_in,
+                  const double *__restrict__ shift, double *__restrict__ partials) {
+    extern __shared__ double sm[];
+    double *xc = sm;       // [D] centred row
+    double *ms = sm + D;   // [D] mean - shift
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int DD = D * D;
+    const int per = (DD + nt - 1) / nt;
+    double *P = partials + (size_t)blockIdx.x * (size_t)(3 + D + 2 * DD);
+    for (int e = tid; e < 3 + D + 2 * DD; e += nt) P[e] = 0.0;
+    __syncthreads();
+    constexpr int NR = PER > 0 ? PER : 1;
+    double cacc[NR], macc[NR];
+    int ei[NR], ej[NR];
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {
+        cacc[k] = 0.0;
+        macc[k] = 0.0;
+        int e = tid + k * nt;
+        ei[k] = (e < DD) ? e / D : 0;
+        ej[k] = (e < DD) ? e % D : 0;
+    }
+    double accM = 0.0, accN = 0.0, accNa = 0.0;
+    for (int64_t t = blockIdx.x; t < n_tasks; t += gridDim.x) {
+        const MomentTask T = tasks[t];
+        const double sw = sw_in[t];
+        const double *base = rows + (size_t)T.chain * cap * width;
+        __syncthreads();
+        for (int d = tid; d < D; d += nt) ms[d] = means[t * D + d] - (shift ? shift[d] : 0.0);
+        __syncthreads();
+        for (int d = tid; d < D; d += nt) P[3 + d] += ms[d];
+        if (PER > 0) {
+#pragma unroll
+            for (int k = 0; k < NR; ++k) macc[k] += ms[ei[k]] * ms[ej[k]];
+        } else {
+            for (int k = 0; k < per; ++k) {
+                int e = tid + k * nt;
+                if (e < DD) P[3 + D + e] += ms[e / D] * ms[e % D];
+            }
+        }
+        const double f = T.N / sw;
+        for (int64_t r = T.first; r < T.last; ++r) {
+            const double *row = base + (size_t)r * width;
+            __syncthreads();
+            for (int d = tid; d < D; d += nt) xc[d] = row[2 + d] - means[t * D + d];
+            __syncthreads();
+            const double wf = row[0] * f;
+            if (PER > 0) {
+#pragma unroll
+                for (int k = 0; k < NR; ++k) cacc[k] += wf * xc[ei[k]] * xc[ej[k]];
+            } else {
+                for (int k = 0; k < per; ++k) {
+                    int e = tid + k * nt;
+                    if (e < DD) P[3 + D + DD + e] += wf * xc[e / D] * xc[e % D];
+                }
+            }
+        }
+        if (tid == 0) {
+            accM += 1.0;
+            accN += T.N;
+            accNa += T.N * ((double)(T.last - T.first) / sw);
+        }
+    }
+    __syncthreads();
+    if (PER > 0) {
+#pragma unroll
+        for (int k = 0; k < NR; ++k) {
+            int e = tid + k * nt;
+            if (e < DD) {
+                P[3 + D + e] = macc[k];
+                P[3 + D + DD + e] = cacc[k];
+            }
+        }
+    }
+    if (tid == 0) {
+        P[0] = accM;
+        P[1] = accN;
+        P[2] = accNa;
+    }
+}
+
+// out[e] = sum over CTAs (fixed order) of partials[cta][e]
+__global__ void k_reduce_partials(const double *__restrict__ partials, int n_parts, int len,
+                                  double *__restrict__ out) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= len) return;
+    double acc = 0.0;
+    for (int p = 0; p < n_parts; ++p) acc += partials[(size_t)p * len + e];
+    out[e] = acc;
+}
+
+// out[0..7] = min rows, max rows, sum rows, #stuck, #rows-full, (unused), sum accepted,
+// sum of current weights.  Single CTA.
+__global__ void k_summary(const int64_t *__restrict__ n_rows, const int64_t *__restrict__ n_acc,
+                          const int64_t *__restrict__ weight, const uint32_t *__restrict__ flags,
+                          int64_t n_chains, int64_t *__restrict__ out) {
+    __shared__ long long s_min[256], s_max[256], s_sum[256], s_stuck[256], s_full[256],
+        s_acc[256], s_w[256], s_int[256];
+    int tid = threadIdx.x;
+    long long mn = INT64_MAX, mx = INT64_MIN, sm_ = 0, st = 0, fu = 0, ac = 0, ww = 0, in = 0;
+    for (int64_t c = tid; c < n_chains; c += blockDim.x) {
+        long long n = n_rows[c];
+        mn = n < mn ? n : mn;
+        mx = n > mx ? n : mx;
+        sm_ += n;
+        st += (flags[c] & 1u) ? 1 : 0;
+        fu += (flags[c] & 2u) ? 1 : 0;
+        in += (flags[c] & 4u) ? 1 : 0;
+        ac += n_acc[c];
+        ww += weight[c];
+    }
+    s_min[tid] = mn; s_max[tid] = mx; s_sum[tid] = sm_; s_stuck[tid] = st; s_full[tid] = fu;
+    s_acc[tid] = ac; s_w[tid] = ww; s_int[tid] = in;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (tid < o) {
+            s_min[tid] = s_min[tid + o] < s_min[tid] ? s_min[tid + o] : s_min[tid];
+            s_max[tid] = s_max[tid + o] > s_max[tid] ? s_max[tid + o] : s_max[tid];
+            s_sum[tid] += s_sum[tid + o]; s_stuck[tid] += s_stuck[tid + o];
+            s_full[tid] += s_full[tid + o]; s_acc[tid] += s_acc[tid + o];
+            s_w[tid] += s_w[tid + o]; s_int[tid] += s_int[tid + o];
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        out[0] = s_min[0]; out[1] = s_max[0]; out[2] = s_sum[0]; out[3] = s_stuck[0];
+        out[4] = s_full[0]; out[5] = s_int[0]; out[6] = s_acc[0]; out[7] = s_w[0];
+    }
+}

@@ -1,0 +1,187 @@
+"""
+Thin object wrapper over the C ABI (include/cobaya_b200.h): one ``Engine`` = one GPU =
+``n_chains`` lock-step chains.  No numerics happen here; numpy arrays are passed to the
+library as plain pointers.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _cabi
+from .flatmodel import LIKE_GAUSSIAN_MIXTURE, LIKE_ROSENBROCK, FlatModel
+
+FLAG_STUCK = 1
+FLAG_ROWS_FULL = 2
+FLAG_INTERNAL = 4
+MOMENTS_HALVES = 0
+MOMENTS_SINGLE_SPLIT = 1
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class Engine:
+    def __init__(self, fm: FlatModel, n_chains: int, seed: int, device: int = 0,
+                 chain_id0: int = 0, rows_cap: int = 1024, burn_in: int = 0):
+        self.lib = _cabi.load()
+        self.fm = fm
+        self.n_chains = int(n_chains)
+        self.D = fm.D
+        self.seed = int(seed)
+        self.chain_id0 = int(chain_id0)
+        self.device = int(device)
+        h = C.c_void_p()
+        rc = self.lib.cb2_create(self.device, self.n_chains, self.D, self.seed,
+                                 self.chain_id0, C.byref(h))
+        if rc != 0:
+            raise EngineError(self.lib.cb2_last_error(None).decode())
+        self.h = h
+        self.rows_cap = int(rows_cap)
+        self.burn_in = int(burn_in)
+        self._upload_model()
+
+    # ------------------------------------------------------------------ plumbing
+    def _ck(self, rc):
+        if rc != 0:
+            raise EngineError(self.lib.cb2_last_error(self.h).decode() or f"error {rc}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cb2_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _upload_model(self):
+        fm, p = self.fm, _cabi.ptr
+        self._ck(self.lib.cb2_set_prior(
+            self.h, p(_i32(fm.prior_kind)), p(_f64(fm.lower)), p(_f64(fm.upper)),
+            p(_f64(fm.loc)), p(_f64(fm.pscale)), p(_i32(fm.periodic)), fm.uniform_logp))
+        self._ck(self.lib.cb2_clear_likelihoods(self.h))
+        for lk in fm.likes:
+            if lk.kind == LIKE_GAUSSIAN_MIXTURE:
+                self._ck(self.lib.cb2_add_gaussian_mixture(
+                    self.h, lk.dim, p(_i32(lk.idx)), lk.n_modes, p(_f64(lk.means)),
+                    p(_f64(lk.linv)), p(_f64(lk.logdet)), p(_f64(lk.weights)),
+                    int(lk.derived)))
+            elif lk.kind == LIKE_ROSENBROCK:
+                self._ck(self.lib.cb2_add_rosenbrock(self.h, lk.dim, p(_i32(lk.idx)),
+                                                     float(lk.scale)))
+            else:
+                raise EngineError(f"unknown likelihood kind {lk.kind}")
+        self._ck(self.lib.cb2_set_blocking(
+            self.h, len(fm.blocks), p(_i32(fm.block_sizes)), p(_i32(fm.oversampling)),
+            p(_i32(fm.i_of_j)), int(fm.drag), int(fm.last_slow),
+            int(fm.drag_interp_steps)))
+        if fm.T is not None:
+            self.set_proposal(fm.T, fm.proposal_scale)
+        self._ck(self.lib.cb2_set_options(
+            self.h, float(fm.temperature), self.burn_in,
+            int(min(fm.max_tries, 2**62)), int(fm.output_thin), self.rows_cap))
+
+    # ------------------------------------------------------------------ API
+    def set_proposal(self, T, proposal_scale=None):
+        """BlockedProposer.set_covariance result (proposal.py:226-260)."""
+        scale = self.fm.proposal_scale if proposal_scale is None else proposal_scale
+        self._ck(self.lib.cb2_set_proposal(self.h, _cabi.ptr(_f64(T)), float(scale)))
+
+    def set_covariance(self, cov):
+        self.fm.set_covariance(cov)
+        self.set_proposal(self.fm.T)
+
+    def set_state(self, x0):
+        x0 = _f64(x0).reshape(self.n_chains, self.D)
+        self._ck(self.lib.cb2_set_state(self.h, _cabi.ptr(x0)))
+
+    def get_state(self):
+        n, D = self.n_chains, self.D
+        x = np.empty((n, D)); lp = np.empty(n)
+        w = np.empty(n, np.int64); nr = np.empty(n, np.int64); na = np.empty(n, np.int64)
+        fl = np.empty(n, np.uint32)
+        p = _cabi.ptr
+        self._ck(self.lib.cb2_get_state(self.h, p(x), p(lp), p(w), p(nr), p(na), p(fl)))
+        return dict(x=x, logpost=lp, weight=w, n_rows=nr, n_accepted=na, flags=fl)
+
+    def logpost(self, X):
+        X = _f64(np.atleast_2d(X))
+        n = X.shape[0]
+        NL, ND = self.fm.n_like, self.fm.n_derived
+        lp = np.empty(n); pr = np.empty(n); ll = np.empty((n, NL))
+        der = np.empty((n, max(ND, 1)))
+        p = _cabi.ptr
+        self._ck(self.lib.cb2_logpost(self.h, p(X), n, p(lp), p(pr), p(ll), p(der)))
+        return lp, pr, ll, der[:, :ND]
+
+    def advance(self, n_proposals: int):
+        self._ck(self.lib.cb2_advance(self.h, int(n_proposals)))
+
+    def sync(self):
+        self._ck(self.lib.cb2_sync(self.h))
+
+    def summary(self):
+        out = np.zeros(8, np.int64)
+        self._ck(self.lib.cb2_summary(self.h, _cabi.ptr(out)))
+        keys = ["min_rows", "max_rows", "sum_rows", "n_stuck", "n_rows_full", "n_internal",
+                "sum_accepted", "sum_weight"]
+        return dict(zip(keys, (int(v) for v in out)))
+
+    @property
+    def moments_len(self):
+        return 3 + self.D + 2 * self.D * self.D
+
+    def moments(self, mode=MOMENTS_HALVES, split=4, shift=None, dev_ptr=None, host=True):
+        out = np.empty(self.moments_len) if host else None
+        sh = None if shift is None else _f64(shift)
+        self._ck(self.lib.cb2_moments(self.h, int(mode), int(split), _cabi.ptr(sh),
+                                      C.c_void_p(dev_ptr) if dev_ptr else None,
+                                      _cabi.ptr(out)))
+        return out
+
+    def rows(self, chain: int, first: int = 0, n: int | None = None):
+        W = self.lib.cb2_row_width(self.h)
+        n = self.rows_cap if n is None else int(n)
+        out = np.empty((max(n, 1), W))
+        got = self.lib.cb2_copy_rows(self.h, int(chain), int(first), n, _cabi.ptr(out))
+        if got < 0:
+            raise EngineError(self.lib.cb2_last_error(self.h).decode())
+        return out[:got].copy()
+
+    def debug_basis(self, chain, block, epoch):
+        n = int(self.fm.block_sizes[block])
+        R = np.empty((n, n))
+        self._ck(self.lib.cb2_debug_basis(self.h, int(chain), int(block), int(epoch),
+                                          _cabi.ptr(R)))
+        return R
+
+    def launch_count(self):
+        return int(self.lib.cb2_launch_count(self.h))
+
+    def timer_start(self):
+        self._ck(self.lib.cb2_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        self._ck(self.lib.cb2_timer_stop(self.h, C.byref(ms)))
+        return float(ms.value)
+
+    def last_step_kernel(self):
+        return int(self.lib.cb2_last_step_kernel(self.h))
+
+    def set_kernel_policy(self, policy: int):
+        self._ck(self.lib.cb2_set_kernel_policy(self.h, int(policy)))

@@ -1,0 +1,149 @@
+/*
+ * cobaya_b200.h -- C ABI of the B200 ensemble-MCMC engine (libcobaya_b200.so).
+ *
+ * The reference (CobayaSampler/cobaya v3.6.2) is pure Python: its plugin
+ * boundary for this path is the Python class cobaya.samplers.mcmc.MCMC
+ * (cobaya/samplers/mcmc/mcmc.py:47) built on cobaya.sampler.CovmatSampler
+ * (cobaya/sampler.py:467).  There is no FFI in the reference; this header is
+ * the FFI a maintainer would bind from that class with ctypes (see
+ * INTEGRATION.md).  Each entry point names the reference code it replaces.
+ *
+ * Conventions: extern "C"; plain pointers and sizes; return 0 = ok, negative =
+ * error (message via cb2_last_error); the caller owns every HOST buffer, the
+ * library owns all DEVICE memory behind the opaque handle; one host thread per
+ * handle; all work is enqueued on the handle's CUDA stream, cb2_sync blocks.
+ * All floating-point data is IEEE binary64; matrices are row-major.
+ */
+#ifndef COBAYA_B200_H
+#define COBAYA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cb2_engine cb2_engine;
+
+#define CB2_MAX_BLOCKS 16
+#define CB2_MAX_LIKES 8
+#define CB2_MAX_MODES 32
+
+/* flags returned per chain by cb2_get_flags */
+#define CB2_FLAG_STUCK 1u        /* mcmc.py:717-743 "chain has been stuck" */
+#define CB2_FLAG_ROWS_FULL 2u    /* per-chain sample capacity exhausted */
+
+/* moment modes of cb2_moments */
+#define CB2_MOMENTS_HALVES 0     /* multi-chain rule, mcmc.py:785-793 */
+#define CB2_MOMENTS_SINGLE_SPLIT 1 /* single-chain rule, mcmc.py:795-822 */
+
+int cb2_abi_version(void);
+/* message of the last failing call on this handle (or of cb2_create if h==NULL) */
+const char *cb2_last_error(const cb2_engine *h);
+
+/* One engine = one GPU = `n_chains` lock-step chains with global ids
+ * chain_id0 .. chain_id0+n_chains-1 (Philox subsequence = global id, replacing
+ * Sampler._set_rng's SeedSequence.spawn per MPI rank, cobaya/sampler.py:369-384). */
+int cb2_create(int device, int64_t n_chains, int32_t D, uint64_t seed,
+               uint64_t chain_id0, cb2_engine **out);
+int cb2_destroy(cb2_engine *h);
+
+/* Prior.logps_internal inputs (cobaya/prior.py:514-533,733-763): per parameter
+ * kind (0 uniform, 1 normal), bounds, normal loc/scale, periodic flag
+ * (prior.py:500-513, reduce_periodic :658-676) and the precomputed
+ * -sum(log(upper-lower)) over uniform parameters (prior.py:526-532). */
+int cb2_set_prior(cb2_engine *h, const int32_t *kind, const double *lower,
+                  const double *upper, const double *loc, const double *scale,
+                  const int32_t *periodic, double uniform_logp);
+
+int cb2_clear_likelihoods(cb2_engine *h);
+/* GaussianMixture (cobaya/likelihoods/gaussian_mixture/gaussian_mixture.py:45-163):
+ * idx[dim] = positions of its input_params in the sampled vector; means[m*dim];
+ * linv[m*dim*dim] = inverse_cholesky(cov_k) (functions.py:81-89); logdet[m];
+ * weights[m] normalised; derived!=0 emits the dim*m whitened derived parameters
+ * (gaussian_mixture.py:146-156) into the sample rows. */
+int cb2_add_gaussian_mixture(cb2_engine *h, int32_t dim, const int32_t *idx,
+                             int32_t n_modes, const double *means, const double *linv,
+                             const double *logdet, const double *weights,
+                             int32_t derived);
+/* Built-in external-likelihood stand-in for BASELINE.json configs[3]:
+ * logp = -scale * sum_i [100 (x_{i+1}-x_i^2)^2 + (1-x_i)^2]. */
+int cb2_add_rosenbrock(cb2_engine *h, int32_t dim, const int32_t *idx, double scale);
+
+/* BlockedProposer.__init__ (cobaya/samplers/mcmc/proposal.py:96-201): blocks in
+ * ascending speed given by their sizes, i_of_j (sorted index -> sampler index),
+ * integer oversampling factors; drag!=0 selects get_new_sample_dragging
+ * (mcmc.py:564-668) with slow blocks 0..i_last_slow and drag_interp_steps. */
+int cb2_set_blocking(cb2_engine *h, int32_t n_blocks, const int32_t *block_sizes,
+                     const int32_t *oversampling, const int32_t *i_of_j, int32_t drag,
+                     int32_t i_last_slow_block, int32_t drag_interp_steps);
+
+/* BlockedProposer.set_covariance output (proposal.py:226-260): T[D*D] = S L' in
+ * block-sorted coordinates (lower triangular); transform[b] = T[j_b:, j_b:j_b+n_b].
+ * May be called between cb2_advance calls (covariance learning, mcmc.py:1023). */
+int cb2_set_proposal(cb2_engine *h, const double *T, double proposal_scale);
+
+/* mcmc.yaml options used on the device: temperature (:24), burn_in (:6, absolute
+ * accepted steps), max_tries (:9, absolute), output_thin (mcmc.py:377-389),
+ * rows_cap = stored rows per chain the engine must be able to hold. */
+int cb2_set_options(cb2_engine *h, double temperature, int64_t burn_in,
+                    int64_t max_tries, int32_t output_thin, int64_t rows_cap);
+
+/* Initial points x0[n_chains*D] (MCMC.initialize, mcmc.py:215-222): uploads,
+ * evaluates the posterior on the device, weight=1, resets counters and samples. */
+int cb2_set_state(cb2_engine *h, const double *x0);
+/* current points (OneSamplePoint): any output pointer may be NULL */
+int cb2_get_state(cb2_engine *h, double *x, double *logpost, int64_t *weight,
+                  int64_t *n_rows, int64_t *n_accepted, uint32_t *flags);
+
+/* Model.logposterior (cobaya/model.py:579-678) for n points X[n*D]:
+ * logpost[n], logprior[n], loglikes[n*n_like], derived[n*n_derived] (NULL ok). */
+int cb2_logpost(cb2_engine *h, const double *X, int64_t n, double *logpost,
+                double *logprior, double *loglikes, double *derived);
+
+/* MCMC.run inner loop (mcmc.py:470-472): every chain makes n_proposals more
+ * proposals (get_new_sample_metropolis / _dragging + process_accept_or_reject). */
+int cb2_advance(cb2_engine *h, int64_t n_proposals);
+int cb2_sync(cb2_engine *h);
+
+/* out[0..7] = min rows, max rows, sum rows, #stuck chains, #rows-full chains,
+ * proposals per chain so far, sum accepted, sum of current weights */
+int cb2_summary(cb2_engine *h, int64_t out[8]);
+
+/* Per-GPU sufficient statistics of check_convergence_and_learn_proposal
+ * (mcmc.py:785-822): for every chain (mode HALVES: rows [n/2:], N_c=n; mode
+ * SINGLE_SPLIT with `split`: segments of one chain, mcmc.py:795-813) the weighted
+ * mean m_c, ddof=0 weighted covariance C_c (collection.py:893-981) and acceptance
+ * a_c; summed into out[2D^2+D+3] = { M, sum N_c, sum N_c a_c, sum (m_c-shift)[D],
+ * sum (m_c-shift)(m_c-shift)^T [D*D], sum N_c C_c [D*D] }.  `shift` (host, may be
+ * NULL = 0) must be identical on all ranks.  `dev_out` is a DEVICE pointer (the
+ * buffer NCCL all-reduces); `host_out` a host pointer; either may be NULL. */
+int cb2_moments(cb2_engine *h, int32_t mode, int32_t split, const double *shift,
+                double *dev_out, double *host_out);
+
+/* SampleCollection rows (collection.py:154-159,519-542) of one chain:
+ * out[n*width], width = cb2_row_width. Returns number of rows copied (>=0). */
+int64_t cb2_copy_rows(cb2_engine *h, int64_t chain, int64_t row_begin, int64_t n,
+                      double *out);
+int32_t cb2_row_width(const cb2_engine *h);
+int32_t cb2_n_derived(const cb2_engine *h);
+
+/* random_SO_N (cobaya/functions.py:21-60) for (local chain, block, epoch):
+ * R[n_b*n_b] row-major -- test/diagnostic entry point. */
+int cb2_debug_basis(cb2_engine *h, int64_t chain, int32_t block, uint32_t epoch,
+                    double *R);
+
+/* instrumentation: kernels launched so far; device-side timing of a region on the
+ * engine's stream (CUDA events) */
+int64_t cb2_launch_count(const cb2_engine *h);
+int cb2_timer_start(cb2_engine *h);
+int cb2_timer_stop(cb2_engine *h, float *ms);
+/* which step kernel the last cb2_advance used: 0 = general warp-per-chain,
+ * 1 = DMMA (mma.sync.m8n8k4.f64) register-resident fast path */
+int cb2_last_step_kernel(const cb2_engine *h);
+int cb2_set_kernel_policy(cb2_engine *h, int32_t policy); /* 0 auto, 1 force general */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -375,7 +375,7 @@ def dump_checkpoint():
     model, sampler, x0, rows = run_reference(info, 6000, 9, 2)
     n = len(rows)
     sampler.check_convergence_and_learn_proposal()
-    out = dict(rows=rows, Rminus1=sampler.Rminus1_last,
+    out = dict(rows=rows, x0=x0, Rminus1=sampler.Rminus1_last,
                learned_cov=sampler.proposer.get_covariance(),
                split=sampler.Rminus1_single_split, n=n,
                acceptance=sampler.progress["acceptance_rate"].iloc[-1],

@@ -1,0 +1,188 @@
+"""
+GPU parity tests (run on the B200 box): the CUDA engine, called through the C ABI,
+against (a) the golden chains produced by the unmodified reference and (b) the C oracle
+on the same seeded inputs.  Tolerances: chain rows 1e-9 relative (fp64 reassociation +
+device/host libm differences); integer quantities (weights, row counts) exact.
+"""
+
+import numpy as np
+import pytest
+
+from tests.util import flat_from_golden, load_golden
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+ATOL = 1e-11
+
+
+def _engine(fm, n_chains, seed, chain_id0=0, rows_cap=4096, burn_in=0):
+    from cobaya_b200.engine import Engine
+
+    return Engine(fm, n_chains=n_chains, seed=seed, chain_id0=chain_id0,
+                  rows_cap=rows_cap, burn_in=burn_in)
+
+
+def test_logpost_matches_reference_known_answers(cuda_lib):
+    """cb2_logpost vs Model.logposterior values recorded from the reference (KAT1, KAT5)."""
+    u = load_golden("units")
+    g = load_golden("g1_gauss3d")
+    fm = flat_from_golden(g)
+    eng = _engine(fm, 1, 1)
+    lp, pr, ll, der = eng.logpost(u["kat1_points"])
+    ref = u["kat1_results"]
+    for i in range(len(ref)):
+        if np.isfinite(ref[i, 0]):
+            np.testing.assert_allclose(lp[i], ref[i, 0], rtol=1e-11)
+            np.testing.assert_allclose(pr[i], ref[i, 1], rtol=1e-13)
+            np.testing.assert_allclose(ll[i, 0], ref[i, 2], rtol=1e-11)
+            np.testing.assert_allclose(der[i], ref[i, 3:], rtol=1e-9, atol=1e-12)
+        else:
+            assert lp[i] == -np.inf and pr[i] == -np.inf
+    g2 = load_golden("g2_blocks_mixture")
+    fm2 = flat_from_golden(g2)
+    eng2 = _engine(fm2, 1, 1)
+    lp, pr, ll, der = eng2.logpost(u["kat5_points"])
+    ref = u["kat5_results"]
+    np.testing.assert_allclose(lp, ref[:, 0], rtol=1e-11)
+    np.testing.assert_allclose(pr, ref[:, 1], rtol=1e-12)
+    np.testing.assert_allclose(ll[:, 0], ref[:, 2], rtol=1e-11)
+    np.testing.assert_allclose(der, ref[:, 3:], rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("n", [2, 3, 7, 16, 64])
+def test_random_so_n_matches_reference_rvs(cuda_lib, n):
+    """Device Haar basis vs the reference's numba _rvs on the same normals (golden)."""
+    from cobaya_b200.flatmodel import FlatModel
+
+    u = load_golden("units")
+    D = n + 1  # block 0 of size 1, block 1 of size n (golden used block=1)
+    fm = FlatModel.gaussian(np.zeros(D), np.eye(D) * 0.01, blocks=[[0], list(range(1, D))],
+                            oversampling=[1, 1], proposal_cov=np.eye(D) * 0.01)
+    eng = _engine(fm, 20, seed=1234)
+    R = eng.debug_basis(chain=17, block=1, epoch=5)
+    np.testing.assert_allclose(R, u[f"son_R_{n}"], rtol=0, atol=5e-14)
+    np.testing.assert_allclose(R @ R.T, np.eye(n), atol=1e-13)
+    assert abs(np.linalg.det(R) - 1) < 1e-12
+
+
+CASES = [("g1_gauss3d", 0), ("g1_gauss3d", 7), ("g2_blocks_mixture", 3),
+         ("g3_dragging", 1), ("g4_block1d", 5)]
+
+
+@pytest.mark.parametrize("name,cid", CASES)
+def test_chain_matches_reference_golden(cuda_lib, name, cid):
+    """One chain advanced by the CUDA engine reproduces the rows the unmodified
+    reference produced with the same Philox draws (tests/golden, oracle/make_golden.py)."""
+    g = load_golden(name)
+    fm = flat_from_golden(g)
+    n = int(g["n_proposals"])
+    eng = _engine(fm, 1, seed=int(g["seed"]), chain_id0=cid, burn_in=int(g["burn_in"]))
+    eng.set_state(g[f"x0_{cid}"][None, :])
+    # deliberately uneven launch sizes: windows must be transparent
+    done = 0
+    for k in (1, 2, 5, 17, 100, n):
+        step = min(k, n - done)
+        if step > 0:
+            eng.advance(step)
+            done += step
+    st = eng.get_state()
+    ref = g[f"rows_{cid}"]
+    rows = eng.rows(0)
+    assert st["flags"][0] == 0
+    assert rows.shape == ref.shape
+    np.testing.assert_array_equal(rows[:, 0], ref[:, 0])  # weights are integers
+    np.testing.assert_allclose(rows, ref, rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(st["x"][0], g[f"final_x_{cid}"], rtol=RTOL, atol=ATOL)
+    assert st["weight"][0] == int(g[f"final_weight_{cid}"])
+
+
+def _oracle_rows(fm, seed, ids, x0, n, burn_in):
+    from oracle import oracle as orc
+
+    om = orc.OracleModel(fm)
+    out = []
+    for i, cid in enumerate(ids):
+        ch = orc.OracleChain(om, seed, int(cid), x0[i], burn_in=burn_in)
+        rc, rows = ch.advance(n)
+        out.append((rc, rows, ch.state()))
+    return out
+
+
+@pytest.mark.parametrize("D,n_chains,n", [(8, 37, 300), (64, 16, 200)])
+def test_ensemble_matches_oracle(cuda_lib, D, n_chains, n):
+    """Many chains, global ids offset (as on rank>0), against the C oracle."""
+    from cobaya_b200.flatmodel import FlatModel, synthetic_gaussian_cov
+
+    cov = synthetic_gaussian_cov(D)
+    fm = FlatModel.gaussian(np.zeros(D), cov, proposal_cov=cov)
+    rng = np.random.default_rng(5)
+    x0 = rng.multivariate_normal(np.zeros(D), cov, size=n_chains)
+    id0 = 1000
+    eng = _engine(fm, n_chains, seed=77, chain_id0=id0, rows_cap=n)
+    eng.set_state(x0)
+    eng.advance(n)
+    st = eng.get_state()
+    ref = _oracle_rows(fm, 77, range(id0, id0 + n_chains), x0, n, 0)
+    for c in range(n_chains):
+        rc, rows_ref, s_ref = ref[c]
+        rows = eng.rows(c)
+        assert rows.shape == rows_ref.shape, f"chain {c}"
+        np.testing.assert_array_equal(rows[:, 0], rows_ref[:, 0])
+        np.testing.assert_allclose(rows, rows_ref, rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(st["x"][c], s_ref["x"], rtol=RTOL, atol=ATOL)
+        assert st["weight"][c] == s_ref["weight"]
+        assert st["n_accepted"][c] == s_ref["n_accepted"]
+
+
+def test_moments_match_numpy(cuda_lib):
+    """cb2_moments (multi-chain halves rule) vs SampleCollection.mean/cov arithmetic
+    restated with numpy on the same rows, and R-1 to 1e-4 as BASELINE.json asks."""
+    from cobaya_b200.convergence import rminus1_from_sums
+    from cobaya_b200.flatmodel import FlatModel, synthetic_gaussian_cov
+    from oracle import oracle as orc
+
+    D, C, n = 6, 24, 600
+    cov = synthetic_gaussian_cov(D)
+    fm = FlatModel.gaussian(np.full(D, 0.1), cov, proposal_cov=cov)
+    rng = np.random.default_rng(2)
+    x0 = 0.1 + rng.multivariate_normal(np.zeros(D), cov, size=C)
+    eng = _engine(fm, C, seed=5, rows_cap=n)
+    eng.set_state(x0)
+    eng.advance(n)
+    shift = np.full(D, 0.09)
+    sums = eng.moments(shift=shift)
+    Ns, means, covs, accs = [], [], [], []
+    for c in range(C):
+        rows = eng.rows(c)
+        m, cv, a = orc.chain_window_stats(rows, D, len(rows) // 2)
+        Ns.append(len(rows)); means.append(m); covs.append(cv); accs.append(a)
+    R_ref, W_ref = orc.rminus1_from_chain_stats(Ns, means, covs)
+    res = rminus1_from_sums(sums, D, shift)
+    assert res["M"] == C and res["N"] == sum(Ns)
+    np.testing.assert_allclose(res["W"], W_ref, rtol=1e-10, atol=1e-18)
+    np.testing.assert_allclose(res["Rminus1"], R_ref, rtol=1e-4)
+    np.testing.assert_allclose(res["acceptance"], np.average(accs, weights=Ns), rtol=1e-12)
+    np.testing.assert_allclose(res["mean"], np.mean(means, axis=0), rtol=1e-9, atol=1e-12)
+
+
+def test_single_chain_split_matches_reference_checkpoint(cuda_lib):
+    """Single-chain R-1 (mcmc.py:795-822) and learned covariance vs the values the
+    reference itself computed on its own chain (tests/golden/checkpoint.npz)."""
+    from cobaya_b200.convergence import rminus1_from_sums
+    from cobaya_b200.engine import MOMENTS_SINGLE_SPLIT
+
+    ck = load_golden("checkpoint")
+    g = load_golden("g1_gauss3d")
+    fm = flat_from_golden(g)
+    eng = _engine(fm, 1, seed=9, chain_id0=2, rows_cap=4096)
+    eng.set_state(ck["x0"][None, :])
+    eng.advance(6000)
+    rows = eng.rows(0)
+    assert rows.shape == ck["rows"].shape
+    np.testing.assert_allclose(rows, ck["rows"], rtol=RTOL, atol=ATOL)
+    sums = eng.moments(mode=MOMENTS_SINGLE_SPLIT, split=int(ck["split"]))
+    res = rminus1_from_sums(sums, 3)
+    np.testing.assert_allclose(res["Rminus1"], float(ck["Rminus1"]), rtol=1e-4)
+    np.testing.assert_allclose(res["W"], ck["learned_cov"], rtol=1e-9)
+    np.testing.assert_allclose(res["acceptance"], float(ck["acceptance"]), rtol=1e-12)
