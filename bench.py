@@ -1,0 +1,413 @@
+#!/usr/bin/env python
+"""
+bench.py -- proposals/s of the adaptive-Metropolis hot path on BASELINE.json configs[1]:
+64-D correlated Gaussian, 8192 lock-step chains per B200, proposal-covariance learning on.
+
+    python bench.py --gpus N --steps K --warmup W            (N=1; N>1 under torchrun)
+    python bench.py --impl reference --steps K --warmup W    (reference on host cores)
+
+A "step" is one pass of the hot path: every chain of every GPU makes ``--locksteps``
+proposals (default 16 proposal cycles = 1024 lock-steps), followed by the run loop's own
+bookkeeping (summary read-back, and the convergence-check + covariance-learning
+checkpoint whenever every chain has accumulated ``learn_every`` more rows -- with an NCCL
+all-reduce of the per-GPU moments when N>1).  ``value`` is device-timed (CUDA events on
+the engine's stream) with all inputs resident in HBM; ``e2e`` times the same pass through
+the public host API with pinned-host inputs uploaded and results read back every step.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+D = 64
+CHAINS_PER_GPU = 8192
+WORKLOAD = "64-D correlated Gaussian, 8192 chains/GPU, covmat learning on (BASELINE configs[1])"
+METRIC = "mcmc_proposals_per_sec"
+UNIT = "proposals/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+FP64_NOMINAL_TFLOPS = 37.0  # 148 SM x 64 FP64 FMA/clk x 2 x 1.965 GHz (nominal, HGX B200)
+
+
+def build_problem(seed=1):
+    from cobaya_b200.flatmodel import FlatModel, synthetic_gaussian_cov
+
+    cov = synthetic_gaussian_cov(D)
+    # start from a deliberately imperfect proposal (diagonal of the truth) so that
+    # learning has something to do, as SURVEY.md section 8d suggests
+    prop0 = np.diag(np.diag(cov))
+    fm = FlatModel.gaussian(np.zeros(D), cov, bounds=(-1.0, 1.0), proposal_cov=prop0)
+    return fm, cov
+
+
+def start_points(fm, cov, n, rank, seed=1):
+    rng = np.random.default_rng([seed, rank])
+    return rng.multivariate_normal(np.zeros(D), cov, size=n)  # ref: N(0, Sigma)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop = index, [], threading.Event()
+
+    def run(self):
+        try:
+            self.p = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            for line in self.p.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+                if self._stop.is_set():
+                    break
+        except Exception:
+            pass
+
+    def stop(self):
+        self._stop.set()
+        try:
+            self.p.terminate()
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown",
+                                    "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ CPU legs
+def cpu_oracle_baseline(fm, cov, target_seconds=12.0):
+    """The C oracle (a scalar port of the reference algorithm) on the host cores, on a
+    bounded sample of the same workload."""
+    from oracle import oracle as orc
+
+    cores = os.cpu_count() or 1
+    om = orc.OracleModel(fm)
+    x0 = start_points(fm, cov, 4 * cores, rank=999)
+    chains = [orc.OracleChain(om, 1, 10**6 + c, x0[c]) for c in range(len(x0))]
+    t = time.perf_counter()
+    orc.ensemble_advance(chains, 64, store=False, n_threads=cores)
+    dt = time.perf_counter() - t
+    rate = len(chains) * 64 / dt
+    n = int(max(64, min(20000, target_seconds * rate / len(chains))) // 64 * 64)
+    t = time.perf_counter()
+    orc.ensemble_advance(chains, n, store=False, n_threads=cores)
+    dt = time.perf_counter() - t
+    return {"value": len(chains) * n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{len(chains)} chains x {n} proposals of the same 64-D target "
+                      f"(oracle/mcmc_oracle.c, OpenMP over chains), {dt:.1f} s"}
+
+
+_REF_WORKER = r"""
+import os, sys, time, json
+import numpy as np
+root, n_samples, seed = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+sys.path.insert(0, os.path.join(root, "oracle", "shims"))
+sys.path.insert(0, os.path.join(root, "baseline", "_ref"))
+sys.path.insert(0, root)
+os.environ["COBAYA_NOMPI"] = "1"
+import logging
+logging.disable(logging.CRITICAL)
+from cobaya_b200.flatmodel import synthetic_gaussian_cov
+from cobaya.model import get_model
+from cobaya.sampler import get_sampler
+D = 64
+cov = synthetic_gaussian_cov(D)
+names = [f"x{i}" for i in range(D)]
+info = {"likelihood": {"gaussian_mixture": {"means": [np.zeros(D)], "covs": [cov],
+                                            "input_params": names, "derived": False}},
+        "params": {n: {"prior": {"min": -1, "max": 1},
+                       "ref": {"dist": "norm", "loc": 0, "scale": 0.001}} for n in names},
+        "sampler": {"mcmc": {"covmat": np.diag(np.diag(cov)), "covmat_params": names,
+                             "measure_speeds": False, "learn_proposal": True, "burn_in": 0,
+                             "seed": seed, "max_samples": n_samples, "Rminus1_stop": 1e-9,
+                             "output_every": "1000s"}}}
+out = []
+for rep in range(int(sys.argv[4])):
+    model = get_model(info)
+    sampler = get_sampler(info["sampler"], model)
+    t = time.perf_counter()
+    sampler.run()
+    dt = time.perf_counter() - t
+    out.append((int(sampler.n_steps_raw), dt))
+print(json.dumps(out))
+"""
+
+
+def reference_available():
+    return os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "cobaya"))
+
+
+def run_reference_arm(args):
+    """bench.py --impl reference: the UNMODIFIED reference (cobaya 3.6.2 installed in
+    baseline/_ref) on the host cores: one independent single-chain process per core
+    (the reference's MPI mode is one chain per rank; mpi4py is not installed), each step a
+    bounded run of ``max_samples`` accepted rows.  Falls back to the oracle port."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    fm, cov = build_problem()
+    cores = os.cpu_count() or 1
+    steps, warm = args.steps, args.warmup
+    peak, _ = peaks()
+    base = {"metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "impl": "reference", "gpu_launches": 0,
+            "config": {"workload": WORKLOAD, "D": D}}
+    if reference_available():
+        n_samples = 250  # accepted rows per chain per step (about 0.15 s of run())
+        procs = []
+        t0 = time.perf_counter()
+        for c in range(cores):
+            procs.append(subprocess.Popen(
+                [sys.executable, "-c", _REF_WORKER, ROOT, str(n_samples), str(100 + c),
+                 str(steps + warm)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                text=True))
+        res = []
+        for p in procs:
+            o, _ = p.communicate()
+            try:
+                res.append(json.loads(o.strip().splitlines()[-1]))
+            except Exception:
+                pass
+        wall = time.perf_counter() - t0
+        if res:
+            res = np.array(res, dtype=float)[:, warm:, :]  # [proc, step, (n, dt)]
+            n_tot = res[:, :, 0].sum()
+            t_run = res[:, :, 1].sum(axis=1).max()       # slowest process' run() time
+            value = n_tot / t_run
+            base.update(value=value, ms_per_step=1e3 * t_run / steps,
+                        cpu_baseline={"value": value, "unit": UNIT, "cores": len(res),
+                                      "kind": "reference",
+                                      "sample": f"{len(res)} independent cobaya 3.6.2 "
+                                                f"processes (1 chain each, numba on), "
+                                                f"{steps} runs of max_samples={n_samples}; "
+                                                f"wall {wall:.0f}s"},
+                        e2e={"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
+                             "d2h_bytes_per_step": 0})
+            print(json.dumps(base))
+            return
+    cb = cpu_oracle_baseline(fm, cov, target_seconds=max(5.0, 2.0 * steps))
+    base.update(value=cb["value"], ms_per_step=None, cpu_baseline=cb,
+                e2e={"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
+                     "d2h_bytes_per_step": 0})
+    print(json.dumps(base))
+
+
+# ------------------------------------------------------------------ GPU arm
+def run_gpu_arm(args):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch N>1 with: python -m torch.distributed.run "
+                             "--nproc-per-node N bench.py --gpus N ...")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as tdist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        tdist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from cobaya_b200.mcmc import EnsembleMCMC, TorchDist
+
+    if world > 1:
+        dist = TorchDist()
+    fm, cov = build_problem()
+    C = args.chains
+    x0 = start_points(fm, cov, C, rank)
+    locksteps = args.locksteps
+    K, W = args.steps, args.warmup
+    total_steps = (K + W) * 2 + 4
+    # stored rows per chain: acceptance stays below ~0.35
+    rows_cap = int(0.45 * locksteps * (K + W + 2)) + 4096
+    opts = {"seed": 1, "chains_per_gpu": C, "device": local, "rows_per_chain": rows_cap,
+            "Rminus1_stop": 0.0, "learn_proposal_Rminus1_max": 1e9, "burn_in": 0}
+
+    def barrier():
+        if world > 1:
+            tdist.barrier()
+        torch.cuda.synchronize()
+
+    smp = EnsembleMCMC(fm, x0, opts, dist=dist)
+    eng = smp.engine
+    n_ckpt = 0
+
+    def one_step():
+        nonlocal n_ckpt
+        eng.advance(locksteps)
+        smp.n_steps_raw += locksteps
+        g = smp._global_summary()
+        smp._check_health(g)
+        if smp.check_ready(g):
+            smp.check_convergence_and_learn_proposal()
+            smp.i_learn += 1
+            n_ckpt += 1
+
+    for _ in range(W):
+        one_step()
+    barrier()
+    clocks = ClockSampler(local) if rank == 0 else None
+    if clocks:
+        clocks.start()
+    eng.set_profiling(True)
+    eng.kernel_times(reset=True)
+    l0 = eng.launch_count()
+    rows0 = eng.summary()["sum_rows"]
+    ck0 = n_ckpt
+    eng.timer_start()
+    t_wall = time.perf_counter()
+    for _ in range(K):
+        one_step()
+    ms_dev = eng.timer_stop()
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    kt = eng.kernel_times(reset=True)
+    eng.set_profiling(False)
+    launches = eng.launch_count() - l0
+    rows1 = eng.summary()["sum_rows"]
+    clk = clocks.stop() if clocks else None
+    # max over ranks of the device time
+    t = torch.tensor([ms_dev], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    proposals = world * C * locksteps * K
+    value = proposals / (ms_total * 1e-3)
+
+    # ---- e2e: same pass through the host API with pinned-host inputs + read-back
+    pin = torch.from_numpy(np.ascontiguousarray(x0)).pin_memory()
+    x0_pinned = pin.numpy()
+    Ke = max(2, min(K, 5))
+    barrier()
+    te = time.perf_counter()
+    for _ in range(Ke):
+        eng.set_state(x0_pinned)                         # H2D: start points
+        eng.advance(locksteps)
+        sums = smp._moments(0, 0)                        # moments (+ all-reduce) -> host
+        st = eng.get_state()                             # D2H: current points + counters
+    barrier()
+    te = time.perf_counter() - te
+    tt = torch.tensor([te], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tdist.all_reduce(tt, op=tdist.ReduceOp.MAX)
+    e2e_value = world * C * locksteps * Ke / float(tt.item())
+    h2d = x0_pinned.nbytes + D * 8
+    d2h = (sums.nbytes + st["x"].nbytes + st["logpost"].nbytes + st["weight"].nbytes
+           + st["n_rows"].nbytes + st["n_accepted"].nbytes + st["flags"].nbytes + 64)
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel (CUDA events bracketing every launch of the
+    # class, on the engine's stream, inside the timed region)
+    peak, peak_src = peaks()
+    dom = max(("step", "basis"), key=lambda k: kt[k]["ms"])
+    acc_rate = (rows1 - rows0) / (C * locksteps * K)     # stored-row rate a
+    bytes_per_prop = 16 * D + 8 * acc_rate * (D + 6)
+    hot_ms = kt["step"]["ms"] + kt["basis"]["ms"]
+    n_l = max(kt[dom]["launches"], 1)
+    props_per_launch = C * locksteps * K / max(kt["step"]["launches"], 1)
+    # the step and basis kernels together implement one proposal; the roofline is quoted
+    # for the pair (achieved = algorithmic bytes / their summed device time) and the
+    # dominant one is named
+    achieved = bytes_per_prop * C * locksteps * K / (hot_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    flops = 4 * D * D * C * locksteps * K / (hot_ms * 1e-3) / 1e12
+    cb = cpu_oracle_baseline(fm, cov) if not args.no_cpu_baseline else None
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "D": D, "chains_per_gpu": C,
+                   "locksteps_per_step": locksteps, "checkpoints_in_timed_region": n_ckpt - ck0,
+                   "l2": "working set per step (268 MB of Haar bases + sample rows) exceeds "
+                         "the 126 MB L2; no explicit flush",
+                   "step_kernel": "dmma" if eng.last_step_kernel() == 1 else "general",
+                   "parallelism": f"chains sharded over {world} GPU(s), no data-path "
+                                  "collective; NCCL all-reduce of moments per checkpoint"},
+        "clocks": clk, "gpu_launches": int(launches),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h), "steps": Ke,
+                "what": "set_state(pinned host) + advance + moments->host + get_state"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic,
+                     "peak_source": peak_src, "dominant_kernel": dom,
+                     "algorithmic_bytes_per_proposal": bytes_per_prop,
+                     "stored_row_rate": acc_rate,
+                     "avg_launch_ms": {k: kt[k]["ms"] / max(kt[k]["launches"], 1)
+                                       for k in kt},
+                     "share_of_step": {k: kt[k]["ms"] / ms_dev for k in kt},
+                     "proposals_per_step_launch": props_per_launch, "launches": n_l,
+                     "fp64": {"tflops": flops, "nominal_peak_tflops": FP64_NOMINAL_TFLOPS,
+                              "frac": flops / FP64_NOMINAL_TFLOPS,
+                              "flops_per_proposal": 4 * D * D,
+                              "note": "binding roof above D~23 (SURVEY.md 8d)"}},
+        "cpu_baseline": cb,
+        "wall_s_timed_region": t_wall,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU)
+    ap.add_argument("--locksteps", type=int, default=1024)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

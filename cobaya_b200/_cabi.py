@@ -23,7 +23,7 @@ EXPORTS = [
     "cb2_get_state", "cb2_logpost", "cb2_advance", "cb2_sync", "cb2_summary",
     "cb2_moments", "cb2_copy_rows", "cb2_row_width", "cb2_n_derived", "cb2_debug_basis",
     "cb2_launch_count", "cb2_timer_start", "cb2_timer_stop", "cb2_last_step_kernel",
-    "cb2_set_kernel_policy",
+    "cb2_set_kernel_policy", "cb2_set_profiling", "cb2_kernel_times",
 ]
 
 
@@ -85,6 +85,8 @@ def load():
     L.cb2_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
     L.cb2_last_step_kernel.argtypes = [vp]
     L.cb2_set_kernel_policy.argtypes = [vp, i32]
+    L.cb2_set_profiling.argtypes = [vp, i32]
+    L.cb2_kernel_times.argtypes = [vp, vp, vp, i32]
     for name in EXPORTS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("cb2_abi_version",):

@@ -96,7 +96,31 @@ struct cb2_engine {
     DevBuf<double> d_tmp;
     int64_t launches = 0;
     int last_kernel = 0, policy = 0;
+    // ---- per-kernel-class device timing (CUDA events on the launching stream)
+    struct ProfRec { cudaEvent_t a, b; int kind; };
+    bool profiling = false;
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> ev_pool;
+    double prof_ms[4] = {0, 0, 0, 0};
+    int64_t prof_n[4] = {0, 0, 0, 0};
+    cudaEvent_t take_event() {
+        if (!ev_pool.empty()) { cudaEvent_t e = ev_pool.back(); ev_pool.pop_back(); return e; }
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        return e;
+    }
+    void prof_begin(int kind) {
+        if (!profiling) return;
+        ProfRec r; r.a = take_event(); r.b = take_event(); r.kind = kind;
+        cudaEventRecord(r.a, stream);
+        prof.push_back(r);
+    }
+    void prof_end() {
+        if (!profiling || prof.empty()) return;
+        cudaEventRecord(prof.back().b, stream);
+    }
 };
+enum { PROF_TAPE = 0, PROF_BASIS = 1, PROF_STEP = 2, PROF_MOMENTS = 3 };
 
 #define FAIL(h, code, ...)                                 \
     do {                                                   \
@@ -651,8 +675,10 @@ static int launch_tape(cb2_engine *h, int which, const std::vector<uint8_t> &ms,
     CK(h, d_tape.ensure((size_t)C * len));
     CK(h, h->d_perm_scratch.ensure((size_t)C * ms.size()));
     int bs = 128, grid = (int)((C + bs - 1) / bs);
+    h->prof_begin(PROF_TAPE);
     k_cycler_tape<<<grid, bs, 0, h->stream>>>(h->M, which, d_ms.p, (int)ms.size(), i0, per_chain,
                                              stride, len, C, d_tape.p, h->d_perm_scratch.p);
+    h->prof_end();
     h->launches++;
     CK(h, cudaGetLastError());
     return 0;
@@ -660,7 +686,14 @@ static int launch_tape(cb2_engine *h, int which, const std::vector<uint8_t> &ms,
 
 // generate cnt epochs of the Haar basis of block b for every chain, starting at each
 // chain's current epoch (vis[b]/n_b)
+static int launch_basis_impl(cb2_engine *h, int b, int cnt);
 static int launch_basis(cb2_engine *h, int b, int cnt) {
+    h->prof_begin(PROF_BASIS);
+    int rc = launch_basis_impl(h, b, cnt);
+    h->prof_end();
+    return rc;
+}
+static int launch_basis_impl(cb2_engine *h, int b, int cnt) {
     const int n = h->bsize[b];
     const int64_t C = h->n_chains;
     const size_t tasks = (size_t)C * cnt;
@@ -787,6 +820,7 @@ extern "C" int cb2_advance(cb2_engine *h, int64_t n_proposals) {
                 W.cnt[b] = cnt;
             }
         }
+        h->prof_begin(PROF_STEP);
         if (fast_ok) {
             if ((rc = launch_step_fast(h->stream, h->M, h->S, W, h->d_fastpack.p, C,
                                        (uint64_t)h->steps_done, w, h->sm_count))) {
@@ -801,6 +835,7 @@ extern "C" int cb2_advance(cb2_engine *h, int64_t n_proposals) {
                                                                    (uint64_t)h->steps_done, w);
             h->last_kernel = 0;
         }
+        h->prof_end();
         h->launches++;
         CK(h, cudaGetLastError());
         h->steps_done += w;
@@ -885,6 +920,7 @@ extern "C" int cb2_moments(cb2_engine *h, int32_t mode, int32_t split, const dou
     } else {
         FAIL(h, -1, "unknown moments mode %d", mode);
     }
+    h->prof_begin(PROF_MOMENTS);
     const int64_t n_mean_tasks = n_tasks + (mode == CB2_MOMENTS_SINGLE_SPLIT ? 1 : 0);
     CK(h, h->d_means.ensure((size_t)n_mean_tasks * D));
     CK(h, h->d_sw.ensure(n_mean_tasks));
@@ -908,6 +944,7 @@ extern "C" int cb2_moments(cb2_engine *h, int32_t mode, int32_t split, const dou
     CK(h, cudaGetLastError());
     double *out = dev_out ? dev_out : h->d_mom_out.p;
     k_reduce_partials<<<(len + 255) / 256, 256, 0, h->stream>>>(h->d_partials.p, grid, len, out);
+    h->prof_end();
     h->launches++;
     CK(h, cudaGetLastError());
     if (mode == CB2_MOMENTS_SINGLE_SPLIT) {
@@ -1013,6 +1050,34 @@ extern "C" int cb2_timer_stop(cb2_engine *h, float *ms) {
 }
 
 extern "C" int cb2_last_step_kernel(const cb2_engine *h) { return h ? h->last_kernel : -1; }
+
+extern "C" int cb2_set_profiling(cb2_engine *h, int32_t on) {
+    if (!h) return -1;
+    h->profiling = on != 0;
+    return 0;
+}
+
+extern "C" int cb2_kernel_times(cb2_engine *h, double ms[4], int64_t n[4], int32_t reset) {
+    if (!h) return -1;
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaStreamSynchronize(h->stream));
+    for (auto &r : h->prof) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
+            h->prof_ms[r.kind] += t;
+            h->prof_n[r.kind] += 1;
+        }
+        h->ev_pool.push_back(r.a);
+        h->ev_pool.push_back(r.b);
+    }
+    h->prof.clear();
+    for (int k = 0; k < 4; ++k) {
+        ms[k] = h->prof_ms[k];
+        n[k] = h->prof_n[k];
+        if (reset) { h->prof_ms[k] = 0; h->prof_n[k] = 0; }
+    }
+    return 0;
+}
 
 extern "C" int cb2_set_kernel_policy(cb2_engine *h, int32_t policy) {
     if (!h) return -1;

@@ -185,3 +185,13 @@ class Engine:
 
     def set_kernel_policy(self, policy: int):
         self._ck(self.lib.cb2_set_kernel_policy(self.h, int(policy)))
+
+    def set_profiling(self, on: bool):
+        self._ck(self.lib.cb2_set_profiling(self.h, int(bool(on))))
+
+    def kernel_times(self, reset: bool = True):
+        """Per-kernel-class device time (ms) and launch counts: tape, basis, step, moments."""
+        ms = np.zeros(4); n = np.zeros(4, np.int64)
+        self._ck(self.lib.cb2_kernel_times(self.h, _cabi.ptr(ms), _cabi.ptr(n), int(reset)))
+        names = ["tape", "basis", "step", "moments"]
+        return {k: dict(ms=float(ms[i]), launches=int(n[i])) for i, k in enumerate(names)}

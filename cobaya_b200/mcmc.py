@@ -1,0 +1,384 @@
+"""
+Host-side driver of the ensemble sampler: the part of ``cobaya.samplers.mcmc.MCMC``
+that is NOT per-proposal work -- option handling (mcmc.yaml), the outer ``run`` loop
+(mcmc.py:451-528), the checkpoint rule (``check_ready`` :752-771), convergence +
+covariance learning (``check_convergence_and_learn_proposal`` :773-1032) and products
+(:1092-1184) -- restated for M = n_gpus x chains_per_gpu lock-step chains.
+
+Per-proposal work (propose -> logposterior -> accept -> store) happens only in the CUDA
+engine (``cobaya_b200.engine.Engine`` -> libcobaya_b200.so).  There is no CPU path.
+
+Ensemble semantics that have no single-chain counterpart in the reference (SURVEY.md
+section 7 "hard parts"), chosen to follow the reference's MPI behaviour (one chain per
+rank) as closely as lock-step allows:
+
+* checkpoint: taken at the end of the launch in which EVERY chain has at least
+  ``i_learn * learn_every`` stored rows (the reference waits until all ranks are ready,
+  mcmc.py:500-506, while ready ranks keep sampling); each chain contributes its own
+  second half ``[n_c//2:]`` and ``N_c = n_c`` (mcmc.py:787-793);
+* ``max_samples``: the run stops when every chain holds at least that many rows;
+* a stuck chain (mcmc.py:717-743) is detected at the end of the launch it occurs in.
+"""
+
+from __future__ import annotations
+
+import datetime
+import logging
+import re
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from .convergence import rminus1_from_sums
+from .engine import (FLAG_INTERNAL, FLAG_ROWS_FULL, FLAG_STUCK, MOMENTS_HALVES,
+                     MOMENTS_SINGLE_SPLIT, Engine)
+from .flatmodel import FlatModel
+
+log = logging.getLogger("mcmc")
+
+
+class SamplerError(RuntimeError):
+    """Mirror of cobaya.log.LoggedError for the standalone driver."""
+
+
+# defaults of cobaya/samplers/mcmc/mcmc.yaml (every key, verbatim) + the engine's keys
+MCMC_DEFAULTS = {
+    "burn_in": 0, "max_tries": "40d", "covmat": None, "covmat_params": None,
+    "proposal_scale": 2.4, "output_every": "60s", "learn_every": "40d",
+    "temperature": 1, "learn_proposal": True, "learn_proposal_Rminus1_max": 2.0,
+    "learn_proposal_Rminus1_max_early": 30.0, "learn_proposal_Rminus1_min": 0.0,
+    "max_samples": np.inf, "Rminus1_stop": 0.01, "Rminus1_cl_stop": 0.2,
+    "Rminus1_cl_level": 0.95, "Rminus1_single_split": 4, "measure_speeds": True,
+    "oversample_power": 0.4, "oversample_thin": True, "drag": False, "blocking": None,
+    "callback_function": None, "callback_every": None, "seed": None,
+    "check_every": None, "oversample": None, "drag_limits": None,
+}
+ENGINE_DEFAULTS = {
+    "chains_per_gpu": 8192,       # lock-step chains on each GPU
+    "device": None,               # CUDA device index (default: LOCAL_RANK or 0)
+    "rows_per_chain": None,       # sample capacity per chain (default: from max_samples)
+    "launch_cycles": None,        # proposal cycles per kernel launch group
+}
+
+
+class NumberWithUnits:
+    """``"40d"`` -> 40 x scale (mirrors cobaya/tools.py:454-518 for the 'd' and 's' units)."""
+
+    def __init__(self, n_with_unit, unit: str, dtype=int, scale=None):
+        self.unit = None
+        self.dtype = dtype
+        if isinstance(n_with_unit, NumberWithUnits):
+            n_with_unit = n_with_unit.original
+        self.original = n_with_unit
+        if isinstance(n_with_unit, str):
+            m = re.fullmatch(r"\s*([0-9.eE+\-]*)\s*(" + unit + r")?\s*", n_with_unit)
+            if not m:
+                raise SamplerError(f"Could not understand {n_with_unit!r} (unit {unit!r}).")
+            num = m.group(1) or "1"
+            self.unit_value = dtype(float(num))
+            self.unit = m.group(2)
+        else:
+            self.unit_value = n_with_unit
+        self.value = self.unit_value
+        if scale is not None:
+            self.set_scale(scale)
+
+    def set_scale(self, scale):
+        if self.unit:
+            self.scale = scale
+            self.value = self.dtype(self.unit_value * scale)
+
+    def __bool__(self):
+        return bool(self.unit_value)
+
+
+@dataclass
+class Checkpoint:
+    N: int
+    timestamp: str
+    acceptance_rate: float
+    Rminus1: float | None
+    Rminus1_cl: float | None = None
+    learned: bool = False
+
+
+class _NoDist:
+    """Single-process stand-in for the torch.distributed calls used below."""
+
+    rank, size = 0, 1
+
+    def all_reduce_sum(self, arr):
+        return arr
+
+    def all_reduce_min_max_sum(self, mins, maxs, sums):
+        return mins, maxs, sums
+
+
+class TorchDist:
+    """One process per GPU (torchrun): NCCL all-reduce of the per-GPU sufficient statistics
+    (replaces mpi.array_gather + share, mcmc.py:791-793,914,1005,1021).  With the gloo
+    backend the same code runs on CPU tensors (used by the world_size-2 CPU tests)."""
+
+    def __init__(self, group=None, device=None):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist, self.group = torch, dist, group
+        self.rank, self.size = dist.get_rank(group), dist.get_world_size(group)
+        self.backend = dist.get_backend(group)
+        self.device = device if device is not None else (
+            torch.device("cuda", torch.cuda.current_device()) if self.backend == "nccl"
+            else torch.device("cpu"))
+
+    def buffer(self, n):
+        return self.torch.zeros(n, dtype=self.torch.float64, device=self.device)
+
+    def all_reduce_sum(self, arr):
+        t = self.torch.as_tensor(np.asarray(arr, dtype=np.float64)).to(self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return t.cpu().numpy()
+
+    def all_reduce_tensor_(self, t):
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def all_reduce_min_max_sum(self, mins, maxs, sums):
+        tt = self.torch
+        a = tt.as_tensor(np.asarray(mins, dtype=np.int64)).to(self.device)
+        b = tt.as_tensor(np.asarray(maxs, dtype=np.int64)).to(self.device)
+        c = tt.as_tensor(np.asarray(sums, dtype=np.int64)).to(self.device)
+        self.dist.all_reduce(a, op=self.dist.ReduceOp.MIN, group=self.group)
+        self.dist.all_reduce(b, op=self.dist.ReduceOp.MAX, group=self.group)
+        self.dist.all_reduce(c, op=self.dist.ReduceOp.SUM, group=self.group)
+        return a.cpu().numpy(), b.cpu().numpy(), c.cpu().numpy()
+
+
+def decide_learning(opts, Rminus1, converged):
+    """Learning gate of mcmc.py:1009-1030. Returns (learn?, message)."""
+    if not opts["learn_proposal"] or converged:
+        return False, ""
+    if Rminus1 > opts["learn_proposal_Rminus1_max"]:
+        return False, ("Convergence less than requested for updates: "
+                       "waiting until the next convergence check.")
+    if Rminus1 < opts["learn_proposal_Rminus1_min"]:
+        return False, ("Convergence better then better than `learn_proposal_Rminus1_min`"
+                       f"={opts['learn_proposal_Rminus1_min']}: covmat will not be updated.")
+    return True, " - Updated covariance matrix of proposal pdf."
+
+
+class EnsembleMCMC:
+    """M = world_size x chains_per_gpu lock-step chains of the adaptive Metropolis sampler."""
+
+    def __init__(self, fm: FlatModel, x0: np.ndarray, options: dict | None = None,
+                 dist=None, engine: Engine | None = None, covmat_incomplete: bool = False):
+        opts = dict(MCMC_DEFAULTS)
+        opts.update(ENGINE_DEFAULTS)
+        unknown = set(options or {}) - set(opts)
+        if unknown:
+            raise SamplerError(f"Unknown mcmc option(s): {sorted(unknown)}")  # input.py:403
+        opts.update(options or {})
+        self.opts = opts
+        self.fm = fm
+        self.dist = dist or _NoDist()
+        x0 = np.ascontiguousarray(x0, dtype=np.float64).reshape(-1, fm.D)
+        self.n_chains_local = x0.shape[0]
+        self.n_chains = self.n_chains_local * self.dist.size
+        if opts["temperature"] is None:
+            opts["temperature"] = 1
+        if opts["temperature"] < 1:
+            log.warning("Sampling temperatures <1 can lead to innacurate inference.")
+        fm.temperature = float(opts["temperature"])
+        fm.proposal_scale = float(opts["proposal_scale"])
+        self.temperature = fm.temperature
+        # quantities in units of the cycle length (mcmc.py:122-125,409-410)
+        self.cycle_length = fm.cycle_length
+        self.output_thin = int(fm.output_thin)
+        scale = self.cycle_length // self.output_thin
+        if opts["callback_every"] is None:
+            opts["callback_every"] = opts["learn_every"]
+        self.max_tries = NumberWithUnits(opts["max_tries"], "d", scale=scale,
+                                         dtype=float)
+        self.learn_every = NumberWithUnits(opts["learn_every"], "d", scale=scale)
+        self.callback_every = NumberWithUnits(opts["callback_every"], "d", scale=scale)
+        self.burn_in = NumberWithUnits(opts["burn_in"], "d", scale=scale)
+        mt = self.max_tries.value
+        fm.max_tries = int(mt) if np.isfinite(mt) else 2**62
+        self.max_samples = opts["max_samples"]
+        if covmat_incomplete and opts["learn_proposal"]:  # mcmc.py:419-429
+            opts["learn_proposal_Rminus1_max"] = opts["learn_proposal_Rminus1_max_early"]
+        # sample capacity per chain
+        rows = opts["rows_per_chain"]
+        if rows is None:
+            rows = (int(self.max_samples) + 2 * self.learn_every.value
+                    if np.isfinite(self.max_samples) else 64 * self.learn_every.value)
+        self.rows_per_chain = int(rows)
+        seed = opts["seed"]
+        self.seed = int(seed) if seed is not None else int(
+            np.random.SeedSequence().generate_state(2, np.uint32).view(np.uint64)[0] >> 1)
+        device = opts["device"]
+        if device is None:
+            import os
+
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+        self.engine = engine or Engine(
+            fm, n_chains=self.n_chains_local, seed=self.seed, device=int(device),
+            chain_id0=self.dist.rank * self.n_chains_local, rows_cap=self.rows_per_chain,
+            burn_in=int(self.burn_in.value))
+        self.engine.set_state(x0)
+        self.converged = False
+        self.Rminus1_last = np.inf
+        self.i_learn = 1
+        self.n_steps_raw = 0
+        self.progress: list[Checkpoint] = []
+        lc = opts["launch_cycles"]
+        if lc is None:
+            lc = max(1, (self.learn_every.value // 2) // max(self.cycle_length, 1))
+        self.launch_steps = int(lc) * self.cycle_length
+        self._shift = np.asarray(self.dist.all_reduce_sum(x0.sum(axis=0))) / self.n_chains
+        self._mom_buf = None
+        self.last_summary = None
+
+    # ------------------------------------------------------------------ helpers
+    def _global_summary(self):
+        s = self.engine.summary()
+        mins, maxs, sums = self.dist.all_reduce_min_max_sum(
+            [s["min_rows"]], [s["max_rows"]],
+            [s["sum_rows"], s["n_stuck"], s["n_rows_full"], s["n_internal"],
+             s["sum_accepted"], s["sum_weight"]])
+        g = dict(min_rows=int(mins[0]), max_rows=int(maxs[0]), sum_rows=int(sums[0]),
+                 n_stuck=int(sums[1]), n_rows_full=int(sums[2]), n_internal=int(sums[3]),
+                 sum_accepted=int(sums[4]), sum_weight=int(sums[5]))
+        self.last_summary = g
+        return g
+
+    def n(self):
+        """Stored rows of the shortest chain (the ensemble analogue of MCMC.n())."""
+        return (self.last_summary or self._global_summary())["min_rows"]
+
+    def _check_health(self, g):
+        if g["n_internal"]:
+            raise SamplerError("internal engine error (basis/tape window violated)")
+        if g["n_stuck"]:  # mcmc.py:720-743
+            raise SamplerError(
+                "The chain has been stuck for %d attempts, stopping sampling "
+                "(%d of %d chains). Make sure the reference point is sensible and initial "
+                "covmat." % (int(self.max_tries.value), g["n_stuck"], self.n_chains))
+        if g["n_rows_full"]:
+            raise SamplerError(
+                f"{g['n_rows_full']} chains filled their sample storage "
+                f"(rows_per_chain={self.rows_per_chain}); increase rows_per_chain.")
+
+    # ------------------------------------------------------------------ run loop
+    def run(self, callback=None):
+        """MCMC.run (mcmc.py:451-528) for the ensemble."""
+        log.info("Sampling! (%d chains on %d GPU(s))", self.n_chains, self.dist.size)
+        g = self._global_summary()
+        while g["min_rows"] < self.max_samples and not self.converged:
+            self.engine.advance(self.launch_steps)
+            self.n_steps_raw += self.launch_steps
+            g = self._global_summary()
+            self._check_health(g)
+            if callback is not None:
+                callback(self)
+            if self.check_ready(g):
+                self.check_convergence_and_learn_proposal()
+                self.i_learn += 1
+        if g["min_rows"] >= self.max_samples:
+            log.info("Reached maximum number of accepted steps allowed (%s). Stopping.",
+                     self.max_samples)
+        log.info("Sampling complete after %d accepted steps.", g["sum_rows"])
+        return self
+
+    def check_ready(self, g=None):
+        """mcmc.py:752-771 with the ensemble rule: all chains reached the next multiple."""
+        g = g or self._global_summary()
+        return g["min_rows"] >= self.i_learn * self.learn_every.value and g["min_rows"] > 0
+
+    def _moments(self, mode, split):
+        eng, d = self.engine, self.dist
+        if isinstance(d, TorchDist) and d.backend == "nccl":
+            if self._mom_buf is None:
+                self._mom_buf = d.buffer(eng.moments_len)
+            eng.moments(mode=mode, split=split, shift=self._shift,
+                        dev_ptr=self._mom_buf.data_ptr(), host=False)
+            eng.sync()
+            d.all_reduce_tensor_(self._mom_buf)      # NCCL over NVLink
+            return self._mom_buf.cpu().numpy()
+        local = eng.moments(mode=mode, split=split, shift=self._shift)
+        return np.asarray(d.all_reduce_sum(local))
+
+    def check_convergence_and_learn_proposal(self):
+        """mcmc.py:773-1032 on all-reduced sums; identical result on every rank."""
+        o = self.opts
+        if self.n_chains > 1:
+            sums = self._moments(MOMENTS_HALVES, 0)
+        else:
+            try:
+                sums = self._moments(MOMENTS_SINGLE_SPLIT, int(o["Rminus1_single_split"]))
+            except Exception as e:  # mcmc.py:816-821
+                log.info("Not enough points in chain to check convergence. (%s)", e)
+                return
+        res = rminus1_from_sums(sums, self.fm.D, self._shift)
+        cp = Checkpoint(N=res["N"], timestamp=datetime.datetime.now().isoformat(),
+                        acceptance_rate=float(res["acceptance"]), Rminus1=res["Rminus1"])
+        self.progress.append(cp)
+        log.info(" - Acceptance rate: %.3f", res["acceptance"])
+        if not res["success"]:
+            log.warning("Negative covariance eigenvectors or failed eigenvalues. "
+                        "Skipping learning a new covmat for now.")  # mcmc.py:872-887
+            return
+        Rminus1 = res["Rminus1"]
+        log.info(" - Convergence of means: R-1 = %f after %d accepted steps", Rminus1,
+                 res["N"])
+        converged_means = max(Rminus1, self.Rminus1_last) < o["Rminus1_stop"]  # :908
+        if converged_means:
+            # The R-1 of the confidence-interval bounds (mcmc.py:918-1002) needs per-chain
+            # weighted quantiles (GetDist in the reference); not evaluated by this engine
+            # yet: convergence is declared on the means.
+            log.info("The run has converged (criterion: R-1 of means, twice in a row).")
+            self.converged = True
+        self.Rminus1_last = Rminus1
+        self._shift = np.asarray(res["mean"], dtype=np.float64)
+        learn, msg = decide_learning(o, Rminus1, self.converged)
+        if msg:
+            log.info(msg)
+        if learn:
+            try:
+                self.engine.set_covariance(res["W"])  # is already tempered (mcmc.py:1023)
+                cp.learned = True
+            except Exception as e:
+                log.debug("Updating covariance matrix failed unexpectedly (%s); "
+                          "waiting until next covmat learning attempt.", e)
+
+    # ------------------------------------------------------------------ products
+    def chain_rows(self, chain: int, skip: float = 0):
+        """Rows (SampleCollection layout, collection.py:154-159) of one local chain."""
+        rows = self.engine.rows(chain)
+        k = int(skip * len(rows)) if 0 < skip < 1 else int(skip)
+        return rows[k:]
+
+    def samples(self, chains=None, skip_samples: float = 0.0):
+        """Concatenated rows of the selected local chains (default: all), each with its
+        first ``skip_samples`` fraction/number of rows removed (mcmc.py:1127-1143)."""
+        chains = range(self.n_chains_local) if chains is None else chains
+        return np.concatenate([self.chain_rows(c, skip_samples) for c in chains])
+
+    def products(self, skip_samples: float = 0.0, chains=None):
+        import pandas as pd
+
+        data = self.samples(chains, skip_samples)
+        return {
+            "sample": pd.DataFrame(data, columns=self.fm.columns()),
+            "progress": pd.DataFrame(
+                [dict(N=c.N, timestamp=c.timestamp, acceptance_rate=c.acceptance_rate,
+                      Rminus1=c.Rminus1, Rminus1_cl=c.Rminus1_cl) for c in self.progress]),
+        }
+
+    def mean_and_cov(self):
+        """Ensemble posterior mean and covariance from the second halves of all chains
+        (the checkpoint statistics): cov = W + B."""
+        sums = self._moments(MOMENTS_HALVES if self.n_chains > 1 else MOMENTS_SINGLE_SPLIT,
+                             int(self.opts["Rminus1_single_split"]))
+        res = rminus1_from_sums(sums, self.fm.D, self._shift)
+        cov = res["W"] + (res.get("B", 0.0) if self.n_chains > 1 else 0.0)
+        return res["mean"], cov, res

@@ -138,6 +138,11 @@ int cb2_debug_basis(cb2_engine *h, int64_t chain, int32_t block, uint32_t epoch,
 int64_t cb2_launch_count(const cb2_engine *h);
 int cb2_timer_start(cb2_engine *h);
 int cb2_timer_stop(cb2_engine *h, float *ms);
+/* per-kernel-class device time: when profiling is on every launch is bracketed by CUDA
+ * events on the engine's stream; ms[k]/n[k] accumulate over launches of class
+ * k = 0 cycler tapes, 1 Haar bases, 2 step kernel, 3 moments. */
+int cb2_set_profiling(cb2_engine *h, int32_t on);
+int cb2_kernel_times(cb2_engine *h, double ms[4], int64_t n[4], int32_t reset);
 /* which step kernel the last cb2_advance used: 0 = general warp-per-chain,
  * 1 = DMMA (mma.sync.m8n8k4.f64) register-resident fast path */
 int cb2_last_step_kernel(const cb2_engine *h);
