@@ -75,6 +75,8 @@ struct cb2_engine {
     DevBuf<int32_t> d_prior_kind, d_periodic, d_ipool, d_i_of_j;
     DevBuf<double> d_lower, d_upper, d_loc, d_pscale, d_dpool, d_TT;
     DevBuf<double> d_fastpack;  // fragment-ordered matrices for the DMMA kernel
+    FastPackDesc fast_desc;
+    bool fast_ready = false;
     ModelDev M;
     // ---- chain state
     DevBuf<double> d_x, d_logpost, d_logprior, d_ll, d_der, d_rows;
@@ -749,7 +751,7 @@ extern "C" int cb2_advance(cb2_engine *h, int64_t n_proposals) {
     StepSmem L = plan_step_smem(h);
     int warps; size_t bytes;
     if ((rc = step_launch_dims(h, L, warps, bytes))) return rc;
-    const bool fast_ok = (h->policy == 0) && fast_step_supported(h->M, h->likes.size());
+    const bool fast_ok = (h->policy == 0) && h->fast_ready;
     int64_t remaining = n_proposals;
     while (remaining > 0) {
         WindowDev W;
@@ -822,8 +824,8 @@ extern "C" int cb2_advance(cb2_engine *h, int64_t n_proposals) {
         }
         h->prof_begin(PROF_STEP);
         if (fast_ok) {
-            if ((rc = launch_step_fast(h->stream, h->M, h->S, W, h->d_fastpack.p, C,
-                                       (uint64_t)h->steps_done, w, h->sm_count))) {
+            if ((rc = launch_step_fast(h->stream, h->M, h->S, W, h->d_fastpack.p, h->fast_desc,
+                                       C, (uint64_t)h->steps_done, w, h->sm_count))) {
                 FAIL(h, -2, "fast step kernel launch failed (%d)", rc);
             }
             h->last_kernel = 1;

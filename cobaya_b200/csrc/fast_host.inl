@@ -1,2 +1,97 @@
-// fast_host.inl -- host-side packing for the fast kernels (included by engine.cu)
-static int pack_fast(cb2_engine *) { return 0; }
+// fast_host.inl -- host-side packing of the constant block consumed by k_step_fast
+// (included at the end of engine.cu).  Everything is expressed in block-SORTED
+// coordinates j (x_sorted[j] = x[i_of_j[j]]), padded to DP = 8*NT, and the two matrices
+// are laid out in m8n8k4 B-fragment order (see warp_matvec8).
+static void pack_frag(std::vector<double> &out, size_t off, const std::vector<double> &Mat,
+                      int DP, int NT, bool tri) {
+    for (int nt = 0; nt < NT; ++nt)
+        for (int m = 0; m < NT; ++m) {
+            if (tri && m > nt) continue;
+            const size_t blk = tri ? (size_t)(nt * (nt + 1)) / 2 + m : (size_t)nt * NT + m;
+            for (int lane = 0; lane < 32; ++lane) {
+                const int q = lane >> 2, r = lane & 3;
+                const int row = 8 * nt + q, col = 8 * m + 2 * r;
+                out[off + blk * 64 + lane * 2 + 0] = Mat[(size_t)row * DP + col];
+                out[off + blk * 64 + lane * 2 + 1] = Mat[(size_t)row * DP + col + 1];
+            }
+        }
+}
+
+static int pack_fast(cb2_engine *h) {
+    h->fast_ready = false;
+    if (!fast_step_supported(h->M, h->likes.size())) return 0;
+    const int D = h->D, NT = (D + 7) / 8, DP = 8 * NT;
+    const LikeHost &L = h->likes[0];
+    const int nm = L.d.n_modes;
+    std::vector<int> j_of_i(D), ilike_of_i(D, -1);
+    for (int j = 0; j < D; ++j) j_of_i[h->i_of_j[j]] = j;
+    for (int a = 0; a < D; ++a) {
+        if (ilike_of_i[L.idx[a]] != -1) return 0;  // repeated input parameter: general path
+        ilike_of_i[L.idx[a]] = a;
+    }
+    bool tri = true;
+    for (int j = 0; j < D; ++j)
+        if (ilike_of_i[h->i_of_j[j]] != j) tri = false;
+    FastPackDesc P;
+    memset(&P, 0, sizeof(P));
+    P.NT = NT;
+    P.n_modes = nm;
+    P.tri_like = tri ? 1 : 0;
+    const int blocks_T = NT * (NT + 1) / 2;
+    P.blocks_A = tri ? blocks_T : NT * NT;
+    int o = 0;
+    auto take = [&](int n) { int r = o; o += (n + 1) & ~1; return r; };
+    P.off_T = take(blocks_T * 64);
+    P.off_A = take(nm * P.blocks_A * 64);
+    P.off_mu = take(nm * DP);
+    P.off_c0 = take(nm);
+    P.off_w = take(nm);
+    P.off_lower = take(DP); P.off_upper = take(DP); P.off_loc = take(DP);
+    P.off_mls = take(DP); P.off_isc = take(DP); P.off_flags = take(DP); P.off_iofj = take(DP);
+    P.total = o;
+    if ((size_t)P.total * 8 > 190 * 1024) return 0;  // does not fit: general path
+    std::vector<double> pk(P.total, 0.0);
+    // T (sorted coordinates already)
+    std::vector<double> Mat((size_t)DP * DP, 0.0);
+    for (int j = 0; j < D; ++j)
+        for (int k = 0; k <= j; ++k) Mat[(size_t)j * DP + k] = h->Trow[(size_t)j * D + k];
+    pack_frag(pk, P.off_T, Mat, DP, NT, true);
+    for (int km = 0; km < nm; ++km) {
+        std::fill(Mat.begin(), Mat.end(), 0.0);
+        for (int a = 0; a < D; ++a)
+            for (int j = 0; j < D; ++j) {
+                const int il = ilike_of_i[h->i_of_j[j]];
+                // Linv[a][il] = linvT[il*dim + a]
+                Mat[(size_t)a * DP + j] = L.linvT[(size_t)km * D * D + (size_t)il * D + a];
+            }
+        pack_frag(pk, P.off_A + (size_t)km * P.blocks_A * 64, Mat, DP, NT, tri);
+        for (int j = 0; j < D; ++j)
+            pk[P.off_mu + km * DP + j] = L.means[(size_t)km * D + ilike_of_i[h->i_of_j[j]]];
+        pk[P.off_c0 + km] = L.c0[km];
+        pk[P.off_w + km] = L.w[km];
+    }
+    for (int j = 0; j < DP; ++j) {
+        if (j < D) {
+            const int i = h->i_of_j[j];
+            pk[P.off_lower + j] = h->lower[i];
+            pk[P.off_upper + j] = h->upper[i];
+            pk[P.off_loc + j] = h->loc[i];
+            pk[P.off_isc + j] = h->pscale[i];
+            pk[P.off_mls + j] = (h->prior_kind[i] == 1)
+                                    ? (-std::log(h->pscale[i]) - CB2_LOG_2PI / 2) : 0.0;
+            pk[P.off_flags + j] = (double)((h->prior_kind[i] == 1 ? 1 : 0) |
+                                           (h->periodic[i] ? 2 : 0));
+            pk[P.off_iofj + j] = (double)i;
+        } else {
+            pk[P.off_lower + j] = -INFINITY;
+            pk[P.off_upper + j] = INFINITY;
+            pk[P.off_isc + j] = 1.0;
+            pk[P.off_iofj + j] = -1.0;
+        }
+    }
+    int rc = upload(h, h->d_fastpack, pk);
+    if (rc) return rc;
+    h->fast_desc = P;
+    h->fast_ready = true;
+    return 0;
+}

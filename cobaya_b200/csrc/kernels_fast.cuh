@@ -1,14 +1,512 @@
-// kernels_fast.cuh -- register-resident fast paths (filled in below the general path).
+// kernels_fast.cuh -- register-resident fast paths for D <= 64 (sm_100a).
+//
+//  * k_basis_fast<NG>  : random_SO_N (cobaya/functions.py:21-60) with one thread per ROW
+//    of H held in registers; the Householder sweep is the reference's own left-to-right
+//    order (functions.py:48-58), the vectors x_m are broadcast from shared memory.
+//  * k_step_fast<NT>   : the propose -> logposterior -> accept -> store loop
+//    (mcmc.py:545-562,670-748) for 8 chains per warp.  The two triangular matrix
+//    products of a proposal -- T v (proposal.py:224) and L^-1 (x'-mu)
+//    (gaussian_mixture.py:148) -- run on the FP64 tensor pipe as m8n8k4 DMMA tiles with
+//    the 8 chains as the M dimension; chain state lives in registers for the whole
+//    window; the shared matrices are staged into shared memory once per CTA with a TMA
+//    bulk copy (cp.async.bulk + mbarrier) in MMA-fragment order.
 #pragma once
 #include "common.cuh"
 #include "kernels_general.cuh"
 
-static inline bool fast_step_supported(const ModelDev &, size_t) { return false; }
-static inline int launch_step_fast(cudaStream_t, const ModelDev &, const ChainState &,
-                                   const WindowDev &, const double *, int64_t, uint64_t, int,
-                                   int) { return -1; }
-static inline bool fast_basis_supported(int) { return false; }
-static inline int launch_basis_fast(cudaStream_t, uint32_t, uint32_t, uint64_t, int, int,
-                                    const int64_t *, int, int, double *, int64_t) { return -1; }
-static inline int launch_basis_fast_one(cudaStream_t, uint32_t, uint32_t, uint64_t, int, int,
-                                        uint32_t, double *) { return -1; }
+// =====================================================================================
+// Haar basis, n <= 64
+// =====================================================================================
+static inline bool fast_basis_supported(int n) { return n >= 2 && n <= 64; }
+
+template <int NG>
+__global__ void __launch_bounds__((NG * 8 < 32) ? 32 : NG * 8)
+k_basis_fast(uint32_t key0, uint32_t key1, uint64_t chain_id0, int block, int n,
+             const int64_t *__restrict__ vis, int vis_stride, uint32_t e0_fixed, int cnt,
+             double *__restrict__ store, int64_t task0, int64_t store_task0) {
+    constexpr int NP = NG * 8;
+    extern __shared__ __align__(16) double fsm[];
+    double *X = fsm;              // [NP][NP]: X[m][c] = x_m[c-m] for c >= m, else 0
+    double *Dv = fsm + NP * NP;   // [NP]
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int64_t task = task0 + blockIdx.x;
+    const int64_t chain = task / cnt;
+    const uint32_t e0 = vis ? (uint32_t)(vis[chain * vis_stride + block] / n) : e0_fixed;
+    const uint32_t epoch = e0 + (uint32_t)(task % cnt);
+    const uint64_t gid = chain_id0 + (uint64_t)chain;
+    for (int e = tid; e < NP * NP; e += nt) X[e] = 0.0;
+    __syncthreads();
+    // 1. standard normals (functions.py:36) scattered into the padded layout
+    const int nn = (n + 2) * (n - 1) / 2;
+    for (int p = tid; p < (nn + 1) / 2; p += nt) {
+        double z[2];
+        draw_normal_pair(key0, key1, gid, block, epoch, (uint32_t)p, z[0], z[1]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            int q = 2 * p + h;
+            if (q < nn) {
+                // q = ix(m) + i, ix(m) = m*n - m(m-1)/2, 0 <= i < n-m
+                double b = 2.0 * n + 1.0;
+                int m = (int)floor((b - sqrt(b * b - 8.0 * q)) * 0.5);
+                if (m > n - 2) m = n - 2;
+                while (m > 0 && m * n - (m * (m - 1)) / 2 > q) --m;
+                while ((m + 1) * n - ((m + 1) * m) / 2 <= q) ++m;
+                int i = q - (m * n - (m * (m - 1)) / 2);
+                X[m * NP + m + i] = z[h];
+            }
+        }
+    }
+    __syncthreads();
+    // 2. Householder vectors (functions.py:49-55)
+    if (tid < n - 1) {
+        const int m = tid, len = n - m;
+        double *x = X + m * NP + m;
+        double norm2 = 0.0;
+        for (int i = 0; i < len; ++i) norm2 += x[i] * x[i];
+        double x0 = x[0];
+        double d = (x0 != 0.0) ? (x0 > 0 ? 1.0 : -1.0) : 1.0;
+        double x0n = x0 + d * sqrt(norm2);
+        x[0] = x0n;
+        double sc = sqrt((norm2 - x0 * x0 + x0n * x0n) / 2.0);
+        for (int i = 0; i < len; ++i) x[i] /= sc;
+        Dv[m] = d;
+    }
+    __syncthreads();
+    if (tid == 0) {  // functions.py:59
+        double prod = 1.0;
+        for (int m = 0; m < n - 1; ++m) prod *= Dv[m];
+        Dv[n - 1] = (((n - 1) & 1) ? -1.0 : 1.0) * prod;
+    }
+    // 3. H = I; for m: H[:, m:] -= (H[:, m:] x_m) x_m^T  (functions.py:57-58); row r here
+    const int r = tid;
+    double h[NP];
+#pragma unroll
+    for (int c = 0; c < NP; ++c) h[c] = (c == r) ? 1.0 : 0.0;
+#pragma unroll
+    for (int G = 0; G < NG; ++G) {
+        const int m_end = min(8 * G + 8, n - 1);
+        for (int m = 8 * G; m < m_end; ++m) {
+            const double2 *x2 = reinterpret_cast<const double2 *>(X + m * NP);
+            double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+#pragma unroll
+            for (int c = 8 * G; c < NP; c += 4) {
+                double2 a = x2[c / 2], b = x2[c / 2 + 1];
+                t0 = fma(h[c], a.x, t0);
+                t1 = fma(h[c + 1], a.y, t1);
+                t2 = fma(h[c + 2], b.x, t2);
+                t3 = fma(h[c + 3], b.y, t3);
+            }
+            const double tmp = (t0 + t1) + (t2 + t3);
+#pragma unroll
+            for (int c = 8 * G; c < NP; c += 2) {
+                double2 a = x2[c / 2];
+                h[c] = fma(-tmp, a.x, h[c]);
+                h[c + 1] = fma(-tmp, a.y, h[c + 1]);
+            }
+        }
+    }
+    __syncthreads();
+    // 4. R = diag(D) H (functions.py:60); stored as Rt[k*n + r] = R[r][k]
+    if (r < n) {
+        const double d = Dv[r];
+        double *out = store + (size_t)(task - store_task0) * (size_t)n * n;
+#pragma unroll
+        for (int k = 0; k < NP; ++k)
+            if (k < n) out[(size_t)k * n + r] = d * h[k];
+    }
+}
+
+template <int NG>
+static int launch_basis_fast_t(cudaStream_t st, uint32_t k0, uint32_t k1, uint64_t chain_id0,
+                               int block, int n, const int64_t *vis, int vis_stride,
+                               uint32_t e0_fixed, int cnt, double *store, int64_t tasks,
+                               int64_t task0, int64_t store_task0) {
+    constexpr int NP = NG * 8;
+    const int threads = NP < 32 ? 32 : NP;
+    const size_t smem = (size_t)(NP * NP + NP) * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(k_basis_fast<NG>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return -1;
+    k_basis_fast<NG><<<(unsigned)tasks, threads, smem, st>>>(
+        k0, k1, chain_id0, block, n, vis, vis_stride, e0_fixed, cnt, store, task0, store_task0);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+static int launch_basis_fast_any(cudaStream_t st, uint32_t k0, uint32_t k1, uint64_t chain_id0,
+                                 int block, int n, const int64_t *vis, int vis_stride,
+                                 uint32_t e0_fixed, int cnt, double *store, int64_t tasks,
+                                 int64_t task0, int64_t store_task0) {
+    const int NG = (n + 7) / 8;
+#define CB2_BF(G)                                                                           \
+    case G:                                                                                 \
+        return launch_basis_fast_t<G>(st, k0, k1, chain_id0, block, n, vis, vis_stride,     \
+                                      e0_fixed, cnt, store, tasks, task0, store_task0);
+    switch (NG) {
+        CB2_BF(1) CB2_BF(2) CB2_BF(3) CB2_BF(4) CB2_BF(5) CB2_BF(6) CB2_BF(7) CB2_BF(8)
+    }
+#undef CB2_BF
+    return -1;
+}
+
+static inline int launch_basis_fast(cudaStream_t st, uint32_t k0, uint32_t k1,
+                                    uint64_t chain_id0, int block, int n, const int64_t *vis,
+                                    int vis_stride, int cnt, double *store, int64_t n_chains) {
+    return launch_basis_fast_any(st, k0, k1, chain_id0, block, n, vis, vis_stride, 0u, cnt,
+                                 store, n_chains * cnt, 0, 0);
+}
+
+static inline int launch_basis_fast_one(cudaStream_t st, uint32_t k0, uint32_t k1, uint64_t gid,
+                                        int block, int n, uint32_t epoch, double *out) {
+    // chain_id0 = gid, task 0 -> chain 0
+    return launch_basis_fast_any(st, k0, k1, gid, block, n, nullptr, 0, epoch, 1, out, 1, 0, 0);
+}
+
+// =====================================================================================
+// DMMA step kernel
+// =====================================================================================
+// Packed constant block staged into shared memory (all offsets in doubles, 16B aligned):
+struct FastPackDesc {
+    int NT;        // DP/8
+    int n_modes;
+    int tri_like;  // likelihood matrix lower-triangular in sorted coordinates
+    int off_T;     // fragment-ordered T      : tri blocks, 64 doubles each
+    int off_A;     // fragment-ordered L^-1 P : per mode, tri or dense blocks
+    int blocks_A;  // blocks per mode
+    int off_mu;    // [n_modes][DP]  means in sorted coordinates
+    int off_c0;    // [n_modes]      d log 2pi + logdet
+    int off_w;     // [n_modes]      weights
+    int off_lower, off_upper, off_loc, off_mls, off_isc;  // [DP] each (mls = -log s - log(2pi)/2, isc = s)
+    int off_flags; // [DP] as doubles: bit0 normal prior, bit1 periodic
+    int off_iofj;  // [DP] as doubles: sampler index of sorted j (or -1 for padding)
+    int total;     // doubles
+};
+
+static inline bool fast_step_supported(const ModelDev &M, size_t n_likes) {
+    if (M.drag || M.D > 64 || n_likes != 1) return false;
+    const LikeDev &L = M.likes[0];
+    if (L.kind != 0 || L.dim != M.D || L.derived) return false;
+    if (L.n_modes > 4) return false;
+    return true;
+}
+
+__device__ __forceinline__ void dmma8x8x4(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ double quad_sum(double v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    return v;
+}
+
+// out[nt][h] += sum_k Mat[8nt+q .. ][k] * a[k]  for the 8 chains of the warp.
+// frag: blocks of 64 doubles, block(nt, m) holds for lane l=(q,r): {Mat[8nt+q][8m+2r],
+// Mat[8nt+q][8m+2r+1]}.  TRI: only m <= nt present, block index nt(nt+1)/2 + m.
+template <int NT, bool TRI>
+__device__ __forceinline__ void warp_matvec8(const double *__restrict__ frag, int lane,
+                                             const double (&a)[NT][2], double (&out)[NT][2]) {
+    const double2 *f2 = reinterpret_cast<const double2 *>(frag) + lane;
+#pragma unroll
+    for (int m = 0; m < NT; ++m) {
+#pragma unroll
+        for (int nt = TRI ? m : 0; nt < NT; ++nt) {
+            const int blk = TRI ? (nt * (nt + 1)) / 2 + m : nt * NT + m;
+            const double2 b = f2[blk * 32];
+            dmma8x8x4(out[nt][0], out[nt][1], a[m][0], b.x);
+            dmma8x8x4(out[nt][0], out[nt][1], a[m][1], b.y);
+        }
+    }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(256, 1)
+k_step_fast(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gpack,
+            FastPackDesc P, int64_t n_chains, uint64_t t0, int n_steps) {
+    constexpr int DP = NT * 8;
+    extern __shared__ __align__(16) double fsm[];
+    __shared__ __align__(8) unsigned long long mbar;
+    double *pack = fsm;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = blockDim.x >> 5;
+    // ---- stage the constant block with a TMA bulk copy (global -> shared, mbarrier)
+    const uint32_t bytes = (uint32_t)P.total * 8u;
+    const uint32_t mbar_a = (uint32_t)__cvta_generic_to_shared(&mbar);
+    const uint32_t dst_a = (uint32_t)__cvta_generic_to_shared(pack);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_a));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_a),
+                     "r"(bytes)
+                     : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+            ::"r"(dst_a), "l"(gpack), "r"(bytes), "r"(mbar_a)
+            : "memory");
+    }
+    {
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(mbar_a)
+                : "memory");
+        }
+    }
+    // per-warp scratch after the pack: visit counters [8 chains][NB] (int32)
+    int *svis = reinterpret_cast<int *>(fsm + P.total) + wid * 8 * CB2_MAX_BLOCKS;
+
+    const int q = lane >> 2, r = lane & 3;
+    const int64_t tile = blockIdx.x * (int64_t)nwarps + wid;
+    const int64_t chain_raw = tile * 8 + q;
+    const bool active = chain_raw < n_chains;
+    const int64_t chain = active ? chain_raw : (n_chains - 1);
+    const uint64_t gid = M.chain_id0 + (uint64_t)chain;
+    const int D = M.D, NB = M.n_blocks, NV = NB + 1;
+    const double *Tf = pack + P.off_T, *Af = pack + P.off_A;
+    const double *lower = pack + P.off_lower, *upper = pack + P.off_upper;
+    const double *iofj = pack + P.off_iofj, *pflags = pack + P.off_flags;
+
+    // ---- load chain state (sorted coordinates): element j = 8n + 2r + h
+    double xs[NT][2];
+#pragma unroll
+    for (int n = 0; n < NT; ++n)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            int i = (int)iofj[8 * n + 2 * r + h];
+            xs[n][h] = (i >= 0) ? S.x[chain * D + i] : 0.0;
+        }
+    double logpost = S.logpost[chain], logprior = S.logprior[chain], loglike = S.ll[chain];
+    long long weight = S.weight[chain], prior_rej = S.prior_rej[chain],
+              burn_left = S.burn_left[chain], added_w = S.added_w[chain],
+              n_rows = S.n_rows[chain], n_acc = S.n_acc[chain];
+    uint32_t flags = S.flags[chain];
+    if (r == 0)
+        for (int b = 0; b < NB; ++b) svis[q * CB2_MAX_BLOCKS + b] = 0;
+    __syncwarp();
+    const bool any_per = M.any_periodic, any_norm = M.any_normal;
+
+    for (int s = 0; s < n_steps; ++s) {
+        const uint64_t t = t0 + (uint64_t)s;
+        const int b = W.tape_main ? W.tape_main[chain * W.len_main + (int64_t)(t - W.base_main)]
+                                  : W.const_main;
+        const int nb = M.bsize[b], j0 = M.jstart[b];
+        // ---- direction + radius (proposal.py:59-93)
+        double rad, sign;
+        draw_radial(M, gid, t, 0, nb, rad, sign);
+        double v[NT][2];
+        if (nb >= 2) {
+            const int vrel = svis[q * CB2_MAX_BLOCKS + b];
+            const long long vstart = S.vis[chain * NV + b];
+            const long long vabs = vstart + vrel;
+            long long slot = vabs / nb - vstart / nb;
+            const int k = (int)(vabs % nb);
+            if (slot < 0 || slot >= W.cnt[b]) {
+                flags |= CB2_FLAG_INTERNAL;
+                slot = 0;
+            }
+            const double *Rk = W.basis[b] + (((size_t)chain * W.cnt[b] + slot) * nb + k) * nb;
+            const double rs = rad;
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int j = 8 * n + 2 * r + h - j0;
+                    v[n][h] = (j >= 0 && j < nb) ? Rk[j] * rs * M.proposal_scale : 0.0;
+                }
+        } else {
+            const double val = (sign > 0) ? rad * M.proposal_scale : -(rad * M.proposal_scale);
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) v[n][h] = (8 * n + 2 * r + h == j0) ? val : 0.0;
+        }
+        __syncwarp();
+        if (r == 0) svis[q * CB2_MAX_BLOCKS + b] += 1;
+        // ---- trial = x + T v  (proposal.py:224) on the FP64 tensor pipe
+        double xt[NT][2];
+#pragma unroll
+        for (int n = 0; n < NT; ++n) { xt[n][0] = 0.0; xt[n][1] = 0.0; }
+        warp_matvec8<NT, true>(Tf, lane, v, xt);
+#pragma unroll
+        for (int n = 0; n < NT; ++n) { xt[n][0] += xs[n][0]; xt[n][1] += xs[n][1]; }
+        // ---- reduce_periodic (prior.py:658-676), bounds + prior (prior.py:733-763)
+        bool bad = false;
+        double ps = 0.0;
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = 8 * n + 2 * r + h;
+                double xv = xt[n][h];
+                const double lo = lower[j], up = upper[j];
+                if (any_per || any_norm) {
+                    const int fl = (int)pflags[j];
+                    if (fl & 2) {
+                        double qq = (xv - lo) / (up - lo);
+                        qq = qq - floor(qq);
+                        xv = qq * (up - lo) + lo;
+                        xt[n][h] = xv;
+                    }
+                    if (fl & 1) {
+                        const double zz = (xv - pack[P.off_loc + j]) / pack[P.off_isc + j];
+                        ps += pack[P.off_mls + j] - zz * zz / 2;
+                    }
+                }
+                if (!(xv <= up) || !(xv >= lo) || !isfinite(xv)) bad = true;
+            }
+        bad = __shfl_xor_sync(0xffffffffu, (int)bad, 1) | (int)bad;
+        bad = __shfl_xor_sync(0xffffffffu, (int)bad, 2) | (int)bad;
+        double t_prior, t_like = 0.0, t_post;
+        if (any_norm) ps = quad_sum(ps);
+        t_prior = bad ? -CUDART_INF : (M.uniform_logp + ps);
+        // ---- GaussianMixture.logp (gaussian_mixture.py:138-163); computed for every chain
+        // of the warp (the MMA is warp-wide), discarded where the prior is -inf
+        {
+            double lpk[4];
+            for (int km = 0; km < P.n_modes; ++km) {
+                const double *mu = pack + P.off_mu + km * DP;
+                double z[NT][2], y[NT][2];
+#pragma unroll
+                for (int n = 0; n < NT; ++n) {
+                    const double2 m2 = *reinterpret_cast<const double2 *>(mu + 8 * n + 2 * r);
+                    z[n][0] = xt[n][0] - m2.x;
+                    z[n][1] = xt[n][1] - m2.y;
+                    y[n][0] = 0.0;
+                    y[n][1] = 0.0;
+                }
+                const double *Ak = Af + (size_t)km * P.blocks_A * 64;
+                if (P.tri_like) warp_matvec8<NT, true>(Ak, lane, z, y);
+                else warp_matvec8<NT, false>(Ak, lane, z, y);
+                double qsum = 0.0;
+#pragma unroll
+                for (int n = 0; n < NT; ++n) qsum += y[n][0] * y[n][0] + y[n][1] * y[n][1];
+                qsum = quad_sum(qsum);
+                lpk[km] = -0.5 * (pack[P.off_c0 + km] + qsum);
+            }
+            if (P.n_modes == 1) t_like = lpk[0];
+            else {
+                double mx = lpk[0];
+                for (int km = 1; km < P.n_modes; ++km) mx = fmax(mx, lpk[km]);
+                if (mx == -CUDART_INF) t_like = -CUDART_INF;
+                else {
+                    double acc = 0.0;
+                    for (int km = 0; km < P.n_modes; ++km)
+                        acc += pack[P.off_w + km] * exp(lpk[km] - mx);
+                    t_like = log(acc) + mx;
+                }
+            }
+        }
+        t_post = bad ? -CUDART_INF : (t_prior + t_like);
+        // ---- metropolis_accept (mcmc.py:670-683)
+        bool acc;
+        if (t_post == -CUDART_INF) acc = false;
+        else if (t_post > logpost) acc = true;
+        else acc = draw_accept_exp(M, gid, t, 0) > (logpost - t_post) / M.temperature;
+        // ---- process_accept_or_reject (mcmc.py:685-748)
+        if (acc) {
+            if (burn_left <= 0) {
+                long long wst = weight;
+                bool store = true;
+                if (M.output_thin > 1) {
+                    added_w += weight;
+                    if (added_w >= M.output_thin) {
+                        wst = added_w / M.output_thin;
+                        added_w %= M.output_thin;
+                    } else store = false;
+                }
+                if (store) {
+                    if (n_rows >= S.cap) flags |= CB2_FLAG_ROWS_FULL;
+                    else {
+                        if (active) {
+                            double *row = S.rows + ((size_t)chain * S.cap + n_rows) * M.width;
+                            if (r == 0) {
+                                row[0] = (double)wst;
+                                row[1] = -(logpost / M.temperature);
+                            } else if (r == 1) {
+                                row[2 + D] = -logprior;
+                                row[3 + D] = -logprior;
+                            } else if (r == 2) {
+                                row[4 + D] = -2 * loglike;
+                                row[5 + D] = -2 * loglike;
+                            }
+#pragma unroll
+                            for (int n = 0; n < NT; ++n)
+#pragma unroll
+                                for (int h = 0; h < 2; ++h) {
+                                    const int i = (int)iofj[8 * n + 2 * r + h];
+                                    if (i >= 0) row[2 + i] = xs[n][h];
+                                }
+                        }
+                        n_rows += 1;
+                    }
+                }
+            } else burn_left -= 1;
+#pragma unroll
+            for (int n = 0; n < NT; ++n) { xs[n][0] = xt[n][0]; xs[n][1] = xt[n][1]; }
+            logpost = t_post; logprior = t_prior; loglike = t_like;
+            weight = 1; prior_rej = 0; n_acc += 1;
+        } else {
+            weight += 1;
+            if (t_prior == -CUDART_INF) prior_rej += 1;
+            const long long sgn = (burn_left > 0) - (burn_left < 0);
+            if (weight - prior_rej > M.max_tries * (1 + 9 * sgn)) flags |= CB2_FLAG_STUCK;
+        }
+    }
+    // ---- write the state back
+    __syncwarp();
+    if (active) {
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int i = (int)iofj[8 * n + 2 * r + h];
+                if (i >= 0) S.x[chain * D + i] = xs[n][h];
+            }
+        if (r == 0) {
+            S.logpost[chain] = logpost; S.logprior[chain] = logprior; S.ll[chain] = loglike;
+            S.weight[chain] = weight; S.prior_rej[chain] = prior_rej;
+            S.burn_left[chain] = burn_left; S.added_w[chain] = added_w;
+            S.n_rows[chain] = n_rows; S.n_acc[chain] = n_acc; S.flags[chain] = flags;
+            for (int b = 0; b < NB; ++b) S.vis[chain * NV + b] += svis[q * CB2_MAX_BLOCKS + b];
+        }
+    }
+}
+
+template <int NT>
+static int launch_step_fast_t(cudaStream_t st, const ModelDev &M, const ChainState &S,
+                              const WindowDev &W, const double *gpack, const FastPackDesc &P,
+                              int64_t n_chains, uint64_t t0, int n_steps, int sm_count) {
+    const int64_t tiles = (n_chains + 7) / 8;
+    int wpc = (int)((tiles + sm_count - 1) / sm_count);
+    if (wpc < 1) wpc = 1;
+    if (wpc > 8) wpc = 8;
+    const int grid = (int)((tiles + wpc - 1) / wpc);
+    const size_t smem = (size_t)P.total * 8 + (size_t)wpc * 8 * CB2_MAX_BLOCKS * sizeof(int);
+    if (smem > 200 * 1024) return -2;
+    if (cudaFuncSetAttribute(k_step_fast<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem) != cudaSuccess)
+        return -1;
+    k_step_fast<NT><<<grid, wpc * 32, smem, st>>>(M, S, W, gpack, P, n_chains, t0, n_steps);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+static inline int launch_step_fast(cudaStream_t st, const ModelDev &M, const ChainState &S,
+                                   const WindowDev &W, const double *gpack,
+                                   const FastPackDesc &P, int64_t n_chains, uint64_t t0,
+                                   int n_steps, int sm_count) {
+#define CB2_SF(N)                                                                       \
+    case N:                                                                             \
+        return launch_step_fast_t<N>(st, M, S, W, gpack, P, n_chains, t0, n_steps, sm_count);
+    switch (P.NT) {
+        CB2_SF(1) CB2_SF(2) CB2_SF(3) CB2_SF(4) CB2_SF(5) CB2_SF(6) CB2_SF(7) CB2_SF(8)
+    }
+#undef CB2_SF
+    return -1;
+}

@@ -1,0 +1,414 @@
+"""
+Cobaya plugin: ``sampler: mcmc`` executed by the B200 ensemble engine.
+
+This module is imported only when the reference package ``cobaya`` is importable; it is
+the drop-in boundary of SURVEY.md section 8b.  ``MCMC`` subclasses
+``cobaya.sampler.CovmatSampler`` (sampler.py:467), is constructed by ``cobaya.run.run``
+exactly like the reference's ``cobaya.samplers.mcmc.MCMC`` (run.py:161) and honours every
+key of ``mcmc.yaml`` (mirrored as class attributes so ``update_info`` accepts them,
+input.py:403-434) plus the engine's own keys.
+
+Two ways to select it:
+
+* non-invasive alias:   ``sampler: {cobaya_b200.plugin.MCMC: {...}}``
+* true drop-in:         ``cobaya_b200.plugin.install_as_mcmc()`` before ``run(info)``;
+                        afterwards ``sampler: mcmc`` resolves to this class.
+
+Host-side setup (start points, blocking, initial covmat) follows ``MCMC.initialize``
+(mcmc.py:111-271) through the model's public API; the per-proposal loop runs only on the
+GPU.  Models outside the recognised set raise ``LoggedError`` (no CPU fallback).
+"""
+
+from __future__ import annotations
+
+import sys
+from collections.abc import Callable, Sequence
+from itertools import chain
+from typing import Any
+
+import numpy as np
+import pandas as pd
+from cobaya import mpi
+from cobaya.collection import SampleCollection, apply_temperature_cov, remove_temperature_cov
+from cobaya.conventions import Extension, OutPar, get_version
+from cobaya.log import LoggedError
+from cobaya.sampler import CovmatSampler
+from cobaya.tools import get_external_function
+from cobaya.yaml import yaml_dump_file
+
+from .flatmodel import FlatModelError
+from .lowering import lower_model
+from .mcmc import EnsembleMCMC
+
+
+class _CurrentPointView:
+    """``sampler.current_point`` as the reference's tests/callbacks touch it
+    (tests/test_mcmc_initial_covmat.py:87-97): the state of local chain 0."""
+
+    def __init__(self, sampler):
+        self._s = sampler
+        self.output_thin = 1
+
+    @property
+    def values(self):
+        if self._s._ens is None:
+            return self._s._x0[0]
+        return self._s._ens.engine.get_state()["x"][0]
+
+    @property
+    def weight(self):
+        return 1 if self._s._ens is None else int(self._s._ens.engine.get_state()["weight"][0])
+
+    @property
+    def logpost(self):
+        if self._s._ens is None:
+            return self._s._logpost0[0]
+        return float(self._s._ens.engine.get_state()["logpost"][0])
+
+
+class _ProposerView:
+    """``sampler.proposer`` surface used by tests and ``write_checkpoint``."""
+
+    def __init__(self, sampler):
+        self._s = sampler
+
+    def get_covariance(self):
+        return self._s._fm.get_covariance()
+
+    def set_covariance(self, cov):
+        self._s._fm.set_covariance(cov)
+        if self._s._ens is not None:
+            self._s._ens.engine.set_covariance(cov)
+
+    def get_scale(self):
+        return self._s.proposal_scale
+
+    def d(self):
+        return self._s._fm.D
+
+    @property
+    def i_of_j(self):
+        return self._s._fm.i_of_j
+
+    @property
+    def j_start(self):
+        return list(self._s._fm.j_start)
+
+    @property
+    def oversampling_factors(self):
+        return np.array(self._s._fm.oversampling, dtype=int)
+
+    @property
+    def transform(self):
+        T, fm = self._s._fm.T, self._s._fm
+        return [T[js:, js: js + n] for js, n in zip(fm.j_start, fm.block_sizes)]
+
+
+class MCMC(CovmatSampler):
+    r"""
+    Adaptive, speed-hierarchy-aware MCMC sampler (adapted from CosmoMC)
+    \cite{Lewis:2002ah,Lewis:2013hha}, run as an ensemble of lock-step chains on
+    NVIDIA B200 GPUs.
+    """
+
+    sampler_type: str = "mcmc"
+    supports_periodic_params = True
+    file_base_name = "mcmc_b200"
+    _at_resume_prefer_new = CovmatSampler._at_resume_prefer_new + [
+        "burn_in", "callback_function", "callback_every", "max_tries", "output_every",
+        "learn_every", "learn_proposal_Rminus1_max", "learn_proposal_Rminus1_max_early",
+        "learn_proposal_Rminus1_min", "max_samples", "Rminus1_stop", "Rminus1_cl_stop",
+        "Rminus1_cl_level", "covmat", "covmat_params",
+    ]
+    _at_resume_prefer_old = CovmatSampler._at_resume_prefer_old + ["proposal_scale", "blocking"]
+
+    # ---- every key of cobaya/samplers/mcmc/mcmc.yaml with its default ------------------
+    burn_in: Any = 0
+    max_tries: Any = "40d"
+    covmat: Any = None
+    covmat_params: Any = None
+    proposal_scale: float = 2.4
+    output_every: Any = "60s"
+    learn_every: Any = "40d"
+    temperature: float | None = 1
+    learn_proposal: bool = True
+    learn_proposal_Rminus1_max: float = 2.0
+    learn_proposal_Rminus1_max_early: float = 30.0
+    learn_proposal_Rminus1_min: float = 0.0
+    max_samples: float = np.inf
+    Rminus1_stop: float = 0.01
+    Rminus1_cl_stop: float = 0.2
+    Rminus1_cl_level: float = 0.95
+    Rminus1_single_split: int = 4
+    measure_speeds: Any = True
+    oversample_power: float = 0.4
+    oversample_thin: Any = True
+    drag: bool = False
+    blocking: Sequence | None = None
+    callback_function: Callable | str | None = None
+    callback_every: Any = None
+    seed: Any = None
+    check_every: Any = None   # deprecated, accepted and ignored (mcmc.yaml:78)
+    oversample: Any = None    # deprecated
+    drag_limits: Any = None   # deprecated
+    # ---- engine keys ---------------------------------------------------------------------
+    chains_per_gpu: int = 8192
+    device: int | None = None
+    rows_per_chain: int | None = None
+    launch_cycles: int | None = None
+
+    def set_instance_defaults(self):
+        super().set_instance_defaults()
+        self.converged = False
+        self.mpi_size = None
+        self.Rminus1_last = np.inf
+
+    # ------------------------------------------------------------------ initialize
+    def initialize(self):
+        """mcmc.py:111-271, for ``chains_per_gpu`` chains per process."""
+        if not self.model.prior.d():
+            raise LoggedError(self.log, "No parameters being varied for sampler")
+        if self.temperature is None:
+            self.temperature = 1
+        self._ens = None
+        self.n_steps_raw = 0
+        self.last_point_callback = 0
+        self.i_learn = 1
+        self.progress = pd.DataFrame(
+            columns=["N", "timestamp", "acceptance_rate", "Rminus1", "Rminus1_cl"])
+        if self.callback_function:
+            self.callback_function_callable = get_external_function(self.callback_function)
+        if self.output and self.output.is_resuming():
+            raise LoggedError(
+                self.log, "Resuming a run is not yet supported by the B200 ensemble engine "
+                          "(SURVEY.md section 8f row 1).")
+        n_local = int(self.chains_per_gpu)
+        # start points: one independent valid point per chain (mcmc.py:215-222)
+        D = self.model.prior.d()
+        max_tries_init = 10 * D + 100
+        self._x0 = np.empty((n_local, D))
+        self._logpost0 = np.empty(n_local)
+        self.log.info("Getting %d initial points...", n_local)
+        for c in range(n_local):
+            x, res = self.model.get_valid_point(max_tries=max_tries_init * 100,
+                                                random_state=self._rng)
+            self._x0[c] = x
+            self._logpost0[c] = res.logpost
+        if self.measure_speeds and not self.blocking:
+            n = None if self.measure_speeds is True else int(self.measure_speeds)
+            self.model.measure_and_set_speeds(n=n, discard=0, random_state=self._rng)
+        self.current_point = _CurrentPointView(self)
+        self.set_proposer_blocking()
+        self.set_proposer_initial_covmat(load=True)
+        self.collection = SampleCollection(
+            self.model, self.output, name=str(1 + mpi.rank()), temperature=self.temperature,
+            sample_type="mcmc", is_batch=True)
+        self.write_checkpoint()
+
+    def set_proposer_blocking(self):
+        """mcmc.py:320-410: blocks/oversampling from the model, dragging gates, thinning."""
+        if self.blocking:
+            self.blocks, self.oversampling_factors = self.model.check_blocking(self.blocking)
+        else:
+            self.blocks, self.oversampling_factors = (
+                self.model.get_param_blocking_for_sampler(
+                    oversample_power=self.oversample_power, split_fast_slow=self.drag))
+        if self.drag:
+            if len(self.blocks) == 1:
+                self.drag = False
+                self.mpi_warning("Dragging disabled: not possible if there is only one block.")
+            if max(self.oversampling_factors) / min(self.oversampling_factors) < 2:
+                self.drag = False
+                self.mpi_warning("Dragging disabled: speed ratios < 2.")
+        self.drag_interp_steps = 0
+        i_last_slow = None
+        if self.drag:
+            i_last_slow = next(i for i, o in enumerate(self.oversampling_factors) if o != 1) - 1
+            n_slow = len(list(chain(*self.blocks[: 1 + i_last_slow])))
+            n_fast = len(list(chain(*self.blocks[1 + i_last_slow:])))
+            self.drag_interp_steps = int(
+                np.round(self.oversampling_factors[i_last_slow + 1] * n_fast / n_slow))
+            if self.drag_interp_steps < 2:
+                self.drag = False
+                self.mpi_warning("Dragging disabled: "
+                                 "speed ratio and fast-to-slow ratio not large enough.")
+        output_thin = 1
+        if not self.drag and np.any(np.array(self.oversampling_factors) > 1):
+            if self.oversample_thin:
+                output_thin = int(np.round(
+                    sum(len(b) * o for b, o in zip(self.blocks, self.oversampling_factors))
+                    / self.model.prior.d()))
+        self.current_point.output_thin = output_thin
+        self._updated_info["blocking"] = list(zip(self.oversampling_factors, self.blocks))
+        sampled = list(self.model.parameterization.sampled_params())
+        blocks_indices = [[sampled.index(p) for p in b] for b in self.blocks]
+        if self.drag:
+            self.cycle_length = sum(len(b) for b in blocks_indices[: 1 + i_last_slow])
+        else:
+            self.cycle_length = sum(
+                len(b) * o for b, o in zip(blocks_indices, self.oversampling_factors))
+        self._blocking_lowered = dict(
+            blocks=blocks_indices, oversampling=[int(o) for o in self.oversampling_factors],
+            drag=bool(self.drag), i_last_slow_block=i_last_slow if self.drag else None,
+            drag_interp_steps=self.drag_interp_steps, output_thin=output_thin)
+        self.proposer = _ProposerView(self)
+
+    def set_proposer_initial_covmat(self, load=False):
+        """mcmc.py:412-440 + lowering of the model (recognised set only)."""
+        self._initial_covmat, where_nan = self._load_covmat(
+            prefer_load_old=self.output.is_resuming() if self.output else False)
+        self._covmat_incomplete = bool(np.any(where_nan))
+        try:
+            self._fm = lower_model(
+                self.model, proposal_cov=apply_temperature_cov(self._initial_covmat,
+                                                               self.temperature),
+                proposal_scale=float(self.proposal_scale), temperature=float(self.temperature),
+                **self._blocking_lowered)
+        except FlatModelError as e:
+            raise LoggedError(self.log, "%s", str(e)) from e
+
+    # ------------------------------------------------------------------ run
+    def _options(self):
+        keys = ["burn_in", "max_tries", "proposal_scale", "learn_every", "temperature",
+                "learn_proposal", "learn_proposal_Rminus1_max",
+                "learn_proposal_Rminus1_max_early", "learn_proposal_Rminus1_min",
+                "max_samples", "Rminus1_stop", "Rminus1_cl_stop", "Rminus1_cl_level",
+                "Rminus1_single_split", "callback_every", "chains_per_gpu", "device",
+                "rows_per_chain", "launch_cycles"]
+        o = {k: getattr(self, k) for k in keys}
+        seed = self.seed
+        o["seed"] = int(self._rng.integers(2**62)) if seed is None else int(
+            np.random.SeedSequence(seed).generate_state(1, np.uint64)[0] >> 2)
+        return o
+
+    def run(self):
+        """mcmc.py:451-528 -- the loop body runs on the GPU."""
+        dist = None
+        try:
+            import torch.distributed as tdist
+
+            if tdist.is_available() and tdist.is_initialized() and tdist.get_world_size() > 1:
+                from .mcmc import TorchDist
+
+                dist = TorchDist()
+        except ImportError:
+            pass
+        try:
+            self._ens = EnsembleMCMC(self._fm, self._x0, self._options(), dist=dist,
+                                     covmat_incomplete=self._covmat_incomplete)
+        except Exception as e:
+            raise LoggedError(self.log, "Could not start the B200 engine: %s", e) from e
+        ens = self._ens
+        self.mpi_info("Sampling! (%d lock-step chains)", ens.n_chains)
+
+        def _cb(_):
+            self.n_steps_raw = ens.n_steps_raw
+            if self.callback_function and ens.n() >= self.last_point_callback + max(
+                    1, ens.callback_every.value):
+                self.callback_function_callable(self)
+                self.last_point_callback = ens.n()
+
+        try:
+            ens.run(callback=_cb)
+        except LoggedError:
+            raise
+        except Exception as e:
+            raise LoggedError(self.log, "%s", e) from e
+        self.n_steps_raw = ens.n_steps_raw
+        self.converged = ens.converged
+        self.Rminus1_last = ens.Rminus1_last
+        for i, c in enumerate(ens.progress, start=1):
+            self.progress.loc[i] = [c.N, c.timestamp, c.acceptance_rate, c.Rminus1,
+                                    c.Rminus1_cl]
+        self._fill_collection()
+        self.write_checkpoint()
+        self.mpi_info("Sampling complete after %d accepted steps.",
+                      ens.last_summary["sum_rows"])
+
+    def n(self, burn_in=False):
+        return 0 if self._ens is None else self._ens.n()
+
+    def _fill_collection(self, skip_samples: float = 0.0):
+        """Materialise the (concatenated) chains as a real SampleCollection: a DataFrame
+        with exactly ``collection.columns`` assigned to ``_data``."""
+        data = self._ens.samples(skip_samples=skip_samples)
+        cols = list(self.collection.columns)
+        if data.shape[1] != len(cols):
+            raise LoggedError(self.log, "Engine row width %d does not match the collection's "
+                                        "%d columns", data.shape[1], len(cols))
+        self.collection._data = pd.DataFrame(data, columns=cols)
+        self.collection._cache_reset()
+        if self.output:
+            self.collection.out_update()
+
+    # ------------------------------------------------------------------ products
+    def samples(self, combined: bool = False, skip_samples: float = 0,
+                to_getdist: bool = False):
+        """mcmc.py:1092-1144: here all local chains are already concatenated."""
+        if to_getdist:
+            raise LoggedError(self.log, "to_getdist needs GetDist (not evaluated by the "
+                                        "ensemble engine yet).")
+        if skip_samples:
+            self._fill_collection(skip_samples)
+        return self.collection
+
+    def products(self, combined: bool = False, skip_samples: float = 0,
+                 to_getdist: bool = False) -> dict:
+        return {"sample": self.samples(combined, skip_samples, to_getdist),
+                "progress": self.progress}
+
+    def write_checkpoint(self):
+        """mcmc.py:1045-1078"""
+        if mpi.is_main_process() and self.output:
+            self.dump_covmat(remove_temperature_cov(self.proposer.get_covariance(),
+                                                    self.temperature))
+            info = {"sampler": {self.get_name(): {
+                "converged": bool(self.converged), "Rminus1_last": self.Rminus1_last,
+                "burn_in": 0, "mpi_size": mpi.get_mpi_size()}}}
+            yaml_dump_file(self.checkpoint_filename(), info, error_if_exists=False)
+
+    def converge_info_changed(self, old_info, new_info):
+        keys = ["Rminus1_stop", "Rminus1_cl_stop", "Rminus1_cl_level", "max_samples"]
+        return any(old_info.get(p) != new_info.get(p) for p in keys)
+
+    @classmethod
+    def output_files_regexps(cls, output, info=None, minimal=False):
+        import re
+
+        regexps = [output.collection_regexp(name=None)]
+        if minimal:
+            return [(r, None) for r in regexps]
+        regexps += [re.compile(output.prefix_regexp_str + re.escape(ext.lstrip(".")) + "$")
+                    for ext in [Extension.checkpoint, Extension.progress, Extension.covmat]]
+        return [(r, None) for r in regexps]
+
+    @classmethod
+    def get_version(cls):
+        return get_version()
+
+    @classmethod
+    def _get_desc(cls, info=None):
+        return ("Adaptive, speed-hierarchy-aware MCMC sampler (adapted from CosmoMC) "
+                r"\cite{Lewis:2002ah,Lewis:2013hha}, B200 ensemble engine.")
+
+
+mcmc = MCMC  # ``sampler: {cobaya_b200.plugin.mcmc: ...}`` also resolves
+
+
+def install_as_mcmc():
+    """Make ``sampler: mcmc`` resolve to the B200 engine: the internal lookup imports
+    ``cobaya.samplers.mcmc`` through ``importlib`` (tools.py:201), which honours
+    ``sys.modules``."""
+    import types
+
+    import cobaya.samplers.mcmc as ref  # the reference module (kept for its helpers)
+
+    mod = types.ModuleType("cobaya.samplers.mcmc")
+    mod.__dict__.update({k: v for k, v in ref.__dict__.items() if not k.startswith("__")})
+    mod.MCMC = MCMC
+    mod.mcmc = MCMC
+    mod.__package__ = "cobaya.samplers.mcmc"
+    mod.__path__ = getattr(ref, "__path__", [])
+    mod.__reference_module__ = ref
+    sys.modules["cobaya.samplers.mcmc"] = mod
+    return mod

@@ -109,8 +109,9 @@ def _oracle_rows(fm, seed, ids, x0, n, burn_in):
     return out
 
 
-@pytest.mark.parametrize("D,n_chains,n", [(8, 37, 300), (64, 16, 200)])
-def test_ensemble_matches_oracle(cuda_lib, D, n_chains, n):
+@pytest.mark.parametrize("policy", [0, 1])
+@pytest.mark.parametrize("D,n_chains,n", [(8, 37, 300), (64, 16, 200), (21, 9, 150)])
+def test_ensemble_matches_oracle(cuda_lib, D, n_chains, n, policy):
     """Many chains, global ids offset (as on rank>0), against the C oracle."""
     from cobaya_b200.flatmodel import FlatModel, synthetic_gaussian_cov
 
@@ -120,6 +121,7 @@ def test_ensemble_matches_oracle(cuda_lib, D, n_chains, n):
     x0 = rng.multivariate_normal(np.zeros(D), cov, size=n_chains)
     id0 = 1000
     eng = _engine(fm, n_chains, seed=77, chain_id0=id0, rows_cap=n)
+    eng.set_kernel_policy(policy)
     eng.set_state(x0)
     eng.advance(n)
     st = eng.get_state()
@@ -186,3 +188,76 @@ def test_single_chain_split_matches_reference_checkpoint(cuda_lib):
     np.testing.assert_allclose(res["Rminus1"], float(ck["Rminus1"]), rtol=1e-4)
     np.testing.assert_allclose(res["W"], ck["learned_cov"], rtol=1e-9)
     np.testing.assert_allclose(res["acceptance"], float(ck["acceptance"]), rtol=1e-12)
+
+
+def _mixed_model(D=10, seed=3, modes=2, thin=1):
+    """2 blocks with oversampling, 2-mode mixture with weights whose input order differs
+    from the block-sorted order (dense likelihood matrix in the DMMA path), one normal
+    prior, one periodic parameter."""
+    from cobaya_b200.flatmodel import FlatModel, LikeSpec
+
+    rng = np.random.default_rng(seed)
+    means, covs = [], []
+    for k in range(modes):
+        A = rng.standard_normal((D, 2 * D))
+        C = A @ A.T / (2 * D)
+        d = np.sqrt(np.diag(C))
+        s = 0.05 * (1 + rng.uniform(0, 1, D))
+        covs.append((C / d[:, None] / d[None, :]) * s[:, None] * s[None, :])
+        means.append(rng.uniform(-0.1, 0.1, D) + 0.15 * k)
+    idx = rng.permutation(D)
+    lk = LikeSpec.gaussian_mixture(idx, np.array(means), np.array(covs),
+                                   weights=None if modes == 1 else rng.uniform(0.5, 1, modes),
+                                   name="gm")
+    kind = np.zeros(D, np.int32); kind[2] = 1
+    lower = np.full(D, -1.0); upper = np.full(D, 1.0)
+    lower[2], upper[2] = -np.inf, np.inf
+    periodic = np.zeros(D, np.int32); periodic[5] = 1
+    lower[5], upper[5] = -0.3, 0.3
+    loc = np.zeros(D); sc = np.ones(D); sc[2] = 0.4
+    blocks = [[7, 0, 3], [1, 2, 4, 5, 6, 8, 9][: D - 3]]
+    prop = np.diag(np.full(D, 0.05**2))
+    prop[0, 1] = prop[1, 0] = 0.3 * 0.05**2
+    return FlatModel(names=[f"p{i}" for i in range(D)], prior_kind=kind, lower=lower,
+                     upper=upper, loc=loc, pscale=sc, periodic=periodic, likes=[lk],
+                     blocks=blocks, oversampling=[1, 2], proposal_cov=prop, temperature=1.5,
+                     output_thin=thin)
+
+
+@pytest.mark.parametrize("policy", [0, 1])
+@pytest.mark.parametrize("modes,thin", [(1, 1), (2, 3)])
+def test_general_and_dmma_paths_match_oracle(cuda_lib, policy, modes, thin):
+    """The same model through the general (warp-per-chain) and the DMMA step kernels,
+    both against the oracle; blocks, mixture, normal/periodic priors, thinning, burn-in."""
+    fm = _mixed_model(modes=modes, thin=thin)
+    C, n = 19, 400
+    rng = np.random.default_rng(8)
+    x0 = rng.uniform(-0.05, 0.05, (C, fm.D))
+    eng = _engine(fm, C, seed=21, chain_id0=300, rows_cap=n, burn_in=3)
+    eng.set_kernel_policy(policy)
+    eng.set_state(x0)
+    for k in (3, 50, 347):
+        eng.advance(k)
+    assert eng.last_step_kernel() == (1 if policy == 0 else 0)
+    st = eng.get_state()
+    assert not st["flags"].any()
+    ref = _oracle_rows(fm, 21, range(300, 300 + C), x0, n, 3)
+    for c in range(C):
+        rc, rows_ref, s_ref = ref[c]
+        rows = eng.rows(c)
+        assert rows.shape == rows_ref.shape, f"chain {c}"
+        np.testing.assert_array_equal(rows[:, 0], rows_ref[:, 0])
+        np.testing.assert_allclose(rows, rows_ref, rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(st["x"][c], s_ref["x"], rtol=RTOL, atol=ATOL)
+        assert st["weight"][c] == s_ref["weight"]
+
+
+def test_dmma_path_is_used_for_headline_config(cuda_lib):
+    from cobaya_b200.flatmodel import FlatModel, synthetic_gaussian_cov
+
+    cov = synthetic_gaussian_cov(64)
+    fm = FlatModel.gaussian(np.zeros(64), cov, proposal_cov=cov)
+    eng = _engine(fm, 8, seed=1, rows_cap=64)
+    eng.set_state(np.zeros((8, 64)))
+    eng.advance(64)
+    assert eng.last_step_kernel() == 1
