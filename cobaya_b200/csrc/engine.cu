@@ -90,6 +90,7 @@ struct cb2_engine {
         d_perm_scratch;
     DevBuf<double> d_basis[CB2_MAX_BLOCKS];
     DevBuf<double> d_basis_scratch;
+    DevBuf<double2> d_draws;
     // ---- moments
     DevBuf<MomentTask> d_tasks;
     DevBuf<double> d_means, d_sw, d_partials, d_mom_out, d_shift;
@@ -226,7 +227,7 @@ extern "C" int cb2_destroy(cb2_engine *h) {
     h->d_tape_main.release(); h->d_tape_slow.release(); h->d_tape_fast.release();
     h->d_perm_scratch.release();
     for (int b = 0; b < CB2_MAX_BLOCKS; ++b) h->d_basis[b].release();
-    h->d_basis_scratch.release(); h->d_tasks.release(); h->d_means.release();
+    h->d_basis_scratch.release(); h->d_draws.release(); h->d_tasks.release(); h->d_means.release();
     h->d_sw.release(); h->d_partials.release(); h->d_mom_out.release(); h->d_shift.release();
     h->d_summary.release(); h->d_tmp.release();
     cudaEventDestroy(h->ev0);
@@ -822,10 +823,19 @@ extern "C" int cb2_advance(cb2_engine *h, int64_t n_proposals) {
                 W.cnt[b] = cnt;
             }
         }
+        if (fast_ok) {
+            CK(h, h->d_draws.ensure((size_t)C * w));
+            h->prof_begin(PROF_TAPE);
+            if (launch_draws(h->stream, h->M, W, C, (uint64_t)h->steps_done, w, h->d_draws.p))
+                FAIL(h, -2, "draws kernel launch failed");
+            h->prof_end();
+            h->launches++;
+        }
         h->prof_begin(PROF_STEP);
         if (fast_ok) {
             if ((rc = launch_step_fast(h->stream, h->M, h->S, W, h->d_fastpack.p, h->fast_desc,
-                                       C, (uint64_t)h->steps_done, w, h->sm_count))) {
+                                       h->d_draws.p, C, (uint64_t)h->steps_done, w,
+                                       h->sm_count))) {
                 FAIL(h, -2, "fast step kernel launch failed (%d)", rc);
             }
             h->last_kernel = 1;
@@ -926,23 +936,43 @@ extern "C" int cb2_moments(cb2_engine *h, int32_t mode, int32_t split, const dou
     const int64_t n_mean_tasks = n_tasks + (mode == CB2_MOMENTS_SINGLE_SPLIT ? 1 : 0);
     CK(h, h->d_means.ensure((size_t)n_mean_tasks * D));
     CK(h, h->d_sw.ensure(n_mean_tasks));
-    {
-        int warps = 4, grid = (int)((n_mean_tasks + warps - 1) / warps);
-        k_task_means<<<grid, warps * 32, 0, h->stream>>>(h->d_rows.p, h->rows_cap, W, D,
-                                                         h->d_tasks.p, n_mean_tasks,
-                                                         h->d_means.p, h->d_sw.p);
-        h->launches++;
-    }
-    int nt = 256;
-    int per = (DD + nt - 1) / nt;
-    int grid = (int)std::min<int64_t>(n_tasks, 2 * h->sm_count);
+    int grid = (int)std::min<int64_t>(n_tasks, 4 * h->sm_count);
     CK(h, h->d_partials.ensure((size_t)grid * len));
     CK(h, h->d_mom_out.ensure(len));
-    if (per <= 1) launch_accumulate<1>(h, grid, nt, n_tasks);
-    else if (per <= 4) launch_accumulate<4>(h, grid, nt, n_tasks);
-    else if (per <= 16) launch_accumulate<16>(h, grid, nt, n_tasks);
-    else launch_accumulate<0>(h, grid, nt, n_tasks);
-    h->launches++;
+    const bool dmma_ok = (D <= 64) && (h->policy == 0);
+    if (dmma_ok) {
+        // proposal-covariance SYRK on the FP64 tensor pipe (one pass over the rows)
+        const int NT = (D + 7) / 8;
+#define CB2_MM(N)                                                                          \
+    case N:                                                                                \
+        k_task_moments_dmma<N><<<grid, N * 32, 0, h->stream>>>(                            \
+            h->d_rows.p, h->rows_cap, W, D, h->d_tasks.p, n_tasks, h->d_shift.p,           \
+            h->d_partials.p, nullptr);                                                     \
+        break;
+        switch (NT) { CB2_MM(1) CB2_MM(2) CB2_MM(3) CB2_MM(4) CB2_MM(5) CB2_MM(6) CB2_MM(7) CB2_MM(8) }
+#undef CB2_MM
+        h->launches++;
+        if (mode == CB2_MOMENTS_SINGLE_SPLIT) {  // sw of the acceptance task only
+            k_task_means<<<1, 32, 0, h->stream>>>(h->d_rows.p, h->rows_cap, W, D,
+                                                  h->d_tasks.p + n_tasks, 1,
+                                                  h->d_means.p + (size_t)n_tasks * D,
+                                                  h->d_sw.p + n_tasks);
+            h->launches++;
+        }
+    } else {
+        int warps = 4, gridm = (int)((n_mean_tasks + warps - 1) / warps);
+        k_task_means<<<gridm, warps * 32, 0, h->stream>>>(h->d_rows.p, h->rows_cap, W, D,
+                                                          h->d_tasks.p, n_mean_tasks,
+                                                          h->d_means.p, h->d_sw.p);
+        h->launches++;
+        int nt = 256;
+        int per = (DD + nt - 1) / nt;
+        if (per <= 1) launch_accumulate<1>(h, grid, nt, n_tasks);
+        else if (per <= 4) launch_accumulate<4>(h, grid, nt, n_tasks);
+        else if (per <= 16) launch_accumulate<16>(h, grid, nt, n_tasks);
+        else launch_accumulate<0>(h, grid, nt, n_tasks);
+        h->launches++;
+    }
     CK(h, cudaGetLastError());
     double *out = dev_out ? dev_out : h->d_mom_out.p;
     k_reduce_partials<<<(len + 255) / 256, 256, 0, h->stream>>>(h->d_partials.p, grid, len, out);

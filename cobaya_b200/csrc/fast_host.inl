@@ -70,6 +70,9 @@ static int pack_fast(cb2_engine *h) {
         pk[P.off_c0 + km] = L.c0[km];
         pk[P.off_w + km] = L.w[km];
     }
+    // flags / i_of_j are stored as int32 inside the (double) pack
+    int32_t *iflags = reinterpret_cast<int32_t *>(pk.data() + P.off_flags);
+    int32_t *iiofj = reinterpret_cast<int32_t *>(pk.data() + P.off_iofj);
     for (int j = 0; j < DP; ++j) {
         if (j < D) {
             const int i = h->i_of_j[j];
@@ -79,14 +82,14 @@ static int pack_fast(cb2_engine *h) {
             pk[P.off_isc + j] = h->pscale[i];
             pk[P.off_mls + j] = (h->prior_kind[i] == 1)
                                     ? (-std::log(h->pscale[i]) - CB2_LOG_2PI / 2) : 0.0;
-            pk[P.off_flags + j] = (double)((h->prior_kind[i] == 1 ? 1 : 0) |
-                                           (h->periodic[i] ? 2 : 0));
-            pk[P.off_iofj + j] = (double)i;
+            iflags[j] = (h->prior_kind[i] == 1 ? 1 : 0) | (h->periodic[i] ? 2 : 0);
+            iiofj[j] = i;
         } else {
             pk[P.off_lower + j] = -INFINITY;
             pk[P.off_upper + j] = INFINITY;
             pk[P.off_isc + j] = 1.0;
-            pk[P.off_iofj + j] = -1.0;
+            iflags[j] = 0;
+            iiofj[j] = -1;
         }
     }
     int rc = upload(h, h->d_fastpack, pk);

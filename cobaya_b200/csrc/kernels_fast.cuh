@@ -36,47 +36,59 @@ k_basis_fast(uint32_t key0, uint32_t key1, uint64_t chain_id0, int block, int n,
     const uint64_t gid = chain_id0 + (uint64_t)chain;
     for (int e = tid; e < NP * NP; e += nt) X[e] = 0.0;
     __syncthreads();
-    // 1. standard normals (functions.py:36) scattered into the padded layout
+    // 1. standard normals (functions.py:36) scattered into the padded layout:
+    //    normal q = ix(m) + i with ix(m) = m*n - m(m-1)/2 goes to X[m][m+i]
     const int nn = (n + 2) * (n - 1) / 2;
-    for (int p = tid; p < (nn + 1) / 2; p += nt) {
-        double z[2];
-        draw_normal_pair(key0, key1, gid, block, epoch, (uint32_t)p, z[0], z[1]);
+    {
+        int m = 0, base = 0;  // base = ix(m); q only grows for a thread
+        for (int p = tid; p < (nn + 1) / 2; p += nt) {
+            double z[2];
+            draw_normal_pair(key0, key1, gid, block, epoch, (uint32_t)p, z[0], z[1]);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            int q = 2 * p + h;
-            if (q < nn) {
-                // q = ix(m) + i, ix(m) = m*n - m(m-1)/2, 0 <= i < n-m
-                double b = 2.0 * n + 1.0;
-                int m = (int)floor((b - sqrt(b * b - 8.0 * q)) * 0.5);
-                if (m > n - 2) m = n - 2;
-                while (m > 0 && m * n - (m * (m - 1)) / 2 > q) --m;
-                while ((m + 1) * n - ((m + 1) * m) / 2 <= q) ++m;
-                int i = q - (m * n - (m * (m - 1)) / 2);
-                X[m * NP + m + i] = z[h];
+            for (int h = 0; h < 2; ++h) {
+                const int q = 2 * p + h;
+                if (q < nn) {
+                    while (q >= base + (n - m)) {
+                        base += n - m;
+                        ++m;
+                    }
+                    X[m * NP + m + (q - base)] = z[h];
+                }
             }
         }
     }
     __syncthreads();
-    // 2. Householder vectors (functions.py:49-55)
+    // 2. Householder vectors (functions.py:49-55): norms by one thread per vector, the
+    //    rescaling x /= sc by all threads
+    double *inv = Dv + NP;  // [NP] 1/sc_m
     if (tid < n - 1) {
         const int m = tid, len = n - m;
-        double *x = X + m * NP + m;
-        double norm2 = 0.0;
-        for (int i = 0; i < len; ++i) norm2 += x[i] * x[i];
-        double x0 = x[0];
-        double d = (x0 != 0.0) ? (x0 > 0 ? 1.0 : -1.0) : 1.0;
-        double x0n = x0 + d * sqrt(norm2);
-        x[0] = x0n;
-        double sc = sqrt((norm2 - x0 * x0 + x0n * x0n) / 2.0);
-        for (int i = 0; i < len; ++i) x[i] /= sc;
+        const double *x = X + m * NP + m;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int i = 0;
+        for (; i + 4 <= len; i += 4) {
+            s0 = fma(x[i], x[i], s0);
+            s1 = fma(x[i + 1], x[i + 1], s1);
+            s2 = fma(x[i + 2], x[i + 2], s2);
+            s3 = fma(x[i + 3], x[i + 3], s3);
+        }
+        for (; i < len; ++i) s0 = fma(x[i], x[i], s0);
+        const double norm2 = (s0 + s1) + (s2 + s3);
+        const double x0 = x[0];
+        const double d = (x0 != 0.0) ? (x0 > 0 ? 1.0 : -1.0) : 1.0;
+        const double x0n = x0 + d * sqrt(norm2);
+        X[m * NP + m] = x0n;
+        inv[m] = 1.0 / sqrt((norm2 - x0 * x0 + x0n * x0n) / 2.0);
         Dv[m] = d;
     }
     __syncthreads();
+    for (int e = tid; e < (n - 1) * NP; e += nt) X[e] *= inv[e / NP];
     if (tid == 0) {  // functions.py:59
         double prod = 1.0;
         for (int m = 0; m < n - 1; ++m) prod *= Dv[m];
         Dv[n - 1] = (((n - 1) & 1) ? -1.0 : 1.0) * prod;
     }
+    __syncthreads();
     // 3. H = I; for m: H[:, m:] -= (H[:, m:] x_m) x_m^T  (functions.py:57-58); row r here
     const int r = tid;
     double h[NP];
@@ -123,7 +135,7 @@ static int launch_basis_fast_t(cudaStream_t st, uint32_t k0, uint32_t k1, uint64
                                int64_t task0, int64_t store_task0) {
     constexpr int NP = NG * 8;
     const int threads = NP < 32 ? 32 : NP;
-    const size_t smem = (size_t)(NP * NP + NP) * sizeof(double);
+    const size_t smem = (size_t)(NP * NP + 2 * NP) * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(k_basis_fast<NG>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return -1;
@@ -220,10 +232,32 @@ __device__ __forceinline__ void warp_matvec8(const double *__restrict__ frag, in
     }
 }
 
+// Proposal-side randomness of a window, generated ahead of the serial accept chain:
+// draws[(chain*len + s)] = { r (signed for 1-parameter blocks), Exp(1) of the accept test }
+// (proposal.py:71-93, mcmc.py:683).  None of it depends on the chain state.
+__global__ void k_draws(ModelDev M, const uint8_t *__restrict__ tape, int tape_len,
+                        int64_t tape_base, uint8_t const_b, int64_t n_chains, uint64_t t0,
+                        int n_steps, double2 *__restrict__ draws) {
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= n_chains * n_steps) return;
+    const int64_t chain = e / n_steps;
+    const int s = (int)(e % n_steps);
+    const uint64_t t = t0 + (uint64_t)s;
+    const uint64_t gid = M.chain_id0 + (uint64_t)chain;
+    const int b = tape ? tape[chain * tape_len + (int64_t)(t - tape_base)] : const_b;
+    double r, sign;
+    draw_radial(M, gid, t, 0, M.bsize[b], r, sign);
+    double2 o;
+    o.x = (M.bsize[b] >= 2) ? r : sign * r;
+    o.y = draw_accept_exp(M, gid, t, 0);
+    draws[e] = o;
+}
+
 template <int NT>
 __global__ void __launch_bounds__(256, 1)
 k_step_fast(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gpack,
-            FastPackDesc P, int64_t n_chains, uint64_t t0, int n_steps) {
+            FastPackDesc P, const double2 *__restrict__ draws, int64_t n_chains, uint64_t t0,
+            int n_steps) {
     constexpr int DP = NT * 8;
     extern __shared__ __align__(16) double fsm[];
     __shared__ __align__(8) unsigned long long mbar;
@@ -259,76 +293,116 @@ k_step_fast(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gp
                 : "memory");
         }
     }
-    // per-warp scratch after the pack: visit counters [8 chains][NB] (int32)
-    int *svis = reinterpret_cast<int *>(fsm + P.total) + wid * 8 * CB2_MAX_BLOCKS;
+    // per-warp scratch after the pack: relative visit counters [8 chains][NB] (int32)
+    int *svis = reinterpret_cast<int *>(fsm + P.total) + wid * 8 * 3 * CB2_MAX_BLOCKS;
 
     const int q = lane >> 2, r = lane & 3;
     const int64_t tile = blockIdx.x * (int64_t)nwarps + wid;
     const int64_t chain_raw = tile * 8 + q;
     const bool active = chain_raw < n_chains;
     const int64_t chain = active ? chain_raw : (n_chains - 1);
-    const uint64_t gid = M.chain_id0 + (uint64_t)chain;
     const int D = M.D, NB = M.n_blocks, NV = NB + 1;
     const double *Tf = pack + P.off_T, *Af = pack + P.off_A;
     const double *lower = pack + P.off_lower, *upper = pack + P.off_upper;
-    const double *iofj = pack + P.off_iofj, *pflags = pack + P.off_flags;
+    const int *iofj = reinterpret_cast<const int *>(pack + P.off_iofj);
+    const int *pflag = reinterpret_cast<const int *>(pack + P.off_flags);
 
     // ---- load chain state (sorted coordinates): element j = 8n + 2r + h
     double xs[NT][2];
+    uint32_t m_norm = 0, m_per = 0;  // bit (2n+h): normal prior / periodic
 #pragma unroll
     for (int n = 0; n < NT; ++n)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            int i = (int)iofj[8 * n + 2 * r + h];
+            const int j = 8 * n + 2 * r + h;
+            const int i = iofj[j];
             xs[n][h] = (i >= 0) ? S.x[chain * D + i] : 0.0;
+            const int fl = pflag[j];
+            m_norm |= (uint32_t)(fl & 1) << (2 * n + h);
+            m_per |= (uint32_t)((fl >> 1) & 1) << (2 * n + h);
         }
     double logpost = S.logpost[chain], logprior = S.logprior[chain], loglike = S.ll[chain];
     long long weight = S.weight[chain], prior_rej = S.prior_rej[chain],
               burn_left = S.burn_left[chain], added_w = S.added_w[chain],
               n_rows = S.n_rows[chain], n_acc = S.n_acc[chain];
     uint32_t flags = S.flags[chain];
+    // per chain and block: {k = visit % n_b, basis slot, visits in this window}
+    int *sv = svis + q * (3 * CB2_MAX_BLOCKS);
     if (r == 0)
-        for (int b = 0; b < NB; ++b) svis[q * CB2_MAX_BLOCKS + b] = 0;
+        for (int b = 0; b < NB; ++b) {
+            sv[3 * b + 0] = (int)(S.vis[chain * NV + b] % M.bsize[b]);
+            sv[3 * b + 1] = 0;
+            sv[3 * b + 2] = 0;
+        }
     __syncwarp();
-    const bool any_per = M.any_periodic, any_norm = M.any_normal;
+    const bool any_special = M.any_periodic || M.any_normal;
+    const double2 *my_draws = draws + chain * (int64_t)n_steps;
+    const double inv_T = M.temperature;
 
-    for (int s = 0; s < n_steps; ++s) {
+    // direction of a step: which block, where its basis row lives (state independent)
+    auto locate = [&](int s, int &nb, int &j0, const double *&Rk) {
         const uint64_t t = t0 + (uint64_t)s;
         const int b = W.tape_main ? W.tape_main[chain * W.len_main + (int64_t)(t - W.base_main)]
                                   : W.const_main;
-        const int nb = M.bsize[b], j0 = M.jstart[b];
-        // ---- direction + radius (proposal.py:59-93)
-        double rad, sign;
-        draw_radial(M, gid, t, 0, nb, rad, sign);
-        double v[NT][2];
+        nb = M.bsize[b];
+        j0 = M.jstart[b];
+        const int k = sv[3 * b + 0];
+        int slot = sv[3 * b + 1];
+        const int cnt = sv[3 * b + 2];
+        Rk = nullptr;
         if (nb >= 2) {
-            const int vrel = svis[q * CB2_MAX_BLOCKS + b];
-            const long long vstart = S.vis[chain * NV + b];
-            const long long vabs = vstart + vrel;
-            long long slot = vabs / nb - vstart / nb;
-            const int k = (int)(vabs % nb);
-            if (slot < 0 || slot >= W.cnt[b]) {
+            if (slot >= W.cnt[b]) {
                 flags |= CB2_FLAG_INTERNAL;
                 slot = 0;
             }
-            const double *Rk = W.basis[b] + (((size_t)chain * W.cnt[b] + slot) * nb + k) * nb;
-            const double rs = rad;
-#pragma unroll
-            for (int n = 0; n < NT; ++n)
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int j = 8 * n + 2 * r + h - j0;
-                    v[n][h] = (j >= 0 && j < nb) ? Rk[j] * rs * M.proposal_scale : 0.0;
-                }
-        } else {
-            const double val = (sign > 0) ? rad * M.proposal_scale : -(rad * M.proposal_scale);
-#pragma unroll
-            for (int n = 0; n < NT; ++n)
-#pragma unroll
-                for (int h = 0; h < 2; ++h) v[n][h] = (8 * n + 2 * r + h == j0) ? val : 0.0;
+            Rk = W.basis[b] + ((size_t)(chain * W.cnt[b] + slot) * nb + k) * (size_t)nb;
         }
         __syncwarp();
-        if (r == 0) svis[q * CB2_MAX_BLOCKS + b] += 1;
+        if (r == 0) {
+            const bool wrap = (k + 1 == nb);
+            sv[3 * b + 0] = wrap ? 0 : k + 1;
+            sv[3 * b + 1] = sv[3 * b + 1] + (wrap ? 1 : 0);
+            sv[3 * b + 2] = cnt + 1;
+        }
+        __syncwarp();
+    };
+    auto fetch = [&](int nb, int j0, const double *Rk, double (&u)[NT][2]) {
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = 8 * n + 2 * r + h - j0;
+                if (nb >= 2) u[n][h] = (j >= 0 && j < nb) ? Rk[j] : 0.0;
+                else u[n][h] = (j == 0) ? 1.0 : 0.0;
+            }
+    };
+
+    // software pipeline: the direction and draws of step s+1 are loaded during step s
+    double un[NT][2];
+    double2 dn;
+    {
+        int nb, j0;
+        const double *Rk;
+        locate(0, nb, j0, Rk);
+        fetch(nb, j0, Rk, un);
+        dn = my_draws[0];
+    }
+    for (int s = 0; s < n_steps; ++s) {
+        // ---- v = R[:,k] * r * scale (proposal.py:69) / +-r*scale (:86-93)
+        double v[NT][2];
+        const double rs = dn.x, e_acc = dn.y;
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+            v[n][0] = un[n][0] * rs * M.proposal_scale;
+            v[n][1] = un[n][1] * rs * M.proposal_scale;
+        }
+        if (s + 1 < n_steps) {  // prefetch (independent of the accept chain)
+            int nb, j0;
+            const double *Rk;
+            locate(s + 1, nb, j0, Rk);
+            fetch(nb, j0, Rk, un);
+            dn = my_draws[s + 1];
+        }
         // ---- trial = x + T v  (proposal.py:224) on the FP64 tensor pipe
         double xt[NT][2];
 #pragma unroll
@@ -340,36 +414,38 @@ k_step_fast(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gp
         bool bad = false;
         double ps = 0.0;
 #pragma unroll
-        for (int n = 0; n < NT; ++n)
+        for (int n = 0; n < NT; ++n) {
+            const double2 lo2 = *reinterpret_cast<const double2 *>(lower + 8 * n + 2 * r);
+            const double2 up2 = *reinterpret_cast<const double2 *>(upper + 8 * n + 2 * r);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const int j = 8 * n + 2 * r + h;
                 double xv = xt[n][h];
-                const double lo = lower[j], up = upper[j];
-                if (any_per || any_norm) {
-                    const int fl = (int)pflags[j];
-                    if (fl & 2) {
+                const double lo = h ? lo2.y : lo2.x, up = h ? up2.y : up2.x;
+                if (any_special) {
+                    const int j = 8 * n + 2 * r + h;
+                    if ((m_per >> (2 * n + h)) & 1u) {
                         double qq = (xv - lo) / (up - lo);
                         qq = qq - floor(qq);
                         xv = qq * (up - lo) + lo;
                         xt[n][h] = xv;
                     }
-                    if (fl & 1) {
+                    if ((m_norm >> (2 * n + h)) & 1u) {
                         const double zz = (xv - pack[P.off_loc + j]) / pack[P.off_isc + j];
                         ps += pack[P.off_mls + j] - zz * zz / 2;
                     }
                 }
                 if (!(xv <= up) || !(xv >= lo) || !isfinite(xv)) bad = true;
             }
+        }
         bad = __shfl_xor_sync(0xffffffffu, (int)bad, 1) | (int)bad;
         bad = __shfl_xor_sync(0xffffffffu, (int)bad, 2) | (int)bad;
         double t_prior, t_like = 0.0, t_post;
-        if (any_norm) ps = quad_sum(ps);
+        if (M.any_normal) ps = quad_sum(ps);
         t_prior = bad ? -CUDART_INF : (M.uniform_logp + ps);
         // ---- GaussianMixture.logp (gaussian_mixture.py:138-163); computed for every chain
         // of the warp (the MMA is warp-wide), discarded where the prior is -inf
         {
-            double lpk[4];
+            double lp0 = 0.0, lp1 = 0.0, lp2 = 0.0, lp3 = 0.0;
             for (int km = 0; km < P.n_modes; ++km) {
                 const double *mu = pack + P.off_mu + km * DP;
                 double z[NT][2], y[NT][2];
@@ -388,17 +464,22 @@ k_step_fast(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gp
 #pragma unroll
                 for (int n = 0; n < NT; ++n) qsum += y[n][0] * y[n][0] + y[n][1] * y[n][1];
                 qsum = quad_sum(qsum);
-                lpk[km] = -0.5 * (pack[P.off_c0 + km] + qsum);
+                const double lp = -0.5 * (pack[P.off_c0 + km] + qsum);
+                if (km == 0) lp0 = lp; else if (km == 1) lp1 = lp; else if (km == 2) lp2 = lp; else lp3 = lp;
             }
-            if (P.n_modes == 1) t_like = lpk[0];
+            if (P.n_modes == 1) t_like = lp0;
             else {
-                double mx = lpk[0];
-                for (int km = 1; km < P.n_modes; ++km) mx = fmax(mx, lpk[km]);
+                const int nm = P.n_modes;
+                double mx = lp0;
+                if (nm > 1) mx = fmax(mx, lp1);
+                if (nm > 2) mx = fmax(mx, lp2);
+                if (nm > 3) mx = fmax(mx, lp3);
                 if (mx == -CUDART_INF) t_like = -CUDART_INF;
                 else {
-                    double acc = 0.0;
-                    for (int km = 0; km < P.n_modes; ++km)
-                        acc += pack[P.off_w + km] * exp(lpk[km] - mx);
+                    double acc = pack[P.off_w] * exp(lp0 - mx);
+                    if (nm > 1) acc += pack[P.off_w + 1] * exp(lp1 - mx);
+                    if (nm > 2) acc += pack[P.off_w + 2] * exp(lp2 - mx);
+                    if (nm > 3) acc += pack[P.off_w + 3] * exp(lp3 - mx);
                     t_like = log(acc) + mx;
                 }
             }
@@ -408,7 +489,7 @@ k_step_fast(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gp
         bool acc;
         if (t_post == -CUDART_INF) acc = false;
         else if (t_post > logpost) acc = true;
-        else acc = draw_accept_exp(M, gid, t, 0) > (logpost - t_post) / M.temperature;
+        else acc = e_acc > (logpost - t_post) / inv_T;
         // ---- process_accept_or_reject (mcmc.py:685-748)
         if (acc) {
             if (burn_left <= 0) {
@@ -440,7 +521,7 @@ k_step_fast(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gp
                             for (int n = 0; n < NT; ++n)
 #pragma unroll
                                 for (int h = 0; h < 2; ++h) {
-                                    const int i = (int)iofj[8 * n + 2 * r + h];
+                                    const int i = iofj[8 * n + 2 * r + h];
                                     if (i >= 0) row[2 + i] = xs[n][h];
                                 }
                         }
@@ -466,7 +547,7 @@ k_step_fast(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gp
         for (int n = 0; n < NT; ++n)
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const int i = (int)iofj[8 * n + 2 * r + h];
+                const int i = iofj[8 * n + 2 * r + h];
                 if (i >= 0) S.x[chain * D + i] = xs[n][h];
             }
         if (r == 0) {
@@ -474,7 +555,7 @@ k_step_fast(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gp
             S.weight[chain] = weight; S.prior_rej[chain] = prior_rej;
             S.burn_left[chain] = burn_left; S.added_w[chain] = added_w;
             S.n_rows[chain] = n_rows; S.n_acc[chain] = n_acc; S.flags[chain] = flags;
-            for (int b = 0; b < NB; ++b) S.vis[chain * NV + b] += svis[q * CB2_MAX_BLOCKS + b];
+            for (int b = 0; b < NB; ++b) S.vis[chain * NV + b] += sv[3 * b + 2];
         }
     }
 }
@@ -482,28 +563,41 @@ k_step_fast(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gp
 template <int NT>
 static int launch_step_fast_t(cudaStream_t st, const ModelDev &M, const ChainState &S,
                               const WindowDev &W, const double *gpack, const FastPackDesc &P,
-                              int64_t n_chains, uint64_t t0, int n_steps, int sm_count) {
+                              const double2 *draws, int64_t n_chains, uint64_t t0, int n_steps,
+                              int sm_count) {
     const int64_t tiles = (n_chains + 7) / 8;
     int wpc = (int)((tiles + sm_count - 1) / sm_count);
     if (wpc < 1) wpc = 1;
     if (wpc > 8) wpc = 8;
     const int grid = (int)((tiles + wpc - 1) / wpc);
-    const size_t smem = (size_t)P.total * 8 + (size_t)wpc * 8 * CB2_MAX_BLOCKS * sizeof(int);
+    const size_t smem = (size_t)P.total * 8 + (size_t)wpc * 8 * 3 * CB2_MAX_BLOCKS * sizeof(int);
     if (smem > 200 * 1024) return -2;
     if (cudaFuncSetAttribute(k_step_fast<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)smem) != cudaSuccess)
         return -1;
-    k_step_fast<NT><<<grid, wpc * 32, smem, st>>>(M, S, W, gpack, P, n_chains, t0, n_steps);
+    k_step_fast<NT><<<grid, wpc * 32, smem, st>>>(M, S, W, gpack, P, draws, n_chains, t0,
+                                                  n_steps);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+static inline int launch_draws(cudaStream_t st, const ModelDev &M, const WindowDev &W,
+                               int64_t n_chains, uint64_t t0, int n_steps, double2 *draws) {
+    const int64_t tot = n_chains * n_steps;
+    const int bs = 256;
+    k_draws<<<(unsigned)((tot + bs - 1) / bs), bs, 0, st>>>(M, W.tape_main, W.len_main,
+                                                            W.base_main, W.const_main, n_chains,
+                                                            t0, n_steps, draws);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
 static inline int launch_step_fast(cudaStream_t st, const ModelDev &M, const ChainState &S,
                                    const WindowDev &W, const double *gpack,
-                                   const FastPackDesc &P, int64_t n_chains, uint64_t t0,
-                                   int n_steps, int sm_count) {
+                                   const FastPackDesc &P, const double2 *draws,
+                                   int64_t n_chains, uint64_t t0, int n_steps, int sm_count) {
 #define CB2_SF(N)                                                                       \
     case N:                                                                             \
-        return launch_step_fast_t<N>(st, M, S, W, gpack, P, n_chains, t0, n_steps, sm_count);
+        return launch_step_fast_t<N>(st, M, S, W, gpack, P, draws, n_chains, t0, n_steps,     \
+                                     sm_count);
     switch (P.NT) {
         CB2_SF(1) CB2_SF(2) CB2_SF(3) CB2_SF(4) CB2_SF(5) CB2_SF(6) CB2_SF(7) CB2_SF(8)
     }

@@ -187,3 +187,128 @@ __global__ void k_summary(const int64_t *__restrict__ n_rows, const int64_t *__r
         out[4] = s_full[0]; out[5] = s_int[0]; out[6] = s_acc[0]; out[7] = s_w[0];
     }
 }
+
+// =====================================================================================
+// DMMA checkpoint statistics (D <= 64): the proposal-covariance SYRK on the FP64 tensor
+// pipe.  One pass over rows [first,last) of every task: with xr = x - ref (ref = first row
+// of the window, removes the cancellation of an uncentred sum)
+//     sw = sum w,  S1 = sum w xr,  S2 = sum w xr xr^T   (m8n8k4 tiles, K = rows)
+//     m = ref + S1/sw,  C = S2/sw - (S1/sw)(S1/sw)^T          (== np.cov(ddof=0, fweights))
+// then the same CTA-level partial sums as k_task_accumulate.  NT warps per CTA, warp w owns
+// output rows 8w..8w+7 (all NT column tiles) in MMA C-fragment layout.
+// =====================================================================================
+#define CB2_MOM_BATCH 32
+
+__device__ __forceinline__ void mom_dmma(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT * 32)
+k_task_moments_dmma(const double *__restrict__ rows, int64_t cap, int width, int D,
+                    const MomentTask *__restrict__ tasks, int64_t n_tasks,
+                    const double *__restrict__ shift, double *__restrict__ partials,
+                    double *__restrict__ sw_out) {
+    constexpr int DP = NT * 8;
+    constexpr int LDX = DP + 4;                    // padded row stride (bank spread)
+    __shared__ double xt[CB2_MOM_BATCH][LDX];      // xr of the current batch
+    __shared__ double wt[CB2_MOM_BATCH];           // weights
+    __shared__ double refv[DP], s1v[DP], mrel[DP], msv[DP];
+    __shared__ double sw_s;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
+    const int q = lane >> 2, r = lane & 3;
+    const int DD = D * D;
+    double *P = partials + (size_t)blockIdx.x * (size_t)(3 + D + 2 * DD);
+    double sc[NT][2], smm[NT][2];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) { sc[n][0] = sc[n][1] = smm[n][0] = smm[n][1] = 0.0; }
+    double accM = 0.0, accN = 0.0, accNa = 0.0, accm = 0.0;  // accm: thread d<D holds sum ms[d]
+    for (int64_t t = blockIdx.x; t < n_tasks; t += gridDim.x) {
+        const MomentTask T = tasks[t];
+        const double *base = rows + (size_t)T.chain * cap * width;
+        double s2[NT][2];
+#pragma unroll
+        for (int n = 0; n < NT; ++n) { s2[n][0] = 0.0; s2[n][1] = 0.0; }
+        double s1 = 0.0, swl = 0.0;
+        __syncthreads();
+        if (tid < DP) refv[tid] = (tid < D) ? base[(size_t)T.first * width + 2 + tid] : 0.0;
+        __syncthreads();
+        for (int64_t r0 = T.first; r0 < T.last; r0 += CB2_MOM_BATCH) {
+            const int nb = (int)min((int64_t)CB2_MOM_BATCH, T.last - r0);
+            __syncthreads();
+            for (int e = tid; e < CB2_MOM_BATCH * DP; e += nt) {
+                const int k = e / DP, d = e % DP;
+                double v = 0.0;
+                if (k < nb && d < D) v = base[(size_t)(r0 + k) * width + 2 + d] - refv[d];
+                xt[k][d] = v;
+            }
+            if (tid < CB2_MOM_BATCH) wt[tid] = (tid < nb) ? base[(size_t)(r0 + tid) * width] : 0.0;
+            __syncthreads();
+            if (tid < DP) {
+#pragma unroll 8
+                for (int k = 0; k < CB2_MOM_BATCH; ++k) s1 = fma(wt[k], xt[k][tid], s1);
+            }
+            if (tid == 0)
+                for (int k = 0; k < CB2_MOM_BATCH; ++k) swl += wt[k];
+            // S2[8w+q][8n+2r+{0,1}] += sum_k (w_k xr_k[8w+q]) * xr_k[8n+..]
+#pragma unroll
+            for (int kk = 0; kk < CB2_MOM_BATCH / 4; ++kk) {
+                const int k = 4 * kk + r;
+                const double a = wt[k] * xt[k][8 * wid + q];
+#pragma unroll
+                for (int n = 0; n < NT; ++n) mom_dmma(s2[n][0], s2[n][1], a, xt[k][8 * n + q]);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) sw_s = swl;
+        if (tid < DP) s1v[tid] = s1;
+        __syncthreads();
+        const double sw = sw_s;
+        if (tid < DP) {
+            const double mr = s1v[tid] / sw;
+            mrel[tid] = mr;
+            const double ms = (tid < D) ? (refv[tid] + mr) - (shift ? shift[tid] : 0.0) : 0.0;
+            msv[tid] = ms;
+            accm += ms;
+        }
+        __syncthreads();
+        const double f = T.N / sw;
+        const int i = 8 * wid + q;
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = 8 * n + 2 * r + h;
+                sc[n][h] += f * s2[n][h] - T.N * (mrel[i] * mrel[j]);
+                smm[n][h] += msv[i] * msv[j];
+            }
+        if (tid == 0) {
+            accM += 1.0;
+            accN += T.N;
+            accNa += T.N * ((double)(T.last - T.first) / sw);
+            if (sw_out) sw_out[t] = sw;
+        }
+    }
+    __syncthreads();
+    {
+        const int i = 8 * wid + q;
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = 8 * n + 2 * r + h;
+                if (i < D && j < D) {
+                    P[3 + D + i * D + j] = smm[n][h];
+                    P[3 + D + DD + i * D + j] = sc[n][h];
+                }
+            }
+    }
+    if (tid < D) P[3 + tid] = accm;
+    if (tid == 0) {
+        P[0] = accM;
+        P[1] = accN;
+        P[2] = accNa;
+    }
+}

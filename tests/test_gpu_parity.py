@@ -137,19 +137,21 @@ def test_ensemble_matches_oracle(cuda_lib, D, n_chains, n, policy):
         assert st["n_accepted"][c] == s_ref["n_accepted"]
 
 
-def test_moments_match_numpy(cuda_lib):
+@pytest.mark.parametrize("policy,D", [(0, 6), (1, 6), (0, 64), (0, 20)])
+def test_moments_match_numpy(cuda_lib, policy, D):
     """cb2_moments (multi-chain halves rule) vs SampleCollection.mean/cov arithmetic
     restated with numpy on the same rows, and R-1 to 1e-4 as BASELINE.json asks."""
     from cobaya_b200.convergence import rminus1_from_sums
     from cobaya_b200.flatmodel import FlatModel, synthetic_gaussian_cov
     from oracle import oracle as orc
 
-    D, C, n = 6, 24, 600
+    C, n = 24, 600
     cov = synthetic_gaussian_cov(D)
     fm = FlatModel.gaussian(np.full(D, 0.1), cov, proposal_cov=cov)
     rng = np.random.default_rng(2)
     x0 = 0.1 + rng.multivariate_normal(np.zeros(D), cov, size=C)
     eng = _engine(fm, C, seed=5, rows_cap=n)
+    eng.set_kernel_policy(policy)
     eng.set_state(x0)
     eng.advance(n)
     shift = np.full(D, 0.09)
