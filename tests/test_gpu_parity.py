@@ -263,3 +263,111 @@ def test_dmma_path_is_used_for_headline_config(cuda_lib):
     eng.set_state(np.zeros((8, 64)))
     eng.advance(64)
     assert eng.last_step_kernel() == 1
+
+
+# ---------------------------------------------------------------------------------------
+# The other BASELINE.json configurations as parity cases (engine vs oracle, few chains)
+# ---------------------------------------------------------------------------------------
+def _mixture_cov(D, rng, scale=0.02):
+    A = rng.standard_normal((D, 2 * D))
+    C = A @ A.T / (2 * D)
+    d = np.sqrt(np.diag(C))
+    s = scale * 10 ** rng.uniform(-0.5, 0.5, D)
+    return (C / d[:, None] / d[None, :]) * s[:, None] * s[None, :]
+
+
+def test_config3_128d_three_modes_two_speed_blocks(cuda_lib):
+    """configs[2]: 128-D, 3-mode mixture, two components of different speed -> two blocks
+    (params 0-31 slow, 32-127 fast, oversampling [1,3], oversample_thin)."""
+    from cobaya_b200.flatmodel import FlatModel, LikeSpec
+
+    rng = np.random.default_rng(20260925)
+    D, n_slow = 128, 32
+    like_a = LikeSpec.gaussian_mixture(
+        np.arange(n_slow), [np.full(n_slow, 0.3 * k) * 0.1 for k in range(3)],
+        [_mixture_cov(n_slow, rng) for _ in range(3)], name="slow")
+    like_b = LikeSpec.gaussian_mixture(
+        np.arange(n_slow, D), [np.full(D - n_slow, 0.3 * k) * 0.1 for k in range(3)],
+        [_mixture_cov(D - n_slow, rng) for _ in range(3)], name="fast")
+    blocks = [list(range(n_slow)), list(range(n_slow, D))]
+    cycle = n_slow + 3 * (D - n_slow)
+    thin = int(np.round(cycle / D))
+    prop = np.diag(np.full(D, 0.02**2))
+    fm = FlatModel(names=[f"x{i}" for i in range(D)], prior_kind=np.zeros(D, np.int32),
+                   lower=np.full(D, -1.0), upper=np.full(D, 1.0), loc=np.zeros(D),
+                   pscale=np.ones(D), periodic=np.zeros(D, np.int32), likes=[like_a, like_b],
+                   blocks=blocks, oversampling=[1, 3], proposal_cov=prop, output_thin=thin)
+    assert fm.cycle_length == 320 and thin == 2
+    C, n = 6, 700  # more than two proposal cycles
+    x0 = rng.normal(0, 0.01, (C, D))
+    eng = _engine(fm, C, seed=4, chain_id0=8192 * 7, rows_cap=n)
+    eng.set_state(x0)
+    eng.advance(333)
+    eng.advance(n - 333)
+    assert eng.last_step_kernel() == 0  # D > 64: general kernel
+    st = eng.get_state()
+    assert not st["flags"].any()
+    ref = _oracle_rows(fm, 4, range(8192 * 7, 8192 * 7 + C), x0, n, 0)
+    for c in range(C):
+        rc, rows_ref, s_ref = ref[c]
+        rows = eng.rows(c)
+        assert rows.shape == rows_ref.shape
+        np.testing.assert_array_equal(rows[:, 0], rows_ref[:, 0])
+        np.testing.assert_allclose(rows, rows_ref, rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(st["x"][c], s_ref["x"], rtol=RTOL, atol=ATOL)
+
+
+def test_config4_30d_rosenbrock_dragging(cuda_lib):
+    """configs[3]: 30-D Rosenbrock (builder-defined external-likelihood stand-in), manual
+    slow/fast blocking, drag: True."""
+    from cobaya_b200.flatmodel import FlatModel, LikeSpec
+
+    D, n_slow, o_fast = 30, 10, 4
+    lk = LikeSpec.rosenbrock(np.arange(D), scale=1.0 / 20.0)
+    n_drag = int(np.round(o_fast * (D - n_slow) / n_slow))
+    fm = FlatModel(names=[f"x{i}" for i in range(D)], prior_kind=np.zeros(D, np.int32),
+                   lower=np.full(D, -5.0), upper=np.full(D, 5.0), loc=np.zeros(D),
+                   pscale=np.ones(D), periodic=np.zeros(D, np.int32), likes=[lk],
+                   blocks=[list(range(n_slow)), list(range(n_slow, D))],
+                   oversampling=[1, o_fast], drag=True, i_last_slow_block=0,
+                   drag_interp_steps=n_drag, proposal_cov=np.diag(np.full(D, 0.05**2)))
+    C, n = 10, 120
+    rng = np.random.default_rng(1)
+    x0 = 1.0 + rng.normal(0, 0.05, (C, D))
+    eng = _engine(fm, C, seed=12, chain_id0=40, rows_cap=n)
+    eng.set_state(x0)
+    for k in (7, 13, 100):
+        eng.advance(k)
+    st = eng.get_state()
+    assert not st["flags"].any()
+    ref = _oracle_rows(fm, 12, range(40, 40 + C), x0, n, 0)
+    for c in range(C):
+        rc, rows_ref, s_ref = ref[c]
+        rows = eng.rows(c)
+        assert rows.shape == rows_ref.shape
+        np.testing.assert_array_equal(rows[:, 0], rows_ref[:, 0])
+        np.testing.assert_allclose(rows, rows_ref, rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(st["x"][c], s_ref["x"], rtol=RTOL, atol=ATOL)
+        assert st["weight"][c] == s_ref["weight"]
+
+
+@pytest.mark.parametrize("D,n", [(32, 200), (128, 260), (512, 40)])
+def test_config5_dimension_sweep_parity(cuda_lib, D, n):
+    """configs[4]: the D sweep as a parity case (single mode, one block)."""
+    from cobaya_b200.flatmodel import FlatModel, synthetic_gaussian_cov
+
+    cov = synthetic_gaussian_cov(D)
+    fm = FlatModel.gaussian(np.zeros(D), cov, proposal_cov=cov)
+    C = 5
+    x0 = np.random.default_rng(D).multivariate_normal(np.zeros(D), cov, size=C)
+    eng = _engine(fm, C, seed=D, chain_id0=3, rows_cap=n)
+    eng.set_state(x0)
+    eng.advance(n)
+    st = eng.get_state()
+    ref = _oracle_rows(fm, D, range(3, 3 + C), x0, n, 0)
+    for c in range(C):
+        rc, rows_ref, s_ref = ref[c]
+        rows = eng.rows(c)
+        assert rows.shape == rows_ref.shape
+        np.testing.assert_allclose(rows, rows_ref, rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(st["x"][c], s_ref["x"], rtol=RTOL, atol=ATOL)

@@ -95,9 +95,9 @@ def test_64d_ensemble_learns_covmat_and_converges(cuda_lib):
     cov = synthetic_gaussian_cov(D)
     fm = FlatModel.gaussian(np.zeros(D), cov, proposal_cov=np.diag(np.diag(cov)))
     x0 = np.random.default_rng(0).multivariate_normal(np.zeros(D), cov, size=C)
-    s = EnsembleMCMC(fm, x0, {"seed": 2, "chains_per_gpu": C, "Rminus1_stop": 0.01,
-                              "rows_per_chain": 12000}).run()
-    assert s.converged and s.Rminus1_last < 0.01
+    s = EnsembleMCMC(fm, x0, {"seed": 2, "chains_per_gpu": C, "Rminus1_stop": 0.05,
+                              "rows_per_chain": 16000}).run()
+    assert s.converged and s.Rminus1_last < 0.05
     assert s.engine.last_step_kernel() == 1
     assert any(c.learned for c in s.progress)
     mean, cv, res = s.mean_and_cov()
