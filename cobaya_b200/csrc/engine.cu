@@ -936,7 +936,7 @@ extern "C" int cb2_moments(cb2_engine *h, int32_t mode, int32_t split, const dou
     const int64_t n_mean_tasks = n_tasks + (mode == CB2_MOMENTS_SINGLE_SPLIT ? 1 : 0);
     CK(h, h->d_means.ensure((size_t)n_mean_tasks * D));
     CK(h, h->d_sw.ensure(n_mean_tasks));
-    int grid = (int)std::min<int64_t>(n_tasks, 4 * h->sm_count);
+    int grid = (int)std::min<int64_t>(n_tasks, 8 * h->sm_count);
     CK(h, h->d_partials.ensure((size_t)grid * len));
     CK(h, h->d_mom_out.ensure(len));
     const bool dmma_ok = (D <= 64) && (h->policy == 0);

@@ -20,14 +20,18 @@
 static inline bool fast_basis_supported(int n) { return n >= 2 && n <= 64; }
 
 template <int NG>
-__global__ void __launch_bounds__((NG * 8 < 32) ? 32 : NG * 8)
+__global__ void __launch_bounds__((NG * 16 < 32) ? 32 : NG * 16, (NG >= 7) ? 4 : 1)
 k_basis_fast(uint32_t key0, uint32_t key1, uint64_t chain_id0, int block, int n,
              const int64_t *__restrict__ vis, int vis_stride, uint32_t e0_fixed, int cnt,
              double *__restrict__ store, int64_t task0, int64_t store_task0) {
-    constexpr int NP = NG * 8;
+    // Two threads per row of H: thread (row i, half p) keeps the column pairs
+    // {4g+2p, 4g+2p+1 : g = 0..NP/4-1} of its row in registers (NP/2 doubles).
+    constexpr int NP = NG * 8;   // padded size
+    constexpr int NK = NP / 2;   // columns per thread
     extern __shared__ __align__(16) double fsm[];
     double *X = fsm;              // [NP][NP]: X[m][c] = x_m[c-m] for c >= m, else 0
     double *Dv = fsm + NP * NP;   // [NP]
+    double *inv = Dv + NP;        // [NP] 1/sc_m
     const int tid = threadIdx.x, nt = blockDim.x;
     const int64_t task = task0 + blockIdx.x;
     const int64_t chain = task / cnt;
@@ -60,7 +64,6 @@ k_basis_fast(uint32_t key0, uint32_t key1, uint64_t chain_id0, int block, int n,
     __syncthreads();
     // 2. Householder vectors (functions.py:49-55): norms by one thread per vector, the
     //    rescaling x /= sc by all threads
-    double *inv = Dv + NP;  // [NP] 1/sc_m
     if (tid < n - 1) {
         const int m = tid, len = n - m;
         const double *x = X + m * NP + m;
@@ -89,42 +92,46 @@ k_basis_fast(uint32_t key0, uint32_t key1, uint64_t chain_id0, int block, int n,
         Dv[n - 1] = (((n - 1) & 1) ? -1.0 : 1.0) * prod;
     }
     __syncthreads();
-    // 3. H = I; for m: H[:, m:] -= (H[:, m:] x_m) x_m^T  (functions.py:57-58); row r here
-    const int r = tid;
-    double h[NP];
+    // 3. H = I; for m: H[:, m:] -= (H[:, m:] x_m) x_m^T  (functions.py:57-58)
+    const int row = tid >> 1, half = tid & 1;
+    double h[NK];
 #pragma unroll
-    for (int c = 0; c < NP; ++c) h[c] = (c == r) ? 1.0 : 0.0;
+    for (int k = 0; k < NK; ++k) {
+        const int c = 4 * (k >> 1) + 2 * half + (k & 1);
+        h[k] = (c == row) ? 1.0 : 0.0;
+    }
 #pragma unroll
     for (int G = 0; G < NG; ++G) {
         const int m_end = min(8 * G + 8, n - 1);
         for (int m = 8 * G; m < m_end; ++m) {
-            const double2 *x2 = reinterpret_cast<const double2 *>(X + m * NP);
-            double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+            // this thread's pairs of group g >= 2G: columns 4g+2*half, +1 -> double2 index 2g+half
+            const double2 *x2 = reinterpret_cast<const double2 *>(X + m * NP) + half;
+            double t0 = 0.0, t1 = 0.0;
 #pragma unroll
-            for (int c = 8 * G; c < NP; c += 4) {
-                double2 a = x2[c / 2], b = x2[c / 2 + 1];
-                t0 = fma(h[c], a.x, t0);
-                t1 = fma(h[c + 1], a.y, t1);
-                t2 = fma(h[c + 2], b.x, t2);
-                t3 = fma(h[c + 3], b.y, t3);
+            for (int g = 2 * G; g < NP / 4; ++g) {
+                const double2 a = x2[2 * g];
+                t0 = fma(h[2 * g], a.x, t0);
+                t1 = fma(h[2 * g + 1], a.y, t1);
             }
-            const double tmp = (t0 + t1) + (t2 + t3);
+            double tmp = t0 + t1;
+            tmp += __shfl_xor_sync(0xffffffffu, tmp, 1);
 #pragma unroll
-            for (int c = 8 * G; c < NP; c += 2) {
-                double2 a = x2[c / 2];
-                h[c] = fma(-tmp, a.x, h[c]);
-                h[c + 1] = fma(-tmp, a.y, h[c + 1]);
+            for (int g = 2 * G; g < NP / 4; ++g) {
+                const double2 a = x2[2 * g];
+                h[2 * g] = fma(-tmp, a.x, h[2 * g]);
+                h[2 * g + 1] = fma(-tmp, a.y, h[2 * g + 1]);
             }
         }
     }
-    __syncthreads();
-    // 4. R = diag(D) H (functions.py:60); stored as Rt[k*n + r] = R[r][k]
-    if (r < n) {
-        const double d = Dv[r];
+    // 4. R = diag(D) H (functions.py:60); stored as Rt[c*n + row] = R[row][c]
+    if (row < n) {
+        const double d = Dv[row];
         double *out = store + (size_t)(task - store_task0) * (size_t)n * n;
 #pragma unroll
-        for (int k = 0; k < NP; ++k)
-            if (k < n) out[(size_t)k * n + r] = d * h[k];
+        for (int k = 0; k < NK; ++k) {
+            const int c = 4 * (k >> 1) + 2 * half + (k & 1);
+            if (c < n) out[(size_t)c * n + row] = d * h[k];
+        }
     }
 }
 
@@ -134,7 +141,7 @@ static int launch_basis_fast_t(cudaStream_t st, uint32_t k0, uint32_t k1, uint64
                                uint32_t e0_fixed, int cnt, double *store, int64_t tasks,
                                int64_t task0, int64_t store_task0) {
     constexpr int NP = NG * 8;
-    const int threads = NP < 32 ? 32 : NP;
+    const int threads = 2 * NP < 32 ? 32 : 2 * NP;
     const size_t smem = (size_t)(NP * NP + 2 * NP) * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(k_basis_fast<NG>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

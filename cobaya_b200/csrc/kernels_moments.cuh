@@ -206,7 +206,7 @@ __device__ __forceinline__ void mom_dmma(double &d0, double &d1, double a, doubl
 }
 
 template <int NT>
-__global__ void __launch_bounds__(NT * 32)
+__global__ void __launch_bounds__(NT * 32, (NT >= 7) ? 2 : 1)
 k_task_moments_dmma(const double *__restrict__ rows, int64_t cap, int width, int D,
                     const MomentTask *__restrict__ tasks, int64_t n_tasks,
                     const double *__restrict__ shift, double *__restrict__ partials,
@@ -238,11 +238,22 @@ k_task_moments_dmma(const double *__restrict__ rows, int64_t cap, int width, int
         for (int64_t r0 = T.first; r0 < T.last; r0 += CB2_MOM_BATCH) {
             const int nb = (int)min((int64_t)CB2_MOM_BATCH, T.last - r0);
             __syncthreads();
-            for (int e = tid; e < CB2_MOM_BATCH * DP; e += nt) {
-                const int k = e / DP, d = e % DP;
-                double v = 0.0;
-                if (k < nb && d < D) v = base[(size_t)(r0 + k) * width + 2 + d] - refv[d];
-                xt[k][d] = v;
+            {
+                // CB2_MOM_BATCH*DP / (32*NT) = 8 elements per thread: issue every load
+                // before the first use so that 8 DRAM requests are in flight per thread
+                double vals[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int e = tid + u * (NT * 32);
+                    const int k = e / DP, d = e % DP;
+                    vals[u] = (k < nb && d < D) ? base[(size_t)(r0 + k) * width + 2 + d] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int e = tid + u * (NT * 32);
+                    const int k = e / DP, d = e % DP;
+                    xt[k][d] = (k < nb && d < D) ? vals[u] - refv[d] : 0.0;
+                }
             }
             if (tid < CB2_MOM_BATCH) wt[tid] = (tid < nb) ? base[(size_t)(r0 + tid) * width] : 0.0;
             __syncthreads();
