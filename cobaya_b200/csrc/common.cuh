@@ -89,10 +89,27 @@ __host__ __device__ __forceinline__ u32x4 philox4x32_10(uint32_t k0, uint32_t k1
     return o;
 }
 
-// 52-bit uniform strictly inside (0,1)
+// 52-bit uniform strictly inside (0,1): (k + 1/2) 2^-52 with k = 26+26 bits of two words.
+// On the device it is assembled from the bit pattern of 1 + k 2^-52 (no 64-bit int->double
+// conversion, which runs on the slow XU pipe); both forms are exact and bit-identical.
 __host__ __device__ __forceinline__ double u52(uint32_t a, uint32_t b) {
     uint64_t k = ((uint64_t)(a >> 6) << 26) | (uint64_t)(b >> 6);
+#ifdef __CUDA_ARCH__
+    return (__longlong_as_double((long long)(0x3FF0000000000000ull | k)) - 1.0) +
+           1.1102230246251565e-16;  // 2^-53
+#else
     return ((double)k + 0.5) * 2.220446049250313e-16;
+#endif
+}
+
+// (w + 1/2) 2^-32 for a 32-bit word, same construction
+__host__ __device__ __forceinline__ double u32half(uint32_t w) {
+#ifdef __CUDA_ARCH__
+    return (__longlong_as_double((long long)(0x4330000000000000ull | (uint64_t)w)) -
+            4503599627370496.0 + 0.5) * 2.3283064365386963e-10;
+#else
+    return ((double)w + 0.5) * 2.3283064365386963e-10;
+#endif
 }
 
 // radial part of a proposal: propose_r / RandProposer1D (proposal.py:71-93)
@@ -101,7 +118,7 @@ __device__ __forceinline__ void draw_radial(const ModelDev &M, uint64_t gid, uin
                                             double &sign) {
     u32x4 w = philox4x32_10(M.key0, M.key1, (uint32_t)t, (uint32_t)(t >> 32),
                             (uint32_t)gid, CB2_TAG_STEP | (sub << 8));
-    double u_mix = ((double)w.x + 0.5) * 2.3283064365386963e-10;
+    double u_mix = u32half(w.x);
     double u_r = u52(w.z, w.w);
     sign = (w.y & 1u) ? 1.0 : -1.0;
     if (u_mix < 0.33) {

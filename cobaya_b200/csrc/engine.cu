@@ -706,7 +706,7 @@ static int launch_basis_impl(cb2_engine *h, int b, int cnt) {
     const size_t bytes = per_task * 8;
     const int use_global = bytes > 200 * 1024;
     int threads = std::min(256, std::max(32, ((n + 31) / 32) * 32));
-    if (fast_basis_supported(n) && h->policy == 0) {
+    if (fast_basis_supported(n) && h->policy != 1) {
         int rc = launch_basis_fast(h->stream, h->M.key0, h->M.key1, h->chain_id0, b, n,
                                    h->d_vis.p, h->n_blocks + 1, cnt, h->d_basis[b].p, C);
         if (rc == 0) {
@@ -752,7 +752,7 @@ extern "C" int cb2_advance(cb2_engine *h, int64_t n_proposals) {
     StepSmem L = plan_step_smem(h);
     int warps; size_t bytes;
     if ((rc = step_launch_dims(h, L, warps, bytes))) return rc;
-    const bool fast_ok = (h->policy == 0) && h->fast_ready;
+    const bool fast_ok = (h->policy == 0 || h->policy == 2) && h->fast_ready;
     int64_t remaining = n_proposals;
     while (remaining > 0) {
         WindowDev W;
@@ -833,12 +833,19 @@ extern "C" int cb2_advance(cb2_engine *h, int64_t n_proposals) {
         }
         h->prof_begin(PROF_STEP);
         if (fast_ok) {
-            if ((rc = launch_step_fast(h->stream, h->M, h->S, W, h->d_fastpack.p, h->fast_desc,
-                                       h->d_draws.p, C, (uint64_t)h->steps_done, w,
-                                       h->sm_count))) {
-                FAIL(h, -2, "fast step kernel launch failed (%d)", rc);
+            rc = -2;
+            if (h->policy != 2 && pc_step_supported(h->M, h->fast_desc)) {
+                rc = launch_step_pc(h->stream, h->M, h->S, W, h->d_fastpack.p, h->fast_desc,
+                                    h->d_draws.p, C, (uint64_t)h->steps_done, w, h->sm_count);
+                if (rc == 0) h->last_kernel = 2;
             }
-            h->last_kernel = 1;
+            if (rc == -2) {  // unsupported by / too large for the producer-consumer kernel
+                rc = launch_step_fast(h->stream, h->M, h->S, W, h->d_fastpack.p, h->fast_desc,
+                                      h->d_draws.p, C, (uint64_t)h->steps_done, w,
+                                      h->sm_count);
+                if (rc == 0) h->last_kernel = 1;
+            }
+            if (rc) FAIL(h, -2, "fast step kernel launch failed (%d)", rc);
         } else {
             CK(h, cudaFuncSetAttribute(k_step_general, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)bytes));
@@ -939,7 +946,7 @@ extern "C" int cb2_moments(cb2_engine *h, int32_t mode, int32_t split, const dou
     int grid = (int)std::min<int64_t>(n_tasks, 8 * h->sm_count);
     CK(h, h->d_partials.ensure((size_t)grid * len));
     CK(h, h->d_mom_out.ensure(len));
-    const bool dmma_ok = (D <= 64) && (h->policy == 0);
+    const bool dmma_ok = (D <= 64) && (h->policy != 1);
     if (dmma_ok) {
         // proposal-covariance SYRK on the FP64 tensor pipe (one pass over the rows)
         const int NT = (D + 7) / 8;
@@ -1037,7 +1044,7 @@ extern "C" int cb2_debug_basis(cb2_engine *h, int64_t chain, int32_t block, uint
     DevBuf<double> out;
     CK(h, out.ensure((size_t)n * n));
     const uint32_t k0 = (uint32_t)h->seed, k1 = (uint32_t)(h->seed >> 32);
-    if (fast_basis_supported(n) && h->policy == 0) {
+    if (fast_basis_supported(n) && h->policy != 1) {
         int rc = launch_basis_fast_one(h->stream, k0, k1, h->chain_id0 + (uint64_t)chain, block,
                                        n, epoch, out.p);
         if (rc) FAIL(h, -2, "fast basis kernel launch failed");

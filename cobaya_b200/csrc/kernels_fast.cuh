@@ -611,3 +611,386 @@ static inline int launch_step_fast(cudaStream_t st, const ModelDev &M, const Cha
 #undef CB2_SF
     return -1;
 }
+
+// =====================================================================================
+// Producer/consumer step kernel (single Gaussian mode, no periodic parameters)
+// =====================================================================================
+// Every quantity on the proposal side of a Metropolis step is independent of the chain
+// state: with delta_s = T v_s (proposal.py:224) and, by linearity of the Gaussian's
+// whitening map, L^-1 (x + delta_s - mu) = y + L^-1 delta_s, both matrix products of a
+// proposal can be formed ahead of the serial accept chain.  Per SM one CTA of 2*wpc warps:
+//   * producer warp p : for its 8 chains, streams steps s = 0,1,...: direction + radius ->
+//     delta_s = T v_s and w_s = L^-1 P delta_s on the FP64 tensor pipe (m8n8k4 DMMA), written
+//     to a shared-memory ring in fragment order, mbarrier "full";
+//   * consumer warp p : keeps x and y = L^-1 P (x - mu) in registers; per step reads
+//     (delta_s, w_s): bounds/prior of x + delta, |y + w|^2, Metropolis test
+//     (mcmc.py:670-683), bookkeeping and row store (mcmc.py:685-748), mbarrier "empty".
+// The tensor pipe therefore never waits for an accept decision.  y is recomputed from x at
+// the start of every window, which bounds the drift of the incremental update.
+#define CB2_PC_RING 3
+
+__device__ __forceinline__ void mbar_init(uint32_t a, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t a) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(a), "r"(parity)
+            : "memory");
+    }
+}
+
+static inline bool pc_step_supported(const ModelDev &M, const FastPackDesc &P) {
+    return P.n_modes == 1 && !M.any_periodic;
+}
+
+template <int NT>
+__global__ void __maxnreg__(144)
+k_step_pc(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gpack,
+          FastPackDesc P, const double2 *__restrict__ draws, int64_t n_chains, uint64_t t0,
+          int n_steps, int wpc) {
+    constexpr int DP = NT * 8;
+    constexpr int SLOT = 2 * NT * 32 * 2;  // doubles per ring slot: delta + w, fragment order
+    extern __shared__ __align__(16) double fsm[];
+    __shared__ __align__(8) unsigned long long mbar_pack;
+    __shared__ __align__(8) unsigned long long mbar_full[8 * CB2_PC_RING];
+    __shared__ __align__(8) unsigned long long mbar_empty[8 * CB2_PC_RING];
+    double *pack = fsm;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool is_producer = warp >= wpc;
+    const int pair = is_producer ? warp - wpc : warp;
+    const uint32_t bytes = (uint32_t)P.total * 8u;
+    const uint32_t mb_pack = (uint32_t)__cvta_generic_to_shared(&mbar_pack);
+    if (tid == 0) {
+        mbar_init(mb_pack, 1);
+        for (int i = 0; i < wpc * CB2_PC_RING; ++i) {
+            mbar_init((uint32_t)__cvta_generic_to_shared(&mbar_full[i]), 1);
+            mbar_init((uint32_t)__cvta_generic_to_shared(&mbar_empty[i]), 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb_pack),
+                     "r"(bytes)
+                     : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+            ::"r"((uint32_t)__cvta_generic_to_shared(pack)), "l"(gpack), "r"(bytes), "r"(mb_pack)
+            : "memory");
+    }
+    mbar_wait(mb_pack, 0);
+
+    double *ring = fsm + P.total + (size_t)pair * CB2_PC_RING * SLOT;
+    int *svis_all = reinterpret_cast<int *>(fsm + P.total + (size_t)wpc * CB2_PC_RING * SLOT);
+    const int q = lane >> 2, r = lane & 3;
+    const int64_t tile = blockIdx.x * (int64_t)wpc + pair;
+    const int64_t chain_raw = tile * 8 + q;
+    const bool active = chain_raw < n_chains;
+    const int64_t chain = active ? chain_raw : (n_chains - 1);
+    const int D = M.D, NB = M.n_blocks, NV = NB + 1;
+    const double2 *my_draws = draws + chain * (int64_t)n_steps;
+    const int *iofj = reinterpret_cast<const int *>(pack + P.off_iofj);
+
+    if (is_producer) {
+        // ================================ producer ====================================
+        const double *Tf = pack + P.off_T, *Af = pack + P.off_A;
+        int *sv = svis_all + (pair * 8 + q) * (3 * CB2_MAX_BLOCKS);
+        uint32_t flags = 0;
+        if (r == 0)
+            for (int b = 0; b < NB; ++b) {
+                sv[3 * b + 0] = (int)(S.vis[chain * NV + b] % M.bsize[b]);
+                sv[3 * b + 1] = 0;
+                sv[3 * b + 2] = 0;
+            }
+        __syncwarp();
+        auto locate = [&](int s, int &nb, int &j0, const double *&Rk) {
+            const uint64_t t = t0 + (uint64_t)s;
+            const int b = W.tape_main
+                              ? W.tape_main[chain * W.len_main + (int64_t)(t - W.base_main)]
+                              : W.const_main;
+            nb = M.bsize[b];
+            j0 = M.jstart[b];
+            const int k = sv[3 * b + 0];
+            int slot = sv[3 * b + 1];
+            const int cnt = sv[3 * b + 2];
+            Rk = nullptr;
+            if (nb >= 2) {
+                if (slot >= W.cnt[b]) {
+                    flags |= CB2_FLAG_INTERNAL;
+                    slot = 0;
+                }
+                Rk = W.basis[b] + ((size_t)(chain * W.cnt[b] + slot) * nb + k) * (size_t)nb;
+            }
+            __syncwarp();
+            if (r == 0) {
+                const bool wrap = (k + 1 == nb);
+                sv[3 * b + 0] = wrap ? 0 : k + 1;
+                sv[3 * b + 1] = sv[3 * b + 1] + (wrap ? 1 : 0);
+                sv[3 * b + 2] = cnt + 1;
+            }
+            __syncwarp();
+        };
+        auto fetch = [&](int nb, int j0, const double *Rk, double (&u)[NT][2]) {
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int j = 8 * n + 2 * r + h - j0;
+                    if (nb >= 2) u[n][h] = (j >= 0 && j < nb) ? Rk[j] : 0.0;
+                    else u[n][h] = (j == 0) ? 1.0 : 0.0;
+                }
+        };
+        double un[NT][2];
+        double rs_next;
+        {
+            int nb, j0;
+            const double *Rk;
+            locate(0, nb, j0, Rk);
+            fetch(nb, j0, Rk, un);
+            rs_next = my_draws[0].x;
+        }
+        for (int s = 0; s < n_steps; ++s) {
+            const int slot = s % CB2_PC_RING;
+            const uint32_t use = (uint32_t)(s / CB2_PC_RING);
+            double v[NT][2];
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+                v[n][0] = un[n][0] * rs_next * M.proposal_scale;
+                v[n][1] = un[n][1] * rs_next * M.proposal_scale;
+            }
+            if (s + 1 < n_steps) {
+                int nb, j0;
+                const double *Rk;
+                locate(s + 1, nb, j0, Rk);
+                fetch(nb, j0, Rk, un);
+                rs_next = my_draws[s + 1].x;
+            }
+            double dl[NT][2];
+#pragma unroll
+            for (int n = 0; n < NT; ++n) { dl[n][0] = 0.0; dl[n][1] = 0.0; }
+            warp_matvec8<NT, true>(Tf, lane, v, dl);
+            // wait until the consumer released this slot (first pass: free)
+            if (use > 0)
+                mbar_wait((uint32_t)__cvta_generic_to_shared(&mbar_empty[pair * CB2_PC_RING + slot]),
+                          (use - 1) & 1u);
+            double2 *sl = reinterpret_cast<double2 *>(ring + (size_t)slot * SLOT);
+#pragma unroll
+            for (int n = 0; n < NT; ++n) sl[n * 32 + lane] = make_double2(dl[n][0], dl[n][1]);
+            double wv[NT][2];
+#pragma unroll
+            for (int n = 0; n < NT; ++n) { wv[n][0] = 0.0; wv[n][1] = 0.0; }
+            if (P.tri_like) warp_matvec8<NT, true>(Af, lane, dl, wv);
+            else warp_matvec8<NT, false>(Af, lane, dl, wv);
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+                sl[(NT + n) * 32 + lane] = make_double2(wv[n][0], wv[n][1]);
+            __syncwarp();
+            if (lane == 0)
+                mbar_arrive((uint32_t)__cvta_generic_to_shared(&mbar_full[pair * CB2_PC_RING + slot]));
+        }
+        __syncwarp();
+        if (active && r == 0) {
+            for (int b = 0; b < NB; ++b) S.vis[chain * NV + b] += sv[3 * b + 2];
+            if (flags) atomicOr(&S.flags[chain], flags);
+        }
+    } else {
+        // ================================ consumer ====================================
+        const double *lower = pack + P.off_lower, *upper = pack + P.off_upper;
+        const int *pflag = reinterpret_cast<const int *>(pack + P.off_flags);
+        double xs[NT][2], ys[NT][2];
+        uint32_t m_norm = 0;
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = 8 * n + 2 * r + h;
+                const int i = iofj[j];
+                xs[n][h] = (i >= 0) ? S.x[chain * D + i] : 0.0;
+                m_norm |= (uint32_t)(pflag[j] & 1) << (2 * n + h);
+            }
+        {   // y = L^-1 P (x - mu), refreshed at every window start
+            const double *mu = pack + P.off_mu;
+            double z[NT][2];
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+                const double2 m2 = *reinterpret_cast<const double2 *>(mu + 8 * n + 2 * r);
+                z[n][0] = xs[n][0] - m2.x;
+                z[n][1] = xs[n][1] - m2.y;
+                ys[n][0] = 0.0;
+                ys[n][1] = 0.0;
+            }
+            if (P.tri_like) warp_matvec8<NT, true>(pack + P.off_A, lane, z, ys);
+            else warp_matvec8<NT, false>(pack + P.off_A, lane, z, ys);
+        }
+        double logpost = S.logpost[chain], logprior = S.logprior[chain], loglike = S.ll[chain];
+        long long weight = S.weight[chain], prior_rej = S.prior_rej[chain],
+                  burn_left = S.burn_left[chain], added_w = S.added_w[chain],
+                  n_rows = S.n_rows[chain], n_acc = S.n_acc[chain];
+        uint32_t flags = S.flags[chain];
+        const double c0 = pack[P.off_c0];
+        double e_next = my_draws[0].y;
+        for (int s = 0; s < n_steps; ++s) {
+            const int slot = s % CB2_PC_RING;
+            const uint32_t use = (uint32_t)(s / CB2_PC_RING);
+            const double e_acc = e_next;
+            if (s + 1 < n_steps) e_next = my_draws[s + 1].y;
+            mbar_wait((uint32_t)__cvta_generic_to_shared(&mbar_full[pair * CB2_PC_RING + slot]),
+                      use & 1u);
+            const double2 *sl = reinterpret_cast<const double2 *>(ring + (size_t)slot * SLOT);
+            double xt[NT][2], yt[NT][2];
+            bool bad = false;
+            double ps = 0.0, qsum = 0.0;
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+                const double2 d2 = sl[n * 32 + lane];
+                const double2 w2 = sl[(NT + n) * 32 + lane];
+                const double2 lo2 = *reinterpret_cast<const double2 *>(lower + 8 * n + 2 * r);
+                const double2 up2 = *reinterpret_cast<const double2 *>(upper + 8 * n + 2 * r);
+                xt[n][0] = xs[n][0] + d2.x;
+                xt[n][1] = xs[n][1] + d2.y;
+                yt[n][0] = ys[n][0] + w2.x;
+                yt[n][1] = ys[n][1] + w2.y;
+                qsum += yt[n][0] * yt[n][0] + yt[n][1] * yt[n][1];
+                if (!(xt[n][0] <= up2.x) || !(xt[n][0] >= lo2.x) || !isfinite(xt[n][0])) bad = true;
+                if (!(xt[n][1] <= up2.y) || !(xt[n][1] >= lo2.y) || !isfinite(xt[n][1])) bad = true;
+                if (M.any_normal) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                        if ((m_norm >> (2 * n + h)) & 1u) {
+                            const int j = 8 * n + 2 * r + h;
+                            const double zz = (xt[n][h] - pack[P.off_loc + j]) / pack[P.off_isc + j];
+                            ps += pack[P.off_mls + j] - zz * zz / 2;
+                        }
+                }
+            }
+            __syncwarp();
+            if (lane == 0)  // the slot's contents are in registers: hand it back
+                mbar_arrive((uint32_t)__cvta_generic_to_shared(&mbar_empty[pair * CB2_PC_RING + slot]));
+            bad = __shfl_xor_sync(0xffffffffu, (int)bad, 1) | (int)bad;
+            bad = __shfl_xor_sync(0xffffffffu, (int)bad, 2) | (int)bad;
+            qsum = quad_sum(qsum);
+            if (M.any_normal) ps = quad_sum(ps);
+            const double t_prior = bad ? -CUDART_INF : (M.uniform_logp + ps);
+            const double t_like = -0.5 * (c0 + qsum);
+            const double t_post = bad ? -CUDART_INF : (t_prior + t_like);
+            bool acc;
+            if (t_post == -CUDART_INF) acc = false;
+            else if (t_post > logpost) acc = true;
+            else acc = e_acc > (logpost - t_post) / M.temperature;
+            if (acc) {
+                if (burn_left <= 0) {
+                    long long wst = weight;
+                    bool store = true;
+                    if (M.output_thin > 1) {
+                        added_w += weight;
+                        if (added_w >= M.output_thin) {
+                            wst = added_w / M.output_thin;
+                            added_w %= M.output_thin;
+                        } else store = false;
+                    }
+                    if (store) {
+                        if (n_rows >= S.cap) flags |= CB2_FLAG_ROWS_FULL;
+                        else {
+                            if (active) {
+                                double *row = S.rows + ((size_t)chain * S.cap + n_rows) * M.width;
+                                if (r == 0) {
+                                    row[0] = (double)wst;
+                                    row[1] = -(logpost / M.temperature);
+                                } else if (r == 1) {
+                                    row[2 + D] = -logprior;
+                                    row[3 + D] = -logprior;
+                                } else if (r == 2) {
+                                    row[4 + D] = -2 * loglike;
+                                    row[5 + D] = -2 * loglike;
+                                }
+#pragma unroll
+                                for (int n = 0; n < NT; ++n)
+#pragma unroll
+                                    for (int h = 0; h < 2; ++h) {
+                                        const int i = iofj[8 * n + 2 * r + h];
+                                        if (i >= 0) row[2 + i] = xs[n][h];
+                                    }
+                            }
+                            n_rows += 1;
+                        }
+                    }
+                } else burn_left -= 1;
+#pragma unroll
+                for (int n = 0; n < NT; ++n) {
+                    xs[n][0] = xt[n][0]; xs[n][1] = xt[n][1];
+                    ys[n][0] = yt[n][0]; ys[n][1] = yt[n][1];
+                }
+                logpost = t_post; logprior = t_prior; loglike = t_like;
+                weight = 1; prior_rej = 0; n_acc += 1;
+            } else {
+                weight += 1;
+                if (t_prior == -CUDART_INF) prior_rej += 1;
+                const long long sgn = (burn_left > 0) - (burn_left < 0);
+                if (weight - prior_rej > M.max_tries * (1 + 9 * sgn)) flags |= CB2_FLAG_STUCK;
+            }
+        }
+        __syncwarp();
+        if (active) {
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int i = iofj[8 * n + 2 * r + h];
+                    if (i >= 0) S.x[chain * D + i] = xs[n][h];
+                }
+            if (r == 0) {
+                S.logpost[chain] = logpost; S.logprior[chain] = logprior; S.ll[chain] = loglike;
+                S.weight[chain] = weight; S.prior_rej[chain] = prior_rej;
+                S.burn_left[chain] = burn_left; S.added_w[chain] = added_w;
+                S.n_rows[chain] = n_rows; S.n_acc[chain] = n_acc;
+                if (flags) atomicOr(&S.flags[chain], flags);
+            }
+        }
+    }
+}
+
+template <int NT>
+static int launch_step_pc_t(cudaStream_t st, const ModelDev &M, const ChainState &S,
+                            const WindowDev &W, const double *gpack, const FastPackDesc &P,
+                            const double2 *draws, int64_t n_chains, uint64_t t0, int n_steps,
+                            int sm_count) {
+    const int64_t tiles = (n_chains + 7) / 8;
+    int wpc = (int)((tiles + sm_count - 1) / sm_count);
+    if (wpc < 1) wpc = 1;
+    if (wpc > 7) wpc = 7;
+    const int grid = (int)((tiles + wpc - 1) / wpc);
+    const size_t slot = (size_t)2 * NT * 32 * 2;
+    const size_t smem = ((size_t)P.total + (size_t)wpc * CB2_PC_RING * slot) * 8 +
+                        (size_t)wpc * 8 * 3 * CB2_MAX_BLOCKS * sizeof(int);
+    if (smem > 220 * 1024) return -2;
+    if (cudaFuncSetAttribute(k_step_pc<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem) != cudaSuccess)
+        return -1;
+    k_step_pc<NT><<<grid, 2 * wpc * 32, smem, st>>>(M, S, W, gpack, P, draws, n_chains, t0,
+                                                     n_steps, wpc);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+static inline int launch_step_pc(cudaStream_t st, const ModelDev &M, const ChainState &S,
+                                 const WindowDev &W, const double *gpack, const FastPackDesc &P,
+                                 const double2 *draws, int64_t n_chains, uint64_t t0,
+                                 int n_steps, int sm_count) {
+#define CB2_PC(N)                                                                         \
+    case N:                                                                               \
+        return launch_step_pc_t<N>(st, M, S, W, gpack, P, draws, n_chains, t0, n_steps,     \
+                                   sm_count);
+    switch (P.NT) {
+        CB2_PC(1) CB2_PC(2) CB2_PC(3) CB2_PC(4) CB2_PC(5) CB2_PC(6) CB2_PC(7) CB2_PC(8)
+    }
+#undef CB2_PC
+    return -1;
+}

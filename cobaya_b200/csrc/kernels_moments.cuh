@@ -198,6 +198,7 @@ __global__ void k_summary(const int64_t *__restrict__ n_rows, const int64_t *__r
 // output rows 8w..8w+7 (all NT column tiles) in MMA C-fragment layout.
 // =====================================================================================
 #define CB2_MOM_BATCH 32
+#define CB2_MOM_PER_THREAD 8   // CB2_MOM_BATCH*DP / (32*NT)
 
 __device__ __forceinline__ void mom_dmma(double &d0, double &d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -235,28 +236,32 @@ k_task_moments_dmma(const double *__restrict__ rows, int64_t cap, int width, int
         __syncthreads();
         if (tid < DP) refv[tid] = (tid < D) ? base[(size_t)T.first * width + 2 + tid] : 0.0;
         __syncthreads();
+        // software pipeline: the rows of batch b+1 are fetched into registers while the
+        // tensor pipe works on batch b (DRAM latency hidden behind the MMAs)
+        double vals[CB2_MOM_PER_THREAD], wnext = 0.0;
+        auto fetch = [&](int64_t r0) {
+            const int nb = (int)min((int64_t)CB2_MOM_BATCH, T.last - r0);
+#pragma unroll
+            for (int u = 0; u < CB2_MOM_PER_THREAD; ++u) {
+                const int e = tid + u * (NT * 32);
+                const int k = e / DP, d = e % DP;
+                vals[u] = (k < nb && d < D) ? base[(size_t)(r0 + k) * width + 2 + d] : 0.0;
+            }
+            if (tid < CB2_MOM_BATCH) wnext = (tid < nb) ? base[(size_t)(r0 + tid) * width] : 0.0;
+        };
+        if (T.first < T.last) fetch(T.first);
         for (int64_t r0 = T.first; r0 < T.last; r0 += CB2_MOM_BATCH) {
             const int nb = (int)min((int64_t)CB2_MOM_BATCH, T.last - r0);
             __syncthreads();
-            {
-                // CB2_MOM_BATCH*DP / (32*NT) = 8 elements per thread: issue every load
-                // before the first use so that 8 DRAM requests are in flight per thread
-                double vals[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int e = tid + u * (NT * 32);
-                    const int k = e / DP, d = e % DP;
-                    vals[u] = (k < nb && d < D) ? base[(size_t)(r0 + k) * width + 2 + d] : 0.0;
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int e = tid + u * (NT * 32);
-                    const int k = e / DP, d = e % DP;
-                    xt[k][d] = (k < nb && d < D) ? vals[u] - refv[d] : 0.0;
-                }
+            for (int u = 0; u < CB2_MOM_PER_THREAD; ++u) {
+                const int e = tid + u * (NT * 32);
+                const int k = e / DP, d = e % DP;
+                xt[k][d] = (k < nb && d < D) ? vals[u] - refv[d] : 0.0;
             }
-            if (tid < CB2_MOM_BATCH) wt[tid] = (tid < nb) ? base[(size_t)(r0 + tid) * width] : 0.0;
+            if (tid < CB2_MOM_BATCH) wt[tid] = wnext;
             __syncthreads();
+            if (r0 + CB2_MOM_BATCH < T.last) fetch(r0 + CB2_MOM_BATCH);
             if (tid < DP) {
 #pragma unroll 8
                 for (int k = 0; k < CB2_MOM_BATCH; ++k) s1 = fma(wt[k], xt[k][tid], s1);

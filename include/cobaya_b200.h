@@ -144,9 +144,10 @@ int cb2_timer_stop(cb2_engine *h, float *ms);
 int cb2_set_profiling(cb2_engine *h, int32_t on);
 int cb2_kernel_times(cb2_engine *h, double ms[4], int64_t n[4], int32_t reset);
 /* which step kernel the last cb2_advance used: 0 = general warp-per-chain,
- * 1 = DMMA (mma.sync.m8n8k4.f64) register-resident fast path */
+ * 1 = DMMA (mma.sync.m8n8k4.f64) register-resident, 2 = DMMA producer/consumer */
 int cb2_last_step_kernel(const cb2_engine *h);
-int cb2_set_kernel_policy(cb2_engine *h, int32_t policy); /* 0 auto, 1 force general */
+/* 0 auto, 1 force the general kernels, 2 fast kernels without the producer/consumer one */
+int cb2_set_kernel_policy(cb2_engine *h, int32_t policy);
 
 #ifdef __cplusplus
 }

@@ -109,7 +109,7 @@ def _oracle_rows(fm, seed, ids, x0, n, burn_in):
     return out
 
 
-@pytest.mark.parametrize("policy", [0, 1])
+@pytest.mark.parametrize("policy", [0, 1, 2])
 @pytest.mark.parametrize("D,n_chains,n", [(8, 37, 300), (64, 16, 200), (21, 9, 150)])
 def test_ensemble_matches_oracle(cuda_lib, D, n_chains, n, policy):
     """Many chains, global ids offset (as on rank>0), against the C oracle."""
@@ -124,6 +124,8 @@ def test_ensemble_matches_oracle(cuda_lib, D, n_chains, n, policy):
     eng.set_kernel_policy(policy)
     eng.set_state(x0)
     eng.advance(n)
+    # 0 auto -> producer/consumer DMMA kernel, 2 -> single-role DMMA kernel, 1 -> general
+    assert eng.last_step_kernel() == {0: 2, 1: 0, 2: 1}[policy]
     st = eng.get_state()
     ref = _oracle_rows(fm, 77, range(id0, id0 + n_chains), x0, n, 0)
     for c in range(n_chains):
@@ -240,6 +242,8 @@ def test_general_and_dmma_paths_match_oracle(cuda_lib, policy, modes, thin):
     eng.set_state(x0)
     for k in (3, 50, 347):
         eng.advance(k)
+    # periodic parameter / two modes: the single-role DMMA kernel (1), not the
+    # producer/consumer one
     assert eng.last_step_kernel() == (1 if policy == 0 else 0)
     st = eng.get_state()
     assert not st["flags"].any()
@@ -262,7 +266,7 @@ def test_dmma_path_is_used_for_headline_config(cuda_lib):
     eng = _engine(fm, 8, seed=1, rows_cap=64)
     eng.set_state(np.zeros((8, 64)))
     eng.advance(64)
-    assert eng.last_step_kernel() == 1
+    assert eng.last_step_kernel() == 2
 
 
 # ---------------------------------------------------------------------------------------
@@ -371,3 +375,41 @@ def test_config5_dimension_sweep_parity(cuda_lib, D, n):
         assert rows.shape == rows_ref.shape
         np.testing.assert_allclose(rows, rows_ref, rtol=RTOL, atol=ATOL)
         np.testing.assert_allclose(st["x"][c], s_ref["x"], rtol=RTOL, atol=ATOL)
+
+
+def test_producer_consumer_kernel_blocks_normal_prior_thinning(cuda_lib):
+    """The producer/consumer DMMA kernel with two blocks + oversampling + thinning, a normal
+    prior, burn-in and temperature (one mode, no periodic parameter), against the oracle;
+    long enough for the incremental y = L^-1(x-mu) update to be refreshed across windows."""
+    from cobaya_b200.flatmodel import FlatModel, LikeSpec
+
+    rng = np.random.default_rng(4)
+    D = 12
+    cov = _mixture_cov(D, rng, scale=0.05)
+    lk = LikeSpec.gaussian_mixture(rng.permutation(D), [rng.uniform(-0.1, 0.1, D)], [cov])
+    kind = np.zeros(D, np.int32); kind[3] = 1
+    lower = np.full(D, -1.0); upper = np.full(D, 1.0)
+    lower[3], upper[3] = -np.inf, np.inf
+    sc = np.ones(D); sc[3] = 0.3
+    fm = FlatModel(names=[f"p{i}" for i in range(D)], prior_kind=kind, lower=lower, upper=upper,
+                   loc=np.zeros(D), pscale=sc, periodic=np.zeros(D, np.int32), likes=[lk],
+                   blocks=[[5, 1, 9, 0], [2, 3, 4, 6, 7, 8, 10, 11]], oversampling=[1, 2],
+                   proposal_cov=np.diag(np.full(D, 0.04**2)), temperature=2.0, output_thin=2)
+    C, n = 21, 500
+    x0 = rng.uniform(-0.05, 0.05, (C, D))
+    eng = _engine(fm, C, seed=31, chain_id0=77, rows_cap=n, burn_in=2)
+    eng.set_state(x0)
+    for k in (1, 19, 200, 280):
+        eng.advance(k)
+    assert eng.last_step_kernel() == 2
+    st = eng.get_state()
+    assert not st["flags"].any()
+    ref = _oracle_rows(fm, 31, range(77, 77 + C), x0, n, 2)
+    for c in range(C):
+        rc, rows_ref, s_ref = ref[c]
+        rows = eng.rows(c)
+        assert rows.shape == rows_ref.shape, f"chain {c}"
+        np.testing.assert_array_equal(rows[:, 0], rows_ref[:, 0])
+        np.testing.assert_allclose(rows, rows_ref, rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(st["x"][c], s_ref["x"], rtol=RTOL, atol=ATOL)
+        assert st["weight"][c] == s_ref["weight"]
