@@ -365,10 +365,11 @@ def run_gpu_arm(args):
                    "locksteps_per_step": locksteps, "checkpoints_in_timed_region": n_ckpt - ck0,
                    "l2": "working set per step (268 MB of Haar bases + sample rows) exceeds "
                          "the 126 MB L2; no explicit flush",
-                   "step_kernel": "dmma" if eng.last_step_kernel() == 1 else "general",
+                   "step_kernel": {0: "general", 1: "dmma", 2: "dmma-producer-consumer"}.get(
+                       eng.last_step_kernel(), "?"),
                    "parallelism": f"chains sharded over {world} GPU(s), no data-path "
                                   "collective; NCCL all-reduce of moments per checkpoint"},
-        "clocks": clk, "gpu_launches": int(launches),
+        "clocks": clk, "gpu_launches": int(launches), "engine_note": eng.debug_message(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "steps": Ke,
                 "what": "set_state(pinned host) + advance + moments->host + get_state"},

@@ -21,9 +21,9 @@ EXPORTS = [
     "cb2_clear_likelihoods", "cb2_add_gaussian_mixture", "cb2_add_rosenbrock",
     "cb2_set_blocking", "cb2_set_proposal", "cb2_set_options", "cb2_set_state",
     "cb2_get_state", "cb2_logpost", "cb2_advance", "cb2_sync", "cb2_summary",
-    "cb2_moments", "cb2_copy_rows", "cb2_row_width", "cb2_n_derived", "cb2_debug_basis",
+    "cb2_moments", "cb2_bounds", "cb2_copy_rows", "cb2_row_width", "cb2_n_derived", "cb2_debug_basis",
     "cb2_launch_count", "cb2_timer_start", "cb2_timer_stop", "cb2_last_step_kernel",
-    "cb2_set_kernel_policy", "cb2_set_profiling", "cb2_kernel_times",
+    "cb2_set_kernel_policy", "cb2_set_profiling", "cb2_kernel_times", "cb2_debug_message",
 ]
 
 
@@ -72,6 +72,7 @@ def load():
     L.cb2_sync.argtypes = [vp]
     L.cb2_summary.argtypes = [vp, vp]
     L.cb2_moments.argtypes = [vp, i32, i32, vp, vp, vp]
+    L.cb2_bounds.argtypes = [vp, i32, i32, dbl, vp, vp, vp]
     L.cb2_copy_rows.restype = i64
     L.cb2_copy_rows.argtypes = [vp, i64, i64, i64, vp]
     L.cb2_row_width.restype = i32
@@ -85,6 +86,8 @@ def load():
     L.cb2_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
     L.cb2_last_step_kernel.argtypes = [vp]
     L.cb2_set_kernel_policy.argtypes = [vp, i32]
+    L.cb2_debug_message.restype = C.c_char_p
+    L.cb2_debug_message.argtypes = [vp]
     L.cb2_set_profiling.argtypes = [vp, i32]
     L.cb2_kernel_times.argtypes = [vp, vp, vp, i32]
     for name in EXPORTS:

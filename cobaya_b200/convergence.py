@@ -59,3 +59,21 @@ def rminus1_from_sums(sums: np.ndarray, D: int, shift: np.ndarray | None = None)
     out["Rminus1"] = float(max(np.abs(eigvals)))
     out["success"] = True
     return out
+
+
+def rminus1_cl_from_sums(bsums: np.ndarray, D: int, W: np.ndarray) -> float:
+    """R-1 of the confidence bounds (mcmc.py:977-982): the standard deviation over chains
+    (``np.std``, ddof=0) of each chain's lower/upper bound, in units of sqrt(diag W); the
+    maximum over parameters and over the two bounds.  ``bsums`` = all-reduced output of
+    ``cb2_bounds``: {M, sum b_low, sum b_low^2, sum b_up, sum b_up^2} (bounds shifted by a
+    common vector, which leaves the standard deviation unchanged)."""
+    bsums = np.asarray(bsums, dtype=np.float64)
+    M = bsums[0]
+    out = 0.0
+    sd = np.sqrt(np.diag(W))
+    for k in range(2):
+        s1 = bsums[1 + 2 * D * k: 1 + 2 * D * k + D]
+        s2 = bsums[1 + 2 * D * k + D: 1 + 2 * D * k + 2 * D]
+        var = np.maximum(s2 / M - (s1 / M) ** 2, 0.0)
+        out = max(out, float(np.max(np.sqrt(var) / sd)))
+    return out

@@ -93,12 +93,13 @@ struct cb2_engine {
     DevBuf<double2> d_draws;
     // ---- moments
     DevBuf<MomentTask> d_tasks;
-    DevBuf<double> d_means, d_sw, d_partials, d_mom_out, d_shift;
+    DevBuf<double> d_means, d_sw, d_partials, d_mom_out, d_shift, d_bounds;
     DevBuf<int64_t> d_summary;
     // ---- misc
     DevBuf<double> d_tmp;
     int64_t launches = 0;
     int last_kernel = 0, policy = 0;
+    char pc_error[256] = {0};
     // ---- per-kernel-class device timing (CUDA events on the launching stream)
     struct ProfRec { cudaEvent_t a, b; int kind; };
     bool profiling = false;
@@ -228,7 +229,7 @@ extern "C" int cb2_destroy(cb2_engine *h) {
     h->d_perm_scratch.release();
     for (int b = 0; b < CB2_MAX_BLOCKS; ++b) h->d_basis[b].release();
     h->d_basis_scratch.release(); h->d_draws.release(); h->d_tasks.release(); h->d_means.release();
-    h->d_sw.release(); h->d_partials.release(); h->d_mom_out.release(); h->d_shift.release();
+    h->d_sw.release(); h->d_bounds.release(); h->d_partials.release(); h->d_mom_out.release(); h->d_shift.release();
     h->d_summary.release(); h->d_tmp.release();
     cudaEventDestroy(h->ev0);
     cudaEventDestroy(h->ev1);
@@ -839,6 +840,11 @@ extern "C" int cb2_advance(cb2_engine *h, int64_t n_proposals) {
                                     h->d_draws.p, C, (uint64_t)h->steps_done, w, h->sm_count);
                 if (rc == 0) h->last_kernel = 2;
             }
+            if (rc <= -1000) {  // launch problem: report it, then use the single-role kernel
+                snprintf(h->pc_error, sizeof(h->pc_error), "k_step_pc launch: %s (%d)",
+                         cudaGetErrorString((cudaError_t)((-rc) % 1000)), rc);
+                rc = -2;
+            }
             if (rc == -2) {  // unsupported by / too large for the producer-consumer kernel
                 rc = launch_step_fast(h->stream, h->M, h->S, W, h->d_fastpack.p, h->fast_desc,
                                       h->d_draws.p, C, (uint64_t)h->steps_done, w,
@@ -1007,6 +1013,79 @@ extern "C" int cb2_moments(cb2_engine *h, int32_t mode, int32_t split, const dou
     return 0;
 }
 
+// build the task list of a checkpoint on the device (shared by cb2_moments / cb2_bounds)
+static int build_tasks(cb2_engine *h, int32_t mode, int32_t split, int64_t &n_tasks) {
+    const int64_t C = h->n_chains;
+    if (mode == CB2_MOMENTS_HALVES) {
+        n_tasks = C;
+        CK(h, h->d_tasks.ensure(n_tasks + 1));
+        k_tasks_halves<<<(int)((C + 127) / 128), 128, 0, h->stream>>>(h->d_n_rows.p, C, h->d_tasks.p);
+        h->launches++;
+        return 0;
+    }
+    if (mode != CB2_MOMENTS_SINGLE_SPLIT) FAIL(h, -1, "unknown moments mode %d", mode);
+    if (C != 1) FAIL(h, -1, "single-split statistics need exactly one chain on this engine");
+    if (split < 1) FAIL(h, -1, "Rminus1_single_split must be >= 1");
+    CK(h, cudaStreamSynchronize(h->stream));
+    int64_t n = 0;
+    CK(h, cudaMemcpy(&n, h->d_n_rows.p, 8, cudaMemcpyDeviceToHost));
+    const int m = 1 + split;
+    const int64_t cut = n / m;
+    if (cut < 2) FAIL(h, -5, "Not enough points in chain to check convergence.");
+    std::vector<MomentTask> tasks;
+    for (int i = 1; i < m; ++i) {
+        MomentTask t;
+        t.chain = 0; t.first = i * cut; t.last = (i + 1) * cut - 1; t.N = (double)cut;
+        tasks.push_back(t);
+    }
+    n_tasks = m - 1;
+    CK(h, h->d_tasks.ensure(tasks.size() + 1));
+    CK(h, cudaMemcpyAsync(h->d_tasks.p, tasks.data(), tasks.size() * sizeof(MomentTask),
+                          cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int cb2_bounds(cb2_engine *h, int32_t mode, int32_t split, double limfrac,
+                          const double *shift, double *dev_out, double *host_out) {
+    if (!h || !h->have_state) return -1;
+    CK(h, cudaSetDevice(h->device));
+    if (!(limfrac > 0.0 && limfrac < 1.0)) FAIL(h, -1, "limfrac must be in (0,1)");
+    const int D = h->D, W = row_width(h);
+    const int len = 1 + 4 * D;
+    int64_t n_tasks = 0;
+    int rc = build_tasks(h, mode, split, n_tasks);
+    if (rc) return rc;
+    std::vector<double> sh(D, 0.0);
+    if (shift) sh.assign(shift, shift + D);
+    if ((rc = upload(h, h->d_shift, sh))) return rc;
+    // longest window -> power-of-two sort size (capped; longer windows are thinned)
+    int64_t sum8[8];
+    if ((rc = cb2_summary(h, sum8))) return rc;
+    int64_t maxwin = (mode == CB2_MOMENTS_HALVES) ? (sum8[1] - sum8[1] / 2) : sum8[1];
+    int n_pow2 = 64;
+    while (n_pow2 < maxwin && n_pow2 < 8192) n_pow2 <<= 1;
+    CK(h, h->d_bounds.ensure((size_t)n_tasks * D * 2));
+    CK(h, h->d_mom_out.ensure(std::max(len, 3 + D + 2 * D * D)));
+    const size_t smem = (size_t)2 * n_pow2 * sizeof(double);
+    CK(h, cudaFuncSetAttribute(k_task_bounds, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    h->prof_begin(PROF_MOMENTS);
+    k_task_bounds<<<(unsigned)(n_tasks * D), 256, smem, h->stream>>>(
+        h->d_rows.p, h->rows_cap, W, D, h->d_tasks.p, n_pow2, limfrac, h->d_bounds.p);
+    h->launches++;
+    double *out = dev_out ? dev_out : h->d_mom_out.p;
+    k_reduce_bounds<<<(2 * D + 127) / 128, 128, 0, h->stream>>>(h->d_bounds.p, n_tasks, D,
+                                                               h->d_shift.p, out);
+    h->prof_end();
+    h->launches++;
+    CK(h, cudaGetLastError());
+    if (host_out) {
+        CK(h, cudaStreamSynchronize(h->stream));
+        CK(h, cudaMemcpy(host_out, out, (size_t)len * 8, cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
 extern "C" int64_t cb2_copy_rows(cb2_engine *h, int64_t chain, int64_t row_begin, int64_t n,
                                  double *out) {
     if (!h || !h->have_state) return -1;
@@ -1089,6 +1168,7 @@ extern "C" int cb2_timer_stop(cb2_engine *h, float *ms) {
 }
 
 extern "C" int cb2_last_step_kernel(const cb2_engine *h) { return h ? h->last_kernel : -1; }
+extern "C" const char *cb2_debug_message(const cb2_engine *h) { return h ? h->pc_error : ""; }
 
 extern "C" int cb2_set_profiling(cb2_engine *h, int32_t on) {
     if (!h) return -1;

@@ -972,12 +972,13 @@ static int launch_step_pc_t(cudaStream_t st, const ModelDev &M, const ChainState
     const size_t smem = ((size_t)P.total + (size_t)wpc * CB2_PC_RING * slot) * 8 +
                         (size_t)wpc * 8 * 3 * CB2_MAX_BLOCKS * sizeof(int);
     if (smem > 220 * 1024) return -2;
-    if (cudaFuncSetAttribute(k_step_pc<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)smem) != cudaSuccess)
-        return -1;
+    cudaError_t e = cudaFuncSetAttribute(k_step_pc<NT>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return -1000 - (int)e;
     k_step_pc<NT><<<grid, 2 * wpc * 32, smem, st>>>(M, S, W, gpack, P, draws, n_chains, t0,
                                                      n_steps, wpc);
-    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+    e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : -2000 - (int)e;
 }
 
 static inline int launch_step_pc(cudaStream_t st, const ModelDev &M, const ChainState &S,

@@ -328,3 +328,97 @@ k_task_moments_dmma(const double *__restrict__ rows, int64_t cap, int width, int
         P[2] = accNa;
     }
 }
+
+// =====================================================================================
+// R-1 of the confidence-interval bounds (mcmc.py:918-1002)
+// =====================================================================================
+// The reference asks GetDist for `MCSamples.confidence(i, limfrac, upper)` of every chain:
+// the raw weighted sample quantile -- sort the values, cumulate the weights, take the first
+// sample whose cumulative weight reaches limfrac*norm (lower) or (1-limfrac)*norm (upper)
+// (getdist/chains.py `confidence`, GetDist>=1.3.1; not vendored: parity unpinned).
+// One CTA per (task, parameter): bitonic sort of (value, weight) in shared memory, inclusive
+// scan of the weights, two binary searches.  Windows longer than `cap_rows` are thinned by a
+// constant stride (documented deviation).
+__global__ void __launch_bounds__(256)
+k_task_bounds(const double *__restrict__ rows, int64_t cap, int width, int D,
+              const MomentTask *__restrict__ tasks, int n_pow2, double limfrac,
+              double *__restrict__ bounds /* [task][D][2] */) {
+    extern __shared__ double bsm[];
+    double *val = bsm;            // [n_pow2]
+    double *wgt = bsm + n_pow2;   // [n_pow2]
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int64_t task = blockIdx.x / D;
+    const int par = blockIdx.x % D;
+    const MomentTask T = tasks[task];
+    const double *base = rows + (size_t)T.chain * cap * width;
+    const int64_t nrows = T.last - T.first;
+    const int64_t stride = (nrows + n_pow2 - 1) / n_pow2;
+    const int n = (int)((nrows + stride - 1) / stride);
+    for (int e = tid; e < n_pow2; e += nt) {
+        if (e < n) {
+            const double *row = base + (size_t)(T.first + (int64_t)e * stride) * width;
+            val[e] = row[2 + par];
+            wgt[e] = row[0];
+        } else {
+            val[e] = CUDART_INF;
+            wgt[e] = 0.0;
+        }
+    }
+    __syncthreads();
+    for (int k = 2; k <= n_pow2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int e = tid; e < n_pow2; e += nt) {
+                const int p = e ^ j;
+                if (p > e) {
+                    const bool up = (e & k) == 0;
+                    const double a = val[e], b = val[p];
+                    if ((a > b) == up) {
+                        val[e] = b; val[p] = a;
+                        const double wa = wgt[e];
+                        wgt[e] = wgt[p]; wgt[p] = wa;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    // inclusive scan of the weights (Hillis-Steele; integer-valued weights: exact)
+    for (int off = 1; off < n_pow2; off <<= 1) {
+        double add[32];
+        int cnt = 0;
+        for (int e = tid; e < n_pow2; e += nt) add[cnt++] = (e >= off) ? wgt[e - off] : 0.0;
+        __syncthreads();
+        cnt = 0;
+        for (int e = tid; e < n_pow2; e += nt) wgt[e] += add[cnt++];
+        __syncthreads();
+    }
+    if (tid < 2) {
+        const double norm = wgt[n - 1];
+        const double target = tid == 0 ? norm * limfrac : norm * (1.0 - limfrac);
+        int lo = 0, hi = n;  // np.searchsorted(cumsum, target) (side='left')
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (wgt[mid] < target) lo = mid + 1;
+            else hi = mid;
+        }
+        if (lo > n - 1) lo = n - 1;
+        bounds[((size_t)task * D + par) * 2 + tid] = val[lo];
+    }
+}
+
+// out = { M, sum (low-s)[D], sum (low-s)^2[D], sum (up-s)[D], sum (up-s)^2[D] }
+__global__ void k_reduce_bounds(const double *__restrict__ bounds, int64_t n_tasks, int D,
+                                const double *__restrict__ shift, double *__restrict__ out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;  // (par, which)
+    if (e == 0) out[0] = (double)n_tasks;
+    if (e >= 2 * D) return;
+    const int par = e >> 1, which = e & 1;
+    double s1 = 0.0, s2 = 0.0;
+    const double sh = shift ? shift[par] : 0.0;
+    for (int64_t t = 0; t < n_tasks; ++t) {
+        const double b = bounds[((size_t)t * D + par) * 2 + which] - sh;
+        s1 += b;
+        s2 += b * b;
+    }
+    out[1 + (which ? 2 * D : 0) + par] = s1;
+    out[1 + (which ? 2 * D : 0) + D + par] = s2;
+}

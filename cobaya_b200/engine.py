@@ -153,6 +153,16 @@ class Engine:
                                       _cabi.ptr(out)))
         return out
 
+    def bounds(self, limfrac, mode=MOMENTS_HALVES, split=4, shift=None, dev_ptr=None,
+               host=True):
+        """Sums of the per-chain confidence bounds (mcmc.py:918-1002): [1 + 4D]."""
+        out = np.empty(1 + 4 * self.D) if host else None
+        sh = None if shift is None else _f64(shift)
+        self._ck(self.lib.cb2_bounds(self.h, int(mode), int(split), float(limfrac),
+                                     _cabi.ptr(sh), C.c_void_p(dev_ptr) if dev_ptr else None,
+                                     _cabi.ptr(out)))
+        return out
+
     def rows(self, chain: int, first: int = 0, n: int | None = None):
         W = self.lib.cb2_row_width(self.h)
         n = self.rows_cap if n is None else int(n)
@@ -182,6 +192,9 @@ class Engine:
 
     def last_step_kernel(self):
         return int(self.lib.cb2_last_step_kernel(self.h))
+
+    def debug_message(self):
+        return self.lib.cb2_debug_message(self.h).decode()
 
     def set_kernel_policy(self, policy: int):
         self._ck(self.lib.cb2_set_kernel_policy(self.h, int(policy)))

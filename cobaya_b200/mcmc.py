@@ -29,7 +29,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-from .convergence import rminus1_from_sums
+from .convergence import rminus1_cl_from_sums, rminus1_from_sums
 from .engine import (FLAG_INTERNAL, FLAG_ROWS_FULL, FLAG_STUCK, MOMENTS_HALVES,
                      MOMENTS_SINGLE_SPLIT, Engine)
 from .flatmodel import FlatModel
@@ -307,6 +307,22 @@ class EnsembleMCMC:
         local = eng.moments(mode=mode, split=split, shift=self._shift)
         return np.asarray(d.all_reduce_sum(local))
 
+    def _bounds(self, mode, split, limfrac):
+        """Per-chain confidence bounds -> all-reduced sums (mcmc.py:918-939)."""
+        eng, d = self.engine, self.dist
+        n = 1 + 4 * self.fm.D
+        if isinstance(d, TorchDist) and d.backend == "nccl":
+            if self._mom_buf is None:
+                self._mom_buf = d.buffer(eng.moments_len)
+            buf = self._mom_buf[:n]
+            eng.bounds(limfrac, mode=mode, split=split, shift=self._shift,
+                       dev_ptr=buf.data_ptr(), host=False)
+            eng.sync()
+            d.all_reduce_tensor_(buf)
+            return buf.cpu().numpy()
+        local = eng.bounds(limfrac, mode=mode, split=split, shift=self._shift)
+        return np.asarray(d.all_reduce_sum(local))
+
     def check_convergence_and_learn_proposal(self):
         """mcmc.py:773-1032 on all-reduced sums; identical result on every rank."""
         o = self.opts
@@ -332,11 +348,24 @@ class EnsembleMCMC:
                  res["N"])
         converged_means = max(Rminus1, self.Rminus1_last) < o["Rminus1_stop"]  # :908
         if converged_means:
-            # The R-1 of the confidence-interval bounds (mcmc.py:918-1002) needs per-chain
-            # weighted quantiles (GetDist in the reference); not evaluated by this engine
-            # yet: convergence is declared on the means.
-            log.info("The run has converged (criterion: R-1 of means, twice in a row).")
-            self.converged = True
+            # R-1 of the confidence-interval bounds (mcmc.py:918-1002): per-chain weighted
+            # quantiles at Rminus1_cl_level/2 on the device, std over chains / sqrt(diag W)
+            try:
+                mode = MOMENTS_HALVES if self.n_chains > 1 else MOMENTS_SINGLE_SPLIT
+                bsums = self._bounds(mode, int(o["Rminus1_single_split"]),
+                                     float(o["Rminus1_cl_level"]) / 2.0)
+                Rminus1_cl = rminus1_cl_from_sums(bsums, self.fm.D, res["W"])
+            except Exception as e:  # mcmc.py:936-938,999-1002
+                log.info("Computation of the bounds was not possible (%s). "
+                         "Waiting until the next converge check.", e)
+                Rminus1_cl = None
+            if Rminus1_cl is not None:
+                cp.Rminus1_cl = Rminus1_cl
+                log.info(" - Convergence of bounds: R-1 = %f after %d accepted steps",
+                         Rminus1_cl, res["N"])
+                if Rminus1_cl < o["Rminus1_cl_stop"]:  # mcmc.py:994-996
+                    self.converged = True
+                    log.info("The run has converged!")
         self.Rminus1_last = Rminus1
         self._shift = np.asarray(res["mean"], dtype=np.float64)
         learn, msg = decide_learning(o, Rminus1, self.converged)

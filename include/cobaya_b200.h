@@ -121,6 +121,14 @@ int cb2_summary(cb2_engine *h, int64_t out[8]);
 int cb2_moments(cb2_engine *h, int32_t mode, int32_t split, const double *shift,
                 double *dev_out, double *host_out);
 
+/* R-1 of the confidence-interval bounds (mcmc.py:918-1002): per (virtual) chain the raw
+ * weighted sample quantiles at limfrac and 1-limfrac of every sampled parameter (GetDist
+ * `MCSamples.confidence`, mcmc.py:926-929 with limfrac = Rminus1_cl_level/2), summed into
+ * out[1+4D] = { M, sum (low-shift)[D], sum (low-shift)^2[D], sum (up-shift)[D],
+ * sum (up-shift)^2[D] } for the NCCL all-reduce.  mode/split/shift as in cb2_moments. */
+int cb2_bounds(cb2_engine *h, int32_t mode, int32_t split, double limfrac,
+               const double *shift, double *dev_out, double *host_out);
+
 /* SampleCollection rows (collection.py:154-159,519-542) of one chain:
  * out[n*width], width = cb2_row_width. Returns number of rows copied (>=0). */
 int64_t cb2_copy_rows(cb2_engine *h, int64_t chain, int64_t row_begin, int64_t n,
@@ -146,6 +154,7 @@ int cb2_kernel_times(cb2_engine *h, double ms[4], int64_t n[4], int32_t reset);
 /* which step kernel the last cb2_advance used: 0 = general warp-per-chain,
  * 1 = DMMA (mma.sync.m8n8k4.f64) register-resident, 2 = DMMA producer/consumer */
 int cb2_last_step_kernel(const cb2_engine *h);
+const char *cb2_debug_message(const cb2_engine *h); /* why a faster kernel was not used */
 /* 0 auto, 1 force the general kernels, 2 fast kernels without the producer/consumer one */
 int cb2_set_kernel_policy(cb2_engine *h, int32_t policy);
 

@@ -413,3 +413,44 @@ def test_producer_consumer_kernel_blocks_normal_prior_thinning(cuda_lib):
         np.testing.assert_allclose(rows, rows_ref, rtol=RTOL, atol=ATOL)
         np.testing.assert_allclose(st["x"][c], s_ref["x"], rtol=RTOL, atol=ATOL)
         assert st["weight"][c] == s_ref["weight"]
+
+
+def test_confidence_bounds_match_numpy(cuda_lib):
+    """cb2_bounds vs the weighted-quantile definition (sort, cumsum, searchsorted) restated
+    with numpy on the same rows; Rminus1_cl as mcmc.py:977-982."""
+    from cobaya_b200.convergence import rminus1_cl_from_sums, rminus1_from_sums
+    from cobaya_b200.flatmodel import FlatModel, synthetic_gaussian_cov
+
+    D, C, n = 7, 13, 900
+    cov = synthetic_gaussian_cov(D)
+    fm = FlatModel.gaussian(np.full(D, 0.1), cov, proposal_cov=cov)
+    x0 = 0.1 + np.random.default_rng(3).multivariate_normal(np.zeros(D), cov, size=C)
+    eng = _engine(fm, C, seed=8, rows_cap=n)
+    eng.set_state(x0)
+    eng.advance(n)
+    shift = np.full(D, 0.1)
+    limfrac = 0.95 / 2
+    bs = eng.bounds(limfrac, shift=shift)
+    lows, ups = [], []
+    for c in range(C):
+        rows = eng.rows(c)
+        r = rows[len(rows) // 2:]
+        lo, up = [], []
+        for i in range(D):
+            v, w = r[:, 2 + i], r[:, 0]
+            idx = np.argsort(v, kind="stable")
+            cs = np.cumsum(w[idx])
+            for frac, dst in ((limfrac, lo), (1 - limfrac, up)):
+                ix = min(np.searchsorted(cs, cs[-1] * frac), len(v) - 1)
+                dst.append(v[idx[ix]])
+        lows.append(lo); ups.append(up)
+    lows, ups = np.array(lows), np.array(ups)
+    assert bs[0] == C
+    np.testing.assert_allclose(bs[1:1 + D], (lows - shift).sum(0), rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(bs[1 + D:1 + 2 * D], ((lows - shift) ** 2).sum(0), rtol=1e-12)
+    np.testing.assert_allclose(bs[1 + 2 * D:1 + 3 * D], (ups - shift).sum(0), rtol=1e-12,
+                               atol=1e-15)
+    res = rminus1_from_sums(eng.moments(shift=shift), D, shift)
+    want = max(np.max(np.std(lows, axis=0) / np.sqrt(np.diag(res["W"]))),
+               np.max(np.std(ups, axis=0) / np.sqrt(np.diag(res["W"]))))
+    np.testing.assert_allclose(rminus1_cl_from_sums(bs, D, res["W"]), want, rtol=1e-7)
