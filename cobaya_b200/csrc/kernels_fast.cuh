@@ -653,7 +653,7 @@ static inline bool pc_step_supported(const ModelDev &M, const FastPackDesc &P) {
 }
 
 template <int NT>
-__global__ void __maxnreg__(144)
+__global__ void __launch_bounds__(448, 1)
 k_step_pc(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gpack,
           FastPackDesc P, const double2 *__restrict__ draws, int64_t n_chains, uint64_t t0,
           int n_steps, int wpc) {
@@ -749,6 +749,8 @@ k_step_pc(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gpac
                     else u[n][h] = (j == 0) ? 1.0 : 0.0;
                 }
         };
+        // `un` holds the direction of the next step; it becomes v in place, and is refilled
+        // (prefetch) as soon as T v has been issued
         double un[NT][2];
         double rs_next;
         {
@@ -761,12 +763,15 @@ k_step_pc(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gpac
         for (int s = 0; s < n_steps; ++s) {
             const int slot = s % CB2_PC_RING;
             const uint32_t use = (uint32_t)(s / CB2_PC_RING);
-            double v[NT][2];
 #pragma unroll
             for (int n = 0; n < NT; ++n) {
-                v[n][0] = un[n][0] * rs_next * M.proposal_scale;
-                v[n][1] = un[n][1] * rs_next * M.proposal_scale;
+                un[n][0] = un[n][0] * rs_next * M.proposal_scale;
+                un[n][1] = un[n][1] * rs_next * M.proposal_scale;
             }
+            double dl[NT][2];
+#pragma unroll
+            for (int n = 0; n < NT; ++n) { dl[n][0] = 0.0; dl[n][1] = 0.0; }
+            warp_matvec8<NT, true>(Tf, lane, un, dl);
             if (s + 1 < n_steps) {
                 int nb, j0;
                 const double *Rk;
@@ -774,10 +779,6 @@ k_step_pc(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gpac
                 fetch(nb, j0, Rk, un);
                 rs_next = my_draws[s + 1].x;
             }
-            double dl[NT][2];
-#pragma unroll
-            for (int n = 0; n < NT; ++n) { dl[n][0] = 0.0; dl[n][1] = 0.0; }
-            warp_matvec8<NT, true>(Tf, lane, v, dl);
             // wait until the consumer released this slot (first pass: free)
             if (use > 0)
                 mbar_wait((uint32_t)__cvta_generic_to_shared(&mbar_empty[pair * CB2_PC_RING + slot]),
@@ -846,7 +847,6 @@ k_step_pc(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gpac
             mbar_wait((uint32_t)__cvta_generic_to_shared(&mbar_full[pair * CB2_PC_RING + slot]),
                       use & 1u);
             const double2 *sl = reinterpret_cast<const double2 *>(ring + (size_t)slot * SLOT);
-            double xt[NT][2], yt[NT][2];
             bool bad = false;
             double ps = 0.0, qsum = 0.0;
 #pragma unroll
@@ -855,26 +855,24 @@ k_step_pc(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gpac
                 const double2 w2 = sl[(NT + n) * 32 + lane];
                 const double2 lo2 = *reinterpret_cast<const double2 *>(lower + 8 * n + 2 * r);
                 const double2 up2 = *reinterpret_cast<const double2 *>(upper + 8 * n + 2 * r);
-                xt[n][0] = xs[n][0] + d2.x;
-                xt[n][1] = xs[n][1] + d2.y;
-                yt[n][0] = ys[n][0] + w2.x;
-                yt[n][1] = ys[n][1] + w2.y;
-                qsum += yt[n][0] * yt[n][0] + yt[n][1] * yt[n][1];
-                if (!(xt[n][0] <= up2.x) || !(xt[n][0] >= lo2.x) || !isfinite(xt[n][0])) bad = true;
-                if (!(xt[n][1] <= up2.y) || !(xt[n][1] >= lo2.y) || !isfinite(xt[n][1])) bad = true;
+                const double x0 = xs[n][0] + d2.x, x1 = xs[n][1] + d2.y;
+                const double y0 = ys[n][0] + w2.x, y1 = ys[n][1] + w2.y;
+                qsum += y0 * y0 + y1 * y1;
+                if (!(x0 <= up2.x) || !(x0 >= lo2.x) || !isfinite(x0)) bad = true;
+                if (!(x1 <= up2.y) || !(x1 >= lo2.y) || !isfinite(x1)) bad = true;
                 if (M.any_normal) {
-#pragma unroll
-                    for (int h = 0; h < 2; ++h)
-                        if ((m_norm >> (2 * n + h)) & 1u) {
-                            const int j = 8 * n + 2 * r + h;
-                            const double zz = (xt[n][h] - pack[P.off_loc + j]) / pack[P.off_isc + j];
-                            ps += pack[P.off_mls + j] - zz * zz / 2;
-                        }
+                    if ((m_norm >> (2 * n)) & 1u) {
+                        const int j = 8 * n + 2 * r;
+                        const double zz = (x0 - pack[P.off_loc + j]) / pack[P.off_isc + j];
+                        ps += pack[P.off_mls + j] - zz * zz / 2;
+                    }
+                    if ((m_norm >> (2 * n + 1)) & 1u) {
+                        const int j = 8 * n + 2 * r + 1;
+                        const double zz = (x1 - pack[P.off_loc + j]) / pack[P.off_isc + j];
+                        ps += pack[P.off_mls + j] - zz * zz / 2;
+                    }
                 }
             }
-            __syncwarp();
-            if (lane == 0)  // the slot's contents are in registers: hand it back
-                mbar_arrive((uint32_t)__cvta_generic_to_shared(&mbar_empty[pair * CB2_PC_RING + slot]));
             bad = __shfl_xor_sync(0xffffffffu, (int)bad, 1) | (int)bad;
             bad = __shfl_xor_sync(0xffffffffu, (int)bad, 2) | (int)bad;
             qsum = quad_sum(qsum);
@@ -925,9 +923,11 @@ k_step_pc(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gpac
                     }
                 } else burn_left -= 1;
 #pragma unroll
-                for (int n = 0; n < NT; ++n) {
-                    xs[n][0] = xt[n][0]; xs[n][1] = xt[n][1];
-                    ys[n][0] = yt[n][0]; ys[n][1] = yt[n][1];
+                for (int n = 0; n < NT; ++n) {  // same sums as in the evaluation above
+                    const double2 d2 = sl[n * 32 + lane];
+                    const double2 w2 = sl[(NT + n) * 32 + lane];
+                    xs[n][0] += d2.x; xs[n][1] += d2.y;
+                    ys[n][0] += w2.x; ys[n][1] += w2.y;
                 }
                 logpost = t_post; logprior = t_prior; loglike = t_like;
                 weight = 1; prior_rej = 0; n_acc += 1;
@@ -937,6 +937,9 @@ k_step_pc(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gpac
                 const long long sgn = (burn_left > 0) - (burn_left < 0);
                 if (weight - prior_rej > M.max_tries * (1 + 9 * sgn)) flags |= CB2_FLAG_STUCK;
             }
+            __syncwarp();
+            if (lane == 0)  // hand the slot back to the producer
+                mbar_arrive((uint32_t)__cvta_generic_to_shared(&mbar_empty[pair * CB2_PC_RING + slot]));
         }
         __syncwarp();
         if (active) {
