@@ -49,6 +49,11 @@ static int pack_fast(cb2_engine *h) {
     P.off_lower = take(DP); P.off_upper = take(DP); P.off_loc = take(DP);
     P.off_mls = take(DP); P.off_isc = take(DP); P.off_flags = take(DP); P.off_iofj = take(DP);
     P.total = o;
+    {
+        bool ident = (D == DP) && (row_width(h) % 2 == 0);
+        for (int j = 0; j < D; ++j) ident = ident && (h->i_of_j[j] == j);
+        P.iofj_identity = ident ? 1 : 0;
+    }
     if ((size_t)P.total * 8 > 190 * 1024) return 0;  // does not fit: general path
     std::vector<double> pk(P.total, 0.0);
     // T (sorted coordinates already)

@@ -197,6 +197,7 @@ struct FastPackDesc {
     int off_lower, off_upper, off_loc, off_mls, off_isc;  // [DP] each (mls = -log s - log(2pi)/2, isc = s)
     int off_flags; // [DP] as doubles: bit0 normal prior, bit1 periodic
     int off_iofj;  // [DP] as doubles: sampler index of sorted j (or -1 for padding)
+    int iofj_identity;  // D == DP, i_of_j[j] == j and the row stride keeps 16-byte alignment
     int total;     // doubles
 };
 
@@ -648,17 +649,30 @@ __device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
     }
 }
 
+// loads that must be ISSUED where they are written (prefetch): asm volatile keeps their
+// program order relative to the (asm volatile) MMAs, the scoreboard wait happens at first use
+__device__ __forceinline__ double ldg_f64_early(const double *p) {
+    double v;
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double2 ldg_f64x2_early(const double2 *p) {
+    double2 v;
+    asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+
 static inline bool pc_step_supported(const ModelDev &M, const FastPackDesc &P) {
     return P.n_modes == 1 && !M.any_periodic;
 }
 
-template <int NT>
+template <int NT, bool HAS_NORMAL>
 __global__ void __launch_bounds__(448, 1)
 k_step_pc(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gpack,
           FastPackDesc P, const double2 *__restrict__ draws, int64_t n_chains, uint64_t t0,
           int n_steps, int wpc) {
     constexpr int DP = NT * 8;
-    constexpr int SLOT = 2 * NT * 32 * 2;  // doubles per ring slot: delta + w, fragment order
+    constexpr int SLOT = 2 * NT * 32 * 2 + 8;  // ring slot: delta + w (fragment order) + 8 accept draws
     extern __shared__ __align__(16) double fsm[];
     __shared__ __align__(8) unsigned long long mbar_pack;
     __shared__ __align__(8) unsigned long long mbar_full[8 * CB2_PC_RING];
@@ -745,28 +759,29 @@ k_step_pc(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gpac
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int j = 8 * n + 2 * r + h - j0;
-                    if (nb >= 2) u[n][h] = (j >= 0 && j < nb) ? Rk[j] : 0.0;
+                    if (nb >= 2) u[n][h] = (j >= 0 && j < nb) ? ldg_f64_early(Rk + j) : 0.0;
                     else u[n][h] = (j == 0) ? 1.0 : 0.0;
                 }
         };
         // `un` holds the direction of the next step; it becomes v in place, and is refilled
         // (prefetch) as soon as T v has been issued
         double un[NT][2];
-        double rs_next;
+        double2 dr_next;  // {radius, Exp(1) of the accept test} of the next step
         {
             int nb, j0;
             const double *Rk;
             locate(0, nb, j0, Rk);
             fetch(nb, j0, Rk, un);
-            rs_next = my_draws[0].x;
+            dr_next = ldg_f64x2_early(my_draws);
         }
         for (int s = 0; s < n_steps; ++s) {
             const int slot = s % CB2_PC_RING;
             const uint32_t use = (uint32_t)(s / CB2_PC_RING);
+            const double rs_cur = dr_next.x, e_cur = dr_next.y;
 #pragma unroll
             for (int n = 0; n < NT; ++n) {
-                un[n][0] = un[n][0] * rs_next * M.proposal_scale;
-                un[n][1] = un[n][1] * rs_next * M.proposal_scale;
+                un[n][0] = un[n][0] * rs_cur * M.proposal_scale;
+                un[n][1] = un[n][1] * rs_cur * M.proposal_scale;
             }
             double dl[NT][2];
 #pragma unroll
@@ -777,7 +792,7 @@ k_step_pc(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gpac
                 const double *Rk;
                 locate(s + 1, nb, j0, Rk);
                 fetch(nb, j0, Rk, un);
-                rs_next = my_draws[s + 1].x;
+                dr_next = ldg_f64x2_early(my_draws + s + 1);
             }
             // wait until the consumer released this slot (first pass: free)
             if (use > 0)
@@ -794,6 +809,7 @@ k_step_pc(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gpac
 #pragma unroll
             for (int n = 0; n < NT; ++n)
                 sl[(NT + n) * 32 + lane] = make_double2(wv[n][0], wv[n][1]);
+            if (r == 0) ring[(size_t)slot * SLOT + 2 * NT * 64 + q] = e_cur;
             __syncwarp();
             if (lane == 0)
                 mbar_arrive((uint32_t)__cvta_generic_to_shared(&mbar_full[pair * CB2_PC_RING + slot]));
@@ -838,14 +854,12 @@ k_step_pc(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gpac
                   n_rows = S.n_rows[chain], n_acc = S.n_acc[chain];
         uint32_t flags = S.flags[chain];
         const double c0 = pack[P.off_c0];
-        double e_next = my_draws[0].y;
         for (int s = 0; s < n_steps; ++s) {
             const int slot = s % CB2_PC_RING;
             const uint32_t use = (uint32_t)(s / CB2_PC_RING);
-            const double e_acc = e_next;
-            if (s + 1 < n_steps) e_next = my_draws[s + 1].y;
             mbar_wait((uint32_t)__cvta_generic_to_shared(&mbar_full[pair * CB2_PC_RING + slot]),
                       use & 1u);
+            const double e_acc = ring[(size_t)slot * SLOT + 2 * NT * 64 + q];
             const double2 *sl = reinterpret_cast<const double2 *>(ring + (size_t)slot * SLOT);
             bool bad = false;
             double ps = 0.0, qsum = 0.0;
@@ -860,7 +874,7 @@ k_step_pc(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gpac
                 qsum += y0 * y0 + y1 * y1;
                 if (!(x0 <= up2.x) || !(x0 >= lo2.x) || !isfinite(x0)) bad = true;
                 if (!(x1 <= up2.y) || !(x1 >= lo2.y) || !isfinite(x1)) bad = true;
-                if (M.any_normal) {
+                if (HAS_NORMAL) {
                     if ((m_norm >> (2 * n)) & 1u) {
                         const int j = 8 * n + 2 * r;
                         const double zz = (x0 - pack[P.off_loc + j]) / pack[P.off_isc + j];
@@ -876,7 +890,7 @@ k_step_pc(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gpac
             bad = __shfl_xor_sync(0xffffffffu, (int)bad, 1) | (int)bad;
             bad = __shfl_xor_sync(0xffffffffu, (int)bad, 2) | (int)bad;
             qsum = quad_sum(qsum);
-            if (M.any_normal) ps = quad_sum(ps);
+            if (HAS_NORMAL) ps = quad_sum(ps);
             const double t_prior = bad ? -CUDART_INF : (M.uniform_logp + ps);
             const double t_like = -0.5 * (c0 + qsum);
             const double t_post = bad ? -CUDART_INF : (t_prior + t_like);
@@ -910,13 +924,20 @@ k_step_pc(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gpac
                                     row[4 + D] = -2 * loglike;
                                     row[5 + D] = -2 * loglike;
                                 }
+                                if (P.iofj_identity) {  // D == DP, sorted == sampler order
 #pragma unroll
-                                for (int n = 0; n < NT; ++n)
+                                    for (int n = 0; n < NT; ++n)
+                                        *reinterpret_cast<double2 *>(row + 2 + 8 * n + 2 * r) =
+                                            make_double2(xs[n][0], xs[n][1]);
+                                } else {
 #pragma unroll
-                                    for (int h = 0; h < 2; ++h) {
-                                        const int i = iofj[8 * n + 2 * r + h];
-                                        if (i >= 0) row[2 + i] = xs[n][h];
-                                    }
+                                    for (int n = 0; n < NT; ++n)
+#pragma unroll
+                                        for (int h = 0; h < 2; ++h) {
+                                            const int i = iofj[8 * n + 2 * r + h];
+                                            if (i >= 0) row[2 + i] = xs[n][h];
+                                        }
+                                }
                             }
                             n_rows += 1;
                         }
@@ -971,15 +992,24 @@ static int launch_step_pc_t(cudaStream_t st, const ModelDev &M, const ChainState
     if (wpc < 1) wpc = 1;
     if (wpc > 7) wpc = 7;
     const int grid = (int)((tiles + wpc - 1) / wpc);
-    const size_t slot = (size_t)2 * NT * 32 * 2;
+    const size_t slot = (size_t)2 * NT * 32 * 2 + 8;
     const size_t smem = ((size_t)P.total + (size_t)wpc * CB2_PC_RING * slot) * 8 +
                         (size_t)wpc * 8 * 3 * CB2_MAX_BLOCKS * sizeof(int);
     if (smem > 220 * 1024) return -2;
-    cudaError_t e = cudaFuncSetAttribute(k_step_pc<NT>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return -1000 - (int)e;
-    k_step_pc<NT><<<grid, 2 * wpc * 32, smem, st>>>(M, S, W, gpack, P, draws, n_chains, t0,
-                                                     n_steps, wpc);
+    cudaError_t e;
+    if (M.any_normal) {
+        e = cudaFuncSetAttribute(k_step_pc<NT, true>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return -1000 - (int)e;
+        k_step_pc<NT, true><<<grid, 2 * wpc * 32, smem, st>>>(M, S, W, gpack, P, draws, n_chains,
+                                                               t0, n_steps, wpc);
+    } else {
+        e = cudaFuncSetAttribute(k_step_pc<NT, false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return -1000 - (int)e;
+        k_step_pc<NT, false><<<grid, 2 * wpc * 32, smem, st>>>(M, S, W, gpack, P, draws,
+                                                                n_chains, t0, n_steps, wpc);
+    }
     e = cudaGetLastError();
     return e == cudaSuccess ? 0 : -2000 - (int)e;
 }
