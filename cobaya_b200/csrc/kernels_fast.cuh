@@ -106,14 +106,16 @@ k_basis_fast(uint32_t key0, uint32_t key1, uint64_t chain_id0, int block, int n,
         for (int m = 8 * G; m < m_end; ++m) {
             // this thread's pairs of group g >= 2G: columns 4g+2*half, +1 -> double2 index 2g+half
             const double2 *x2 = reinterpret_cast<const double2 *>(X + m * NP) + half;
-            double t0 = 0.0, t1 = 0.0;
+            double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
 #pragma unroll
-            for (int g = 2 * G; g < NP / 4; ++g) {
-                const double2 a = x2[2 * g];
+            for (int g = 2 * G; g < NP / 4; g += 2) {  // NP/4 - 2G is even
+                const double2 a = x2[2 * g], b = x2[2 * g + 2];
                 t0 = fma(h[2 * g], a.x, t0);
                 t1 = fma(h[2 * g + 1], a.y, t1);
+                t2 = fma(h[2 * g + 2], b.x, t2);
+                t3 = fma(h[2 * g + 3], b.y, t3);
             }
-            double tmp = t0 + t1;
+            double tmp = (t0 + t1) + (t2 + t3);
             tmp += __shfl_xor_sync(0xffffffffu, tmp, 1);
 #pragma unroll
             for (int g = 2 * G; g < NP / 4; ++g) {
@@ -230,13 +232,18 @@ __device__ __forceinline__ void warp_matvec8(const double *__restrict__ frag, in
     const double2 *f2 = reinterpret_cast<const double2 *>(frag) + lane;
 #pragma unroll
     for (int m = 0; m < NT; ++m) {
+        // all B fragments of this k-block first, then the MMAs ordered so that consecutive
+        // instructions update DIFFERENT accumulators (no back-to-back dependent DMMAs)
+        double2 b[NT];
 #pragma unroll
         for (int nt = TRI ? m : 0; nt < NT; ++nt) {
             const int blk = TRI ? (nt * (nt + 1)) / 2 + m : nt * NT + m;
-            const double2 b = f2[blk * 32];
-            dmma8x8x4(out[nt][0], out[nt][1], a[m][0], b.x);
-            dmma8x8x4(out[nt][0], out[nt][1], a[m][1], b.y);
+            b[nt] = f2[blk * 32];
         }
+#pragma unroll
+        for (int nt = TRI ? m : 0; nt < NT; ++nt) dmma8x8x4(out[nt][0], out[nt][1], a[m][0], b[nt].x);
+#pragma unroll
+        for (int nt = TRI ? m : 0; nt < NT; ++nt) dmma8x8x4(out[nt][0], out[nt][1], a[m][1], b[nt].y);
     }
 }
 
