@@ -1200,7 +1200,8 @@ extern "C" int cb2_kernel_times(cb2_engine *h, double ms[4], int64_t n[4], int32
 
 extern "C" int cb2_set_kernel_policy(cb2_engine *h, int32_t policy) {
     if (!h) return -1;
-    h->policy = policy;
+    h->policy = policy & 3;
+    g_basis_wy = (policy & 4) ? 0 : 1;  // +4: Householder sweep with DFMA (k_basis_fast)
     return 0;
 }
 

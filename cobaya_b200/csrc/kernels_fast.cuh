@@ -14,6 +14,14 @@
 #include "common.cuh"
 #include "kernels_general.cuh"
 
+// D[8x8] += A[8x4] B[4x8] in fp64 on the tensor pipe.  Lane l = 4q + r holds
+// A[q][r], B[r][q], D[q][2r], D[q][2r+1].
+__device__ __forceinline__ void dmma8x8x4(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
 // =====================================================================================
 // Haar basis, n <= 64
 // =====================================================================================
@@ -137,12 +145,206 @@ k_basis_fast(uint32_t key0, uint32_t key1, uint64_t chain_id0, int block, int n,
     }
 }
 
+// -------------------------------------------------------------------------------------
+// k_basis_wy<NG>: the same Haar basis with the Householder sweep on the FP64 TENSOR pipe.
+// Reflectors are grouped 8 at a time in compact-WY form (LAPACK dlarft, forward/columnwise):
+//   G_{m0} ... G_{m0+7} = I - V T V^T,  V = [x_{m0} .. x_{m0+7}],  T upper triangular,
+//   T_jj = 1,  T[0:j, j] = -T[0:j,0:j] (V[:,0:j]^T v_j)        (|x_m|^2 = 2  =>  tau = 1)
+// and H <- H - ((H V) T) V^T is three small matrix products per group, issued as m8n8k4 DMMA
+// tiles.  4 warps per basis, warp w owns rows 16w..16w+15 of H in C-fragment layout (lane
+// (q,r): H[row q][cols 8nt+2r, +1]); with the even/odd k interleave a C fragment is directly
+// an A fragment.  Same matrix as functions.py:48-58 up to rounding (~1e-15).
+// -------------------------------------------------------------------------------------
+template <int NG>
+__global__ void __launch_bounds__(128, 4)
+k_basis_wy(uint32_t key0, uint32_t key1, uint64_t chain_id0, int block, int n,
+           const int64_t *__restrict__ vis, int vis_stride, uint32_t e0_fixed, int cnt,
+           double *__restrict__ store, int64_t task0, int64_t store_task0) {
+    constexpr int NP = NG * 8;
+    constexpr int LDX = NP + 1;  // odd row stride: both B-fragment access patterns spread banks
+    extern __shared__ __align__(16) double fsm[];
+    double *X = fsm;                    // [NP][LDX]: X[m][c] = x_m[c-m] for c >= m, else 0
+    double *Dv = X + NP * LDX;          // [NP]
+    double *inv = Dv + NP;              // [NP]
+    double *Sg = inv + NP;              // [NG][8][8] Gram (strict upper) per group
+    double *Tg = Sg + NG * 64;          // [NG][8][8] T per group
+    const int tid = threadIdx.x, nt_ = blockDim.x;
+    const int64_t task = task0 + blockIdx.x;
+    const int64_t chain = task / cnt;
+    const uint32_t e0 = vis ? (uint32_t)(vis[chain * vis_stride + block] / n) : e0_fixed;
+    const uint32_t epoch = e0 + (uint32_t)(task % cnt);
+    const uint64_t gid = chain_id0 + (uint64_t)chain;
+    for (int e = tid; e < NP * LDX; e += nt_) X[e] = 0.0;
+    __syncthreads();
+    const int nn = (n + 2) * (n - 1) / 2;
+    {
+        int m = 0, base = 0;
+        for (int p = tid; p < (nn + 1) / 2; p += nt_) {
+            double z[2];
+            draw_normal_pair(key0, key1, gid, block, epoch, (uint32_t)p, z[0], z[1]);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int q = 2 * p + h;
+                if (q < nn) {
+                    while (q >= base + (n - m)) {
+                        base += n - m;
+                        ++m;
+                    }
+                    X[m * LDX + m + (q - base)] = z[h];
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < n - 1) {  // functions.py:49-55
+        const int m = tid, len = n - m;
+        const double *x = X + m * LDX + m;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int i = 0;
+        for (; i + 4 <= len; i += 4) {
+            s0 = fma(x[i], x[i], s0);
+            s1 = fma(x[i + 1], x[i + 1], s1);
+            s2 = fma(x[i + 2], x[i + 2], s2);
+            s3 = fma(x[i + 3], x[i + 3], s3);
+        }
+        for (; i < len; ++i) s0 = fma(x[i], x[i], s0);
+        const double norm2 = (s0 + s1) + (s2 + s3);
+        const double x0 = x[0];
+        const double d = (x0 != 0.0) ? (x0 > 0 ? 1.0 : -1.0) : 1.0;
+        const double x0n = x0 + d * sqrt(norm2);
+        X[m * LDX + m] = x0n;
+        inv[m] = 1.0 / sqrt((norm2 - x0 * x0 + x0n * x0n) / 2.0);
+        Dv[m] = d;
+    }
+    __syncthreads();
+    for (int e = tid; e < (n - 1) * NP; e += nt_) {
+        const int m = e / NP, c = e % NP;
+        X[m * LDX + c] *= inv[m];
+    }
+    if (tid == 0) {  // functions.py:59
+        double prod = 1.0;
+        for (int m = 0; m < n - 1; ++m) prod *= Dv[m];
+        Dv[n - 1] = (((n - 1) & 1) ? -1.0 : 1.0) * prod;
+    }
+    __syncthreads();
+    // Gram entries S_g[i][j] = x_{8g+i} . x_{8g+j}, i < j   (28 per group)
+    for (int e = tid; e < NG * 28; e += nt_) {
+        const int g = e / 28;
+        int k = e % 28, i = 0;
+        while (k >= 7 - i) { k -= 7 - i; ++i; }
+        const int j = i + 1 + k;
+        const double *xi = X + (8 * g + i) * LDX, *xj = X + (8 * g + j) * LDX;
+        double a0 = 0.0, a1 = 0.0;
+        for (int c = 8 * g + j; c + 1 < NP; c += 2) {  // x_j vanishes before column 8g+j
+            a0 = fma(xi[c], xj[c], a0);
+            a1 = fma(xi[c + 1], xj[c + 1], a1);
+        }
+        if ((NP - (8 * g + j)) & 1) a0 = fma(xi[NP - 1], xj[NP - 1], a0);
+        Sg[g * 64 + i * 8 + j] = a0 + a1;
+    }
+    __syncthreads();
+    if (tid < NG) {  // T of group tid (dlarft)
+        const int g = tid;
+        double *T = Tg + g * 64;
+        const double *S = Sg + g * 64;
+        for (int i = 0; i < 8; ++i)
+            for (int j = 0; j < 8; ++j) T[i * 8 + j] = (i == j) ? 1.0 : 0.0;
+        for (int j = 1; j < 8; ++j)
+            for (int i = 0; i < j; ++i) {
+                double acc = 0.0;
+                for (int l = i; l < j; ++l) acc = fma(T[i * 8 + l], S[l * 8 + j], acc);
+                T[i * 8 + j] = -acc;
+            }
+    }
+    __syncthreads();
+    // ---- sweep on the tensor pipe
+    const int lane = tid & 31, w = tid >> 5, q = lane >> 2, r = lane & 3;
+    double hreg[2][NG][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NG; ++nt)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                hreg[mt][nt][h] = (16 * w + 8 * mt + q == 8 * nt + 2 * r + h) ? 1.0 : 0.0;
+    if (16 * w < NP) {
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            if (8 * g >= n - 1) break;  // no reflectors left
+            const double *Xg = X + (8 * g) * LDX;
+            // Y = H[:, 8g:] V   (two partial accumulators per row tile for ILP)
+            double y[2][2][2];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int pa = 0; pa < 2; ++pa) { y[mt][pa][0] = 0.0; y[mt][pa][1] = 0.0; }
+#pragma unroll
+            for (int nt = g; nt < NG; ++nt)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const double b = Xg[q * LDX + 8 * nt + 2 * r + h];  // V[col][reflector q]
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt)
+                        dmma8x8x4(y[mt][(nt + h) & 1][0], y[mt][(nt + h) & 1][1], hreg[mt][nt][h], b);
+                }
+            // Z = Y T
+            double z[2][2];
+            const double *T = Tg + g * 64;
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                z[mt][0] = 0.0; z[mt][1] = 0.0;
+                const double ya = y[mt][0][0] + y[mt][1][0], yb = y[mt][0][1] + y[mt][1][1];
+                dmma8x8x4(z[mt][0], z[mt][1], ya, T[(2 * r) * 8 + q]);
+                dmma8x8x4(z[mt][0], z[mt][1], yb, T[(2 * r + 1) * 8 + q]);
+            }
+            // H[:, 8g:] -= Z V^T
+#pragma unroll
+            for (int nt = g; nt < NG; ++nt)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const double b = Xg[(2 * r + h) * LDX + 8 * nt + q];  // V^T[reflector][col]
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt)
+                        dmma8x8x4(hreg[mt][nt][0], hreg[mt][nt][1], -z[mt][h], b);
+                }
+        }
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            const int row = 16 * w + 8 * mt + q;
+            if (row < n) {
+                const double d = Dv[row];
+                double *out = store + (size_t)(task - store_task0) * (size_t)n * n;
+#pragma unroll
+                for (int nt = 0; nt < NG; ++nt)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int c = 8 * nt + 2 * r + h;
+                        if (c < n) out[(size_t)c * n + row] = d * hreg[mt][nt][h];
+                    }
+            }
+        }
+    }
+}
+
+static int g_basis_wy = 1;  // 1: Householder sweep on the tensor pipe (k_basis_wy)
+
 template <int NG>
 static int launch_basis_fast_t(cudaStream_t st, uint32_t k0, uint32_t k1, uint64_t chain_id0,
                                int block, int n, const int64_t *vis, int vis_stride,
                                uint32_t e0_fixed, int cnt, double *store, int64_t tasks,
                                int64_t task0, int64_t store_task0) {
     constexpr int NP = NG * 8;
+    if (g_basis_wy) {
+        const size_t smem_wy = (size_t)(NP * (NP + 1) + 2 * NP + 2 * NG * 64) * sizeof(double);
+        cudaError_t e2 = cudaFuncSetAttribute(k_basis_wy<NG>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)smem_wy);
+        if (e2 != cudaSuccess) return -1;
+        k_basis_wy<NG><<<(unsigned)tasks, 128, smem_wy, st>>>(
+            k0, k1, chain_id0, block, n, vis, vis_stride, e0_fixed, cnt, store, task0,
+            store_task0);
+        return cudaGetLastError() == cudaSuccess ? 0 : -1;
+    }
     const int threads = 2 * NP < 32 ? 32 : 2 * NP;
     const size_t smem = (size_t)(NP * NP + 2 * NP) * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(k_basis_fast<NG>,
@@ -211,11 +413,6 @@ static inline bool fast_step_supported(const ModelDev &M, size_t n_likes) {
     return true;
 }
 
-__device__ __forceinline__ void dmma8x8x4(double &d0, double &d1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(d0), "+d"(d1)
-                 : "d"(a), "d"(b));
-}
 
 __device__ __forceinline__ double quad_sum(double v) {
     v += __shfl_xor_sync(0xffffffffu, v, 1);

@@ -50,8 +50,9 @@ def test_logpost_matches_reference_known_answers(cuda_lib):
     np.testing.assert_allclose(der, ref[:, 3:], rtol=1e-9, atol=1e-12)
 
 
-@pytest.mark.parametrize("n", [2, 3, 7, 16, 64])
-def test_random_so_n_matches_reference_rvs(cuda_lib, n):
+@pytest.mark.parametrize("policy", [0, 4, 1])
+@pytest.mark.parametrize("n", [2, 3, 7, 16, 41, 64])
+def test_random_so_n_matches_reference_rvs(cuda_lib, n, policy):
     """Device Haar basis vs the reference's numba _rvs on the same normals (golden)."""
     from cobaya_b200.flatmodel import FlatModel
 
@@ -60,8 +61,14 @@ def test_random_so_n_matches_reference_rvs(cuda_lib, n):
     fm = FlatModel.gaussian(np.zeros(D), np.eye(D) * 0.01, blocks=[[0], list(range(1, D))],
                             oversampling=[1, 1], proposal_cov=np.eye(D) * 0.01)
     eng = _engine(fm, 20, seed=1234)
+    eng.set_kernel_policy(policy)  # 0: compact-WY DMMA sweep, 4: DFMA sweep, 1: general kernel
     R = eng.debug_basis(chain=17, block=1, epoch=5)
-    np.testing.assert_allclose(R, u[f"son_R_{n}"], rtol=0, atol=5e-14)
+    if f"son_R_{n}" in u:
+        ref = u[f"son_R_{n}"]   # the reference's numba _rvs on the same normals
+    else:
+        from oracle import oracle as orc
+        ref = orc.random_SO_N(n, 1234, 17, 1, 5)
+    np.testing.assert_allclose(R, ref, rtol=0, atol=5e-14)
     np.testing.assert_allclose(R @ R.T, np.eye(n), atol=1e-13)
     assert abs(np.linalg.det(R) - 1) < 1e-12
 

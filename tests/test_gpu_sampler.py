@@ -98,7 +98,7 @@ def test_64d_ensemble_learns_covmat_and_converges(cuda_lib):
     s = EnsembleMCMC(fm, x0, {"seed": 2, "chains_per_gpu": C, "Rminus1_stop": 0.05,
                               "rows_per_chain": 16000}).run()
     assert s.converged and s.Rminus1_last < 0.05
-    assert s.engine.last_step_kernel() == 1
+    assert s.engine.last_step_kernel() == 2
     assert any(c.learned for c in s.progress)
     mean, cv, res = s.mean_and_cov()
     sd = np.sqrt(np.diag(cov))
