@@ -283,6 +283,10 @@ def run_gpu_arm(args):
 
     for _ in range(W):
         one_step()
+    # the checkpoint kernels are part of the warm-up too (CUDA loads a kernel lazily on its
+    # first launch; a first checkpoint inside the timed region would time the module load)
+    smp._moments(0, 0)
+    smp._bounds(0, 0, 0.475)
     barrier()
     clocks = ClockSampler(local) if rank == 0 else None
     if clocks:
