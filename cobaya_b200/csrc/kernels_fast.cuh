@@ -196,69 +196,75 @@ k_basis_wy(uint32_t key0, uint32_t key1, uint64_t chain_id0, int block, int n,
         }
     }
     __syncthreads();
-    if (tid < n - 1) {  // functions.py:49-55
-        const int m = tid, len = n - m;
-        const double *x = X + m * LDX + m;
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        int i = 0;
-        for (; i + 4 <= len; i += 4) {
-            s0 = fma(x[i], x[i], s0);
-            s1 = fma(x[i + 1], x[i + 1], s1);
-            s2 = fma(x[i + 2], x[i + 2], s2);
-            s3 = fma(x[i + 3], x[i + 3], s3);
+    // functions.py:49-55 -- two threads per vector for the norm
+    {
+        const int m = tid >> 1, half = tid & 1;
+        double part = 0.0;
+        if (m < n - 1) {
+            const double *x = X + m * LDX + m;
+            const int len = n - m;
+            double s0 = 0.0, s1 = 0.0;
+            int i = half;
+            for (; i + 2 < len; i += 4) {
+                s0 = fma(x[i], x[i], s0);
+                s1 = fma(x[i + 2], x[i + 2], s1);
+            }
+            for (; i < len; i += 2) s0 = fma(x[i], x[i], s0);
+            part = s0 + s1;
         }
-        for (; i < len; ++i) s0 = fma(x[i], x[i], s0);
-        const double norm2 = (s0 + s1) + (s2 + s3);
-        const double x0 = x[0];
-        const double d = (x0 != 0.0) ? (x0 > 0 ? 1.0 : -1.0) : 1.0;
-        const double x0n = x0 + d * sqrt(norm2);
-        X[m * LDX + m] = x0n;
-        inv[m] = 1.0 / sqrt((norm2 - x0 * x0 + x0n * x0n) / 2.0);
-        Dv[m] = d;
+        const double norm2 = part + __shfl_xor_sync(0xffffffffu, part, 1);
+        if (m < n - 1 && half == 0) {
+            const double x0 = X[m * LDX + m];
+            const double d = (x0 != 0.0) ? (x0 > 0 ? 1.0 : -1.0) : 1.0;
+            const double x0n = x0 + d * sqrt(norm2);
+            X[m * LDX + m] = x0n;
+            inv[m] = 1.0 / sqrt((norm2 - x0 * x0 + x0n * x0n) / 2.0);
+            Dv[m] = d;
+        }
     }
     __syncthreads();
-    for (int e = tid; e < (n - 1) * NP; e += nt_) {
-        const int m = e / NP, c = e % NP;
-        X[m * LDX + c] *= inv[m];
-    }
+    for (int e = tid; e < (n - 1) * LDX; e += nt_) X[e] *= inv[e / LDX];  // x /= sc
     if (tid == 0) {  // functions.py:59
         double prod = 1.0;
         for (int m = 0; m < n - 1; ++m) prod *= Dv[m];
         Dv[n - 1] = (((n - 1) & 1) ? -1.0 : 1.0) * prod;
     }
     __syncthreads();
-    // Gram entries S_g[i][j] = x_{8g+i} . x_{8g+j}, i < j   (28 per group)
-    for (int e = tid; e < NG * 28; e += nt_) {
-        const int g = e / 28;
-        int k = e % 28, i = 0;
-        while (k >= 7 - i) { k -= 7 - i; ++i; }
-        const int j = i + 1 + k;
-        const double *xi = X + (8 * g + i) * LDX, *xj = X + (8 * g + j) * LDX;
-        double a0 = 0.0, a1 = 0.0;
-        for (int c = 8 * g + j; c + 1 < NP; c += 2) {  // x_j vanishes before column 8g+j
-            a0 = fma(xi[c], xj[c], a0);
-            a1 = fma(xi[c + 1], xj[c + 1], a1);
+    const int lane = tid & 31, w = tid >> 5, q = lane >> 2, r = lane & 3;
+    // Gram S_g = V_g^T V_g of every group on the tensor pipe (A and B fragments coincide:
+    // lane (q,r) holds x_{8g+q}[k = r]), then row i of T (dlarft) by lane i
+    for (int g = w; g < NG; g += 4) {
+        double s0 = 0.0, s1 = 0.0;
+        const double *xq = X + (8 * g + q) * LDX + 8 * g + r;
+#pragma unroll 4
+        for (int kk = 0; kk < (NP - 8 * g) / 4; ++kk) {
+            const double a = xq[4 * kk];
+            dmma8x8x4(s0, s1, a, a);
         }
-        if ((NP - (8 * g + j)) & 1) a0 = fma(xi[NP - 1], xj[NP - 1], a0);
-        Sg[g * 64 + i * 8 + j] = a0 + a1;
-    }
-    __syncthreads();
-    if (tid < NG) {  // T of group tid (dlarft)
-        const int g = tid;
-        double *T = Tg + g * 64;
-        const double *S = Sg + g * 64;
-        for (int i = 0; i < 8; ++i)
-            for (int j = 0; j < 8; ++j) T[i * 8 + j] = (i == j) ? 1.0 : 0.0;
-        for (int j = 1; j < 8; ++j)
-            for (int i = 0; i < j; ++i) {
+        double *S = Sg + g * 64;
+        S[q * 8 + 2 * r] = s0;
+        S[q * 8 + 2 * r + 1] = s1;
+        __syncwarp();
+        if (lane < 8) {
+            const int i = lane;
+            double *T = Tg + g * 64;
+            double trow[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) trow[j] = (j == i) ? 1.0 : 0.0;
+#pragma unroll
+            for (int j = 1; j < 8; ++j) {
                 double acc = 0.0;
-                for (int l = i; l < j; ++l) acc = fma(T[i * 8 + l], S[l * 8 + j], acc);
-                T[i * 8 + j] = -acc;
+#pragma unroll
+                for (int l = 0; l < 8; ++l)
+                    if (l >= i && l < j) acc = fma(trow[l], S[l * 8 + j], acc);
+                if (i < j) trow[j] = -acc;
             }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) T[i * 8 + j] = trow[j];
+        }
     }
     __syncthreads();
     // ---- sweep on the tensor pipe
-    const int lane = tid & 31, w = tid >> 5, q = lane >> 2, r = lane & 3;
     double hreg[2][NG][2];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
