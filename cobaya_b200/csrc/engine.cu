@@ -91,6 +91,7 @@ struct cb2_engine {
     DevBuf<double> d_basis[CB2_MAX_BLOCKS];
     DevBuf<double> d_basis_scratch;
     DevBuf<double2> d_draws;
+    DevBuf<int2> d_plan;
     // ---- moments
     DevBuf<MomentTask> d_tasks;
     DevBuf<double> d_means, d_sw, d_partials, d_mom_out, d_shift, d_bounds;
@@ -228,7 +229,7 @@ extern "C" int cb2_destroy(cb2_engine *h) {
     h->d_tape_main.release(); h->d_tape_slow.release(); h->d_tape_fast.release();
     h->d_perm_scratch.release();
     for (int b = 0; b < CB2_MAX_BLOCKS; ++b) h->d_basis[b].release();
-    h->d_basis_scratch.release(); h->d_draws.release(); h->d_tasks.release(); h->d_means.release();
+    h->d_basis_scratch.release(); h->d_draws.release(); h->d_plan.release(); h->d_tasks.release(); h->d_means.release();
     h->d_sw.release(); h->d_bounds.release(); h->d_partials.release(); h->d_mom_out.release(); h->d_shift.release();
     h->d_summary.release(); h->d_tmp.release();
     cudaEventDestroy(h->ev0);
@@ -826,18 +827,21 @@ extern "C" int cb2_advance(cb2_engine *h, int64_t n_proposals) {
         }
         if (fast_ok) {
             CK(h, h->d_draws.ensure((size_t)C * w));
+            CK(h, h->d_plan.ensure((size_t)C * w));
             h->prof_begin(PROF_TAPE);
-            if (launch_draws(h->stream, h->M, W, C, (uint64_t)h->steps_done, w, h->d_draws.p))
-                FAIL(h, -2, "draws kernel launch failed");
+            if (launch_draws(h->stream, h->M, h->S, W, C, (uint64_t)h->steps_done, w,
+                             h->d_draws.p, h->d_plan.p))
+                FAIL(h, -2, "draws/plan kernel launch failed");
             h->prof_end();
-            h->launches++;
+            h->launches += 2;
         }
         h->prof_begin(PROF_STEP);
         if (fast_ok) {
             rc = -2;
             if (h->policy != 2 && pc_step_supported(h->M, h->fast_desc)) {
                 rc = launch_step_pc(h->stream, h->M, h->S, W, h->d_fastpack.p, h->fast_desc,
-                                    h->d_draws.p, C, (uint64_t)h->steps_done, w, h->sm_count);
+                                    h->d_draws.p, h->d_plan.p, C, (uint64_t)h->steps_done, w,
+                                    h->sm_count);
                 if (rc == 0) h->last_kernel = 2;
             }
             if (rc <= -1000) {  // launch problem: report it, then use the single-role kernel
@@ -847,8 +851,8 @@ extern "C" int cb2_advance(cb2_engine *h, int64_t n_proposals) {
             }
             if (rc == -2) {  // unsupported by / too large for the producer-consumer kernel
                 rc = launch_step_fast(h->stream, h->M, h->S, W, h->d_fastpack.p, h->fast_desc,
-                                      h->d_draws.p, C, (uint64_t)h->steps_done, w,
-                                      h->sm_count);
+                                      h->d_draws.p, h->d_plan.p, C, (uint64_t)h->steps_done,
+                                      w, h->sm_count);
                 if (rc == 0) h->last_kernel = 1;
             }
             if (rc) FAIL(h, -2, "fast step kernel launch failed (%d)", rc);

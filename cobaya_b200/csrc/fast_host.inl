@@ -53,6 +53,10 @@ static int pack_fast(cb2_engine *h) {
         bool ident = (D == DP) && (row_width(h) % 2 == 0);
         for (int j = 0; j < D; ++j) ident = ident && (h->i_of_j[j] == j);
         P.iofj_identity = ident ? 1 : 0;
+        bool vec = true;
+        for (int b = 0; b < h->n_blocks; ++b)
+            if (h->bsize[b] >= 2 && ((h->bsize[b] | h->jstart[b]) & 1)) vec = false;
+        P.vec_ok = vec ? 1 : 0;
     }
     if ((size_t)P.total * 8 > 190 * 1024) return 0;  // does not fit: general path
     std::vector<double> pk(P.total, 0.0);

@@ -178,10 +178,21 @@ k_basis_wy(uint32_t key0, uint32_t key1, uint64_t chain_id0, int block, int n,
     __syncthreads();
     const int nn = (n + 2) * (n - 1) / 2;
     {
-        int m = 0, base = 0;
-        for (int p = tid; p < (nn + 1) / 2; p += nt_) {
-            double z[2];
-            draw_normal_pair(key0, key1, gid, block, epoch, (uint32_t)p, z[0], z[1]);
+        // all Box-Muller pairs of this thread first (independent chains: the compiler can
+        // interleave the Philox rounds / log / sincospi of several pairs), then the scatter
+        constexpr int NNMAX = (NP + 2) * (NP - 1) / 2;
+        constexpr int PPT = ((NNMAX + 1) / 2 + 127) / 128;  // pairs per thread
+        double z[PPT][2];
+#pragma unroll
+        for (int u = 0; u < PPT; ++u) {
+            const int p = tid + u * 128;
+            if (2 * p < nn)
+                draw_normal_pair(key0, key1, gid, block, epoch, (uint32_t)p, z[u][0], z[u][1]);
+        }
+        int m = 0, base = 0;  // base = ix(m); q only grows
+#pragma unroll
+        for (int u = 0; u < PPT; ++u) {
+            const int p = tid + u * 128;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int q = 2 * p + h;
@@ -190,7 +201,7 @@ k_basis_wy(uint32_t key0, uint32_t key1, uint64_t chain_id0, int block, int n,
                         base += n - m;
                         ++m;
                     }
-                    X[m * LDX + m + (q - base)] = z[h];
+                    X[m * LDX + m + (q - base)] = z[u][h];
                 }
             }
         }
@@ -408,6 +419,7 @@ struct FastPackDesc {
     int off_flags; // [DP] as doubles: bit0 normal prior, bit1 periodic
     int off_iofj;  // [DP] as doubles: sampler index of sorted j (or -1 for padding)
     int iofj_identity;  // D == DP, i_of_j[j] == j and the row stride keeps 16-byte alignment
+    int vec_ok;         // every block with n_b >= 2 has even start and even size
     int total;     // doubles
 };
 
@@ -450,6 +462,63 @@ __device__ __forceinline__ void warp_matvec8(const double *__restrict__ frag, in
     }
 }
 
+// loads that must be ISSUED where they are written (prefetch): asm volatile keeps their
+// program order relative to the (asm volatile) MMAs, the scoreboard wait happens at first use
+__device__ __forceinline__ double ldg_f64_early(const double *p) {
+    double v;
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double2 ldg_f64x2_early(const double2 *p) {
+    double2 v;
+    asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+
+// direction of a planned step in the lane's fragment layout (zero outside the block;
+// +1 at the block's single coordinate for a 1-parameter block).  vec: every block starts at
+// an even sorted index and has even size -> 16-byte loads.
+template <int NT>
+__device__ __forceinline__ void fetch_direction(const ModelDev &M, const WindowDev &W,
+                                                int2 pl, int r, bool vec, double (&u)[NT][2]) {
+    const int b = pl.y, nb = M.bsize[b], j0 = M.jstart[b];
+    if (nb >= 2) {
+        const double *Rk = W.basis[b] + (size_t)pl.x * (size_t)nb;
+        if (vec) {
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+                const int j = 8 * n + 2 * r - j0;
+                if (j >= 0 && j < nb) {
+                    const double2 v2 = ldg_f64x2_early(reinterpret_cast<const double2 *>(Rk + j));
+                    u[n][0] = v2.x;
+                    u[n][1] = v2.y;
+                } else {
+                    u[n][0] = 0.0;
+                    u[n][1] = 0.0;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int j = 8 * n + 2 * r + h - j0;
+                    u[n][h] = (j >= 0 && j < nb) ? ldg_f64_early(Rk + j) : 0.0;
+                }
+        }
+    } else {
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) u[n][h] = (8 * n + 2 * r + h == j0) ? 1.0 : 0.0;
+    }
+}
+__device__ __forceinline__ int2 ldg_int2_early(const int2 *p) {
+    int2 v;
+    asm volatile("ld.global.nc.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+
 // Proposal-side randomness of a window, generated ahead of the serial accept chain:
 // draws[(chain*len + s)] = { r (signed for 1-parameter blocks), Exp(1) of the accept test }
 // (proposal.py:71-93, mcmc.py:683).  None of it depends on the chain state.
@@ -471,11 +540,48 @@ __global__ void k_draws(ModelDev M, const uint8_t *__restrict__ tape, int tape_l
     draws[e] = o;
 }
 
+// Where every step of the window finds its direction: CyclicIndexRandomizer.next +
+// RandDirectionProposer's loop_index / basis epoch (proposal.py:46-55,63-68) advanced for all
+// steps of the window, one thread per chain.  plan[chain*n_steps + s] = { row index of the
+// direction inside the block's basis store (units of n_b doubles), block }.  Also advances the
+// persistent visit counters (none of this depends on accept/reject).
+__global__ void k_plan(ModelDev M, ChainState S, WindowDev W, int64_t n_chains, uint64_t t0,
+                       int n_steps, int2 *__restrict__ plan) {
+    const int64_t chain = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (chain >= n_chains) return;
+    const int NB = M.n_blocks, NV = NB + 1;
+    int kcur[CB2_MAX_BLOCKS], slot[CB2_MAX_BLOCKS], cntv[CB2_MAX_BLOCKS];
+    for (int b = 0; b < NB; ++b) {
+        kcur[b] = (int)(S.vis[chain * NV + b] % M.bsize[b]);
+        slot[b] = 0;
+        cntv[b] = 0;
+    }
+    bool bad = false;
+    for (int s = 0; s < n_steps; ++s) {
+        const uint64_t t = t0 + (uint64_t)s;
+        const int b = W.tape_main ? W.tape_main[chain * W.len_main + (int64_t)(t - W.base_main)]
+                                  : W.const_main;
+        const int nb = M.bsize[b];
+        int sl = slot[b];
+        if (nb >= 2 && sl >= W.cnt[b]) { bad = true; sl = 0; }
+        int2 o;
+        o.x = (nb >= 2) ? (int)((chain * W.cnt[b] + sl) * nb + kcur[b]) : 0;
+        o.y = b;
+        plan[chain * n_steps + s] = o;
+        const bool wrap = (kcur[b] + 1 == nb);
+        kcur[b] = wrap ? 0 : kcur[b] + 1;
+        slot[b] += wrap ? 1 : 0;
+        cntv[b] += 1;
+    }
+    for (int b = 0; b < NB; ++b) S.vis[chain * NV + b] += cntv[b];
+    if (bad) atomicOr(&S.flags[chain], CB2_FLAG_INTERNAL);
+}
+
 template <int NT>
 __global__ void __launch_bounds__(256, 1)
 k_step_fast(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gpack,
-            FastPackDesc P, const double2 *__restrict__ draws, int64_t n_chains, uint64_t t0,
-            int n_steps) {
+            FastPackDesc P, const double2 *__restrict__ draws,
+            const int2 *__restrict__ plan, int64_t n_chains, uint64_t t0, int n_steps) {
     constexpr int DP = NT * 8;
     extern __shared__ __align__(16) double fsm[];
     __shared__ __align__(8) unsigned long long mbar;
@@ -511,15 +617,13 @@ k_step_fast(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gp
                 : "memory");
         }
     }
-    // per-warp scratch after the pack: relative visit counters [8 chains][NB] (int32)
-    int *svis = reinterpret_cast<int *>(fsm + P.total) + wid * 8 * 3 * CB2_MAX_BLOCKS;
 
     const int q = lane >> 2, r = lane & 3;
     const int64_t tile = blockIdx.x * (int64_t)nwarps + wid;
     const int64_t chain_raw = tile * 8 + q;
     const bool active = chain_raw < n_chains;
     const int64_t chain = active ? chain_raw : (n_chains - 1);
-    const int D = M.D, NB = M.n_blocks, NV = NB + 1;
+    const int D = M.D;
     const double *Tf = pack + P.off_T, *Af = pack + P.off_A;
     const double *lower = pack + P.off_lower, *upper = pack + P.off_upper;
     const int *iofj = reinterpret_cast<const int *>(pack + P.off_iofj);
@@ -544,67 +648,17 @@ k_step_fast(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gp
               burn_left = S.burn_left[chain], added_w = S.added_w[chain],
               n_rows = S.n_rows[chain], n_acc = S.n_acc[chain];
     uint32_t flags = S.flags[chain];
-    // per chain and block: {k = visit % n_b, basis slot, visits in this window}
-    int *sv = svis + q * (3 * CB2_MAX_BLOCKS);
-    if (r == 0)
-        for (int b = 0; b < NB; ++b) {
-            sv[3 * b + 0] = (int)(S.vis[chain * NV + b] % M.bsize[b]);
-            sv[3 * b + 1] = 0;
-            sv[3 * b + 2] = 0;
-        }
-    __syncwarp();
     const bool any_special = M.any_periodic || M.any_normal;
     const double2 *my_draws = draws + chain * (int64_t)n_steps;
+    const int2 *my_plan = plan + chain * (int64_t)n_steps;
     const double inv_T = M.temperature;
-
-    // direction of a step: which block, where its basis row lives (state independent)
-    auto locate = [&](int s, int &nb, int &j0, const double *&Rk) {
-        const uint64_t t = t0 + (uint64_t)s;
-        const int b = W.tape_main ? W.tape_main[chain * W.len_main + (int64_t)(t - W.base_main)]
-                                  : W.const_main;
-        nb = M.bsize[b];
-        j0 = M.jstart[b];
-        const int k = sv[3 * b + 0];
-        int slot = sv[3 * b + 1];
-        const int cnt = sv[3 * b + 2];
-        Rk = nullptr;
-        if (nb >= 2) {
-            if (slot >= W.cnt[b]) {
-                flags |= CB2_FLAG_INTERNAL;
-                slot = 0;
-            }
-            Rk = W.basis[b] + ((size_t)(chain * W.cnt[b] + slot) * nb + k) * (size_t)nb;
-        }
-        __syncwarp();
-        if (r == 0) {
-            const bool wrap = (k + 1 == nb);
-            sv[3 * b + 0] = wrap ? 0 : k + 1;
-            sv[3 * b + 1] = sv[3 * b + 1] + (wrap ? 1 : 0);
-            sv[3 * b + 2] = cnt + 1;
-        }
-        __syncwarp();
-    };
-    auto fetch = [&](int nb, int j0, const double *Rk, double (&u)[NT][2]) {
-#pragma unroll
-        for (int n = 0; n < NT; ++n)
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int j = 8 * n + 2 * r + h - j0;
-                if (nb >= 2) u[n][h] = (j >= 0 && j < nb) ? Rk[j] : 0.0;
-                else u[n][h] = (j == 0) ? 1.0 : 0.0;
-            }
-    };
+    const bool vec = P.vec_ok != 0;
 
     // software pipeline: the direction and draws of step s+1 are loaded during step s
     double un[NT][2];
     double2 dn;
-    {
-        int nb, j0;
-        const double *Rk;
-        locate(0, nb, j0, Rk);
-        fetch(nb, j0, Rk, un);
-        dn = my_draws[0];
-    }
+    fetch_direction<NT>(M, W, my_plan[0], r, vec, un);
+    dn = my_draws[0];
     for (int s = 0; s < n_steps; ++s) {
         // ---- v = R[:,k] * r * scale (proposal.py:69) / +-r*scale (:86-93)
         double v[NT][2];
@@ -615,11 +669,8 @@ k_step_fast(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gp
             v[n][1] = un[n][1] * rs * M.proposal_scale;
         }
         if (s + 1 < n_steps) {  // prefetch (independent of the accept chain)
-            int nb, j0;
-            const double *Rk;
-            locate(s + 1, nb, j0, Rk);
-            fetch(nb, j0, Rk, un);
-            dn = my_draws[s + 1];
+            fetch_direction<NT>(M, W, ldg_int2_early(my_plan + s + 1), r, vec, un);
+            dn = ldg_f64x2_early(my_draws + s + 1);
         }
         // ---- trial = x + T v  (proposal.py:224) on the FP64 tensor pipe
         double xt[NT][2];
@@ -773,7 +824,6 @@ k_step_fast(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gp
             S.weight[chain] = weight; S.prior_rej[chain] = prior_rej;
             S.burn_left[chain] = burn_left; S.added_w[chain] = added_w;
             S.n_rows[chain] = n_rows; S.n_acc[chain] = n_acc; S.flags[chain] = flags;
-            for (int b = 0; b < NB; ++b) S.vis[chain * NV + b] += sv[3 * b + 2];
         }
     }
 }
@@ -781,41 +831,45 @@ k_step_fast(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gp
 template <int NT>
 static int launch_step_fast_t(cudaStream_t st, const ModelDev &M, const ChainState &S,
                               const WindowDev &W, const double *gpack, const FastPackDesc &P,
-                              const double2 *draws, int64_t n_chains, uint64_t t0, int n_steps,
-                              int sm_count) {
+                              const double2 *draws, const int2 *plan, int64_t n_chains,
+                              uint64_t t0, int n_steps, int sm_count) {
     const int64_t tiles = (n_chains + 7) / 8;
     int wpc = (int)((tiles + sm_count - 1) / sm_count);
     if (wpc < 1) wpc = 1;
     if (wpc > 8) wpc = 8;
     const int grid = (int)((tiles + wpc - 1) / wpc);
-    const size_t smem = (size_t)P.total * 8 + (size_t)wpc * 8 * 3 * CB2_MAX_BLOCKS * sizeof(int);
+    const size_t smem = (size_t)P.total * 8;
     if (smem > 200 * 1024) return -2;
     if (cudaFuncSetAttribute(k_step_fast<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)smem) != cudaSuccess)
         return -1;
-    k_step_fast<NT><<<grid, wpc * 32, smem, st>>>(M, S, W, gpack, P, draws, n_chains, t0,
+    k_step_fast<NT><<<grid, wpc * 32, smem, st>>>(M, S, W, gpack, P, draws, plan, n_chains, t0,
                                                   n_steps);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
-static inline int launch_draws(cudaStream_t st, const ModelDev &M, const WindowDev &W,
-                               int64_t n_chains, uint64_t t0, int n_steps, double2 *draws) {
+static inline int launch_draws(cudaStream_t st, const ModelDev &M, const ChainState &S,
+                               const WindowDev &W, int64_t n_chains, uint64_t t0, int n_steps,
+                               double2 *draws, int2 *plan) {
     const int64_t tot = n_chains * n_steps;
     const int bs = 256;
     k_draws<<<(unsigned)((tot + bs - 1) / bs), bs, 0, st>>>(M, W.tape_main, W.len_main,
                                                             W.base_main, W.const_main, n_chains,
                                                             t0, n_steps, draws);
+    k_plan<<<(unsigned)((n_chains + 127) / 128), 128, 0, st>>>(M, S, W, n_chains, t0, n_steps,
+                                                               plan);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
 static inline int launch_step_fast(cudaStream_t st, const ModelDev &M, const ChainState &S,
                                    const WindowDev &W, const double *gpack,
                                    const FastPackDesc &P, const double2 *draws,
-                                   int64_t n_chains, uint64_t t0, int n_steps, int sm_count) {
+                                   const int2 *plan, int64_t n_chains, uint64_t t0, int n_steps,
+                                   int sm_count) {
 #define CB2_SF(N)                                                                       \
     case N:                                                                             \
-        return launch_step_fast_t<N>(st, M, S, W, gpack, P, draws, n_chains, t0, n_steps,     \
-                                     sm_count);
+        return launch_step_fast_t<N>(st, M, S, W, gpack, P, draws, plan, n_chains, t0,        \
+                                     n_steps, sm_count);
     switch (P.NT) {
         CB2_SF(1) CB2_SF(2) CB2_SF(3) CB2_SF(4) CB2_SF(5) CB2_SF(6) CB2_SF(7) CB2_SF(8)
     }
@@ -859,19 +913,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
     }
 }
 
-// loads that must be ISSUED where they are written (prefetch): asm volatile keeps their
-// program order relative to the (asm volatile) MMAs, the scoreboard wait happens at first use
-__device__ __forceinline__ double ldg_f64_early(const double *p) {
-    double v;
-    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ double2 ldg_f64x2_early(const double2 *p) {
-    double2 v;
-    asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-    return v;
-}
-
 static inline bool pc_step_supported(const ModelDev &M, const FastPackDesc &P) {
     return P.n_modes == 1 && !M.any_periodic;
 }
@@ -879,8 +920,8 @@ static inline bool pc_step_supported(const ModelDev &M, const FastPackDesc &P) {
 template <int NT, bool HAS_NORMAL>
 __global__ void __launch_bounds__(448, 1)
 k_step_pc(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gpack,
-          FastPackDesc P, const double2 *__restrict__ draws, int64_t n_chains, uint64_t t0,
-          int n_steps, int wpc) {
+          FastPackDesc P, const double2 *__restrict__ draws, const int2 *__restrict__ plan,
+          int64_t n_chains, uint64_t t0, int n_steps, int wpc) {
     constexpr int DP = NT * 8;
     constexpr int SLOT = 2 * NT * 32 * 2 + 8;  // ring slot: delta + w (fragment order) + 8 accept draws
     extern __shared__ __align__(16) double fsm[];
@@ -914,76 +955,26 @@ k_step_pc(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gpac
     mbar_wait(mb_pack, 0);
 
     double *ring = fsm + P.total + (size_t)pair * CB2_PC_RING * SLOT;
-    int *svis_all = reinterpret_cast<int *>(fsm + P.total + (size_t)wpc * CB2_PC_RING * SLOT);
     const int q = lane >> 2, r = lane & 3;
     const int64_t tile = blockIdx.x * (int64_t)wpc + pair;
     const int64_t chain_raw = tile * 8 + q;
     const bool active = chain_raw < n_chains;
     const int64_t chain = active ? chain_raw : (n_chains - 1);
-    const int D = M.D, NB = M.n_blocks, NV = NB + 1;
+    const int D = M.D;
     const double2 *my_draws = draws + chain * (int64_t)n_steps;
+    const int2 *my_plan = plan + chain * (int64_t)n_steps;
+    const bool vec = P.vec_ok != 0;
     const int *iofj = reinterpret_cast<const int *>(pack + P.off_iofj);
 
     if (is_producer) {
         // ================================ producer ====================================
         const double *Tf = pack + P.off_T, *Af = pack + P.off_A;
-        int *sv = svis_all + (pair * 8 + q) * (3 * CB2_MAX_BLOCKS);
-        uint32_t flags = 0;
-        if (r == 0)
-            for (int b = 0; b < NB; ++b) {
-                sv[3 * b + 0] = (int)(S.vis[chain * NV + b] % M.bsize[b]);
-                sv[3 * b + 1] = 0;
-                sv[3 * b + 2] = 0;
-            }
-        __syncwarp();
-        auto locate = [&](int s, int &nb, int &j0, const double *&Rk) {
-            const uint64_t t = t0 + (uint64_t)s;
-            const int b = W.tape_main
-                              ? W.tape_main[chain * W.len_main + (int64_t)(t - W.base_main)]
-                              : W.const_main;
-            nb = M.bsize[b];
-            j0 = M.jstart[b];
-            const int k = sv[3 * b + 0];
-            int slot = sv[3 * b + 1];
-            const int cnt = sv[3 * b + 2];
-            Rk = nullptr;
-            if (nb >= 2) {
-                if (slot >= W.cnt[b]) {
-                    flags |= CB2_FLAG_INTERNAL;
-                    slot = 0;
-                }
-                Rk = W.basis[b] + ((size_t)(chain * W.cnt[b] + slot) * nb + k) * (size_t)nb;
-            }
-            __syncwarp();
-            if (r == 0) {
-                const bool wrap = (k + 1 == nb);
-                sv[3 * b + 0] = wrap ? 0 : k + 1;
-                sv[3 * b + 1] = sv[3 * b + 1] + (wrap ? 1 : 0);
-                sv[3 * b + 2] = cnt + 1;
-            }
-            __syncwarp();
-        };
-        auto fetch = [&](int nb, int j0, const double *Rk, double (&u)[NT][2]) {
-#pragma unroll
-            for (int n = 0; n < NT; ++n)
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int j = 8 * n + 2 * r + h - j0;
-                    if (nb >= 2) u[n][h] = (j >= 0 && j < nb) ? ldg_f64_early(Rk + j) : 0.0;
-                    else u[n][h] = (j == 0) ? 1.0 : 0.0;
-                }
-        };
         // `un` holds the direction of the next step; it becomes v in place, and is refilled
         // (prefetch) as soon as T v has been issued
         double un[NT][2];
         double2 dr_next;  // {radius, Exp(1) of the accept test} of the next step
-        {
-            int nb, j0;
-            const double *Rk;
-            locate(0, nb, j0, Rk);
-            fetch(nb, j0, Rk, un);
-            dr_next = ldg_f64x2_early(my_draws);
-        }
+        fetch_direction<NT>(M, W, my_plan[0], r, vec, un);
+        dr_next = ldg_f64x2_early(my_draws);
         for (int s = 0; s < n_steps; ++s) {
             const int slot = s % CB2_PC_RING;
             const uint32_t use = (uint32_t)(s / CB2_PC_RING);
@@ -998,10 +989,7 @@ k_step_pc(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gpac
             for (int n = 0; n < NT; ++n) { dl[n][0] = 0.0; dl[n][1] = 0.0; }
             warp_matvec8<NT, true>(Tf, lane, un, dl);
             if (s + 1 < n_steps) {
-                int nb, j0;
-                const double *Rk;
-                locate(s + 1, nb, j0, Rk);
-                fetch(nb, j0, Rk, un);
+                fetch_direction<NT>(M, W, ldg_int2_early(my_plan + s + 1), r, vec, un);
                 dr_next = ldg_f64x2_early(my_draws + s + 1);
             }
             // wait until the consumer released this slot (first pass: free)
@@ -1023,11 +1011,6 @@ k_step_pc(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gpac
             __syncwarp();
             if (lane == 0)
                 mbar_arrive((uint32_t)__cvta_generic_to_shared(&mbar_full[pair * CB2_PC_RING + slot]));
-        }
-        __syncwarp();
-        if (active && r == 0) {
-            for (int b = 0; b < NB; ++b) S.vis[chain * NV + b] += sv[3 * b + 2];
-            if (flags) atomicOr(&S.flags[chain], flags);
         }
     } else {
         // ================================ consumer ====================================
@@ -1195,29 +1178,28 @@ k_step_pc(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gpac
 template <int NT>
 static int launch_step_pc_t(cudaStream_t st, const ModelDev &M, const ChainState &S,
                             const WindowDev &W, const double *gpack, const FastPackDesc &P,
-                            const double2 *draws, int64_t n_chains, uint64_t t0, int n_steps,
-                            int sm_count) {
+                            const double2 *draws, const int2 *plan, int64_t n_chains,
+                            uint64_t t0, int n_steps, int sm_count) {
     const int64_t tiles = (n_chains + 7) / 8;
     int wpc = (int)((tiles + sm_count - 1) / sm_count);
     if (wpc < 1) wpc = 1;
     if (wpc > 7) wpc = 7;
     const int grid = (int)((tiles + wpc - 1) / wpc);
     const size_t slot = (size_t)2 * NT * 32 * 2 + 8;
-    const size_t smem = ((size_t)P.total + (size_t)wpc * CB2_PC_RING * slot) * 8 +
-                        (size_t)wpc * 8 * 3 * CB2_MAX_BLOCKS * sizeof(int);
+    const size_t smem = ((size_t)P.total + (size_t)wpc * CB2_PC_RING * slot) * 8;
     if (smem > 220 * 1024) return -2;
     cudaError_t e;
     if (M.any_normal) {
         e = cudaFuncSetAttribute(k_step_pc<NT, true>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return -1000 - (int)e;
-        k_step_pc<NT, true><<<grid, 2 * wpc * 32, smem, st>>>(M, S, W, gpack, P, draws, n_chains,
-                                                               t0, n_steps, wpc);
+        k_step_pc<NT, true><<<grid, 2 * wpc * 32, smem, st>>>(M, S, W, gpack, P, draws, plan,
+                                                               n_chains, t0, n_steps, wpc);
     } else {
         e = cudaFuncSetAttribute(k_step_pc<NT, false>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return -1000 - (int)e;
-        k_step_pc<NT, false><<<grid, 2 * wpc * 32, smem, st>>>(M, S, W, gpack, P, draws,
+        k_step_pc<NT, false><<<grid, 2 * wpc * 32, smem, st>>>(M, S, W, gpack, P, draws, plan,
                                                                 n_chains, t0, n_steps, wpc);
     }
     e = cudaGetLastError();
@@ -1226,11 +1208,11 @@ static int launch_step_pc_t(cudaStream_t st, const ModelDev &M, const ChainState
 
 static inline int launch_step_pc(cudaStream_t st, const ModelDev &M, const ChainState &S,
                                  const WindowDev &W, const double *gpack, const FastPackDesc &P,
-                                 const double2 *draws, int64_t n_chains, uint64_t t0,
-                                 int n_steps, int sm_count) {
+                                 const double2 *draws, const int2 *plan, int64_t n_chains,
+                                 uint64_t t0, int n_steps, int sm_count) {
 #define CB2_PC(N)                                                                         \
     case N:                                                                               \
-        return launch_step_pc_t<N>(st, M, S, W, gpack, P, draws, n_chains, t0, n_steps,     \
+        return launch_step_pc_t<N>(st, M, S, W, gpack, P, draws, plan, n_chains, t0, n_steps, \
                                    sm_count);
     switch (P.NT) {
         CB2_PC(1) CB2_PC(2) CB2_PC(3) CB2_PC(4) CB2_PC(5) CB2_PC(6) CB2_PC(7) CB2_PC(8)
