@@ -245,6 +245,7 @@ def run_gpu_arm(args):
         import torch.distributed as tdist
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line
         tdist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from cobaya_b200.mcmc import EnsembleMCMC, TorchDist
 

@@ -900,6 +900,20 @@ __device__ __forceinline__ void mbar_init(uint32_t a, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t a) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
 }
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t a, uint32_t parity) {
+    uint32_t done = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(64);  // leave the issue slots to the producer warps
+    }
+}
 __device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
     uint32_t done = 0;
     while (!done) {
@@ -992,21 +1006,22 @@ k_step_pc(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gpac
                 fetch_direction<NT>(M, W, ldg_int2_early(my_plan + s + 1), r, vec, un);
                 dr_next = ldg_f64x2_early(my_draws + s + 1);
             }
-            // wait until the consumer released this slot (first pass: free)
-            if (use > 0)
-                mbar_wait((uint32_t)__cvta_generic_to_shared(&mbar_empty[pair * CB2_PC_RING + slot]),
-                          (use - 1) & 1u);
-            double2 *sl = reinterpret_cast<double2 *>(ring + (size_t)slot * SLOT);
-#pragma unroll
-            for (int n = 0; n < NT; ++n) sl[n * 32 + lane] = make_double2(dl[n][0], dl[n][1]);
             double wv[NT][2];
 #pragma unroll
             for (int n = 0; n < NT; ++n) { wv[n][0] = 0.0; wv[n][1] = 0.0; }
             if (P.tri_like) warp_matvec8<NT, true>(Af, lane, dl, wv);
             else warp_matvec8<NT, false>(Af, lane, dl, wv);
+            // both products are in registers: only now wait for the consumer to have
+            // released this slot (first pass: free)
+            if (use > 0)
+                mbar_wait((uint32_t)__cvta_generic_to_shared(&mbar_empty[pair * CB2_PC_RING + slot]),
+                          (use - 1) & 1u);
+            double2 *sl = reinterpret_cast<double2 *>(ring + (size_t)slot * SLOT);
 #pragma unroll
-            for (int n = 0; n < NT; ++n)
+            for (int n = 0; n < NT; ++n) {
+                sl[n * 32 + lane] = make_double2(dl[n][0], dl[n][1]);
                 sl[(NT + n) * 32 + lane] = make_double2(wv[n][0], wv[n][1]);
+            }
             if (r == 0) ring[(size_t)slot * SLOT + 2 * NT * 64 + q] = e_cur;
             __syncwarp();
             if (lane == 0)
@@ -1050,8 +1065,8 @@ k_step_pc(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gpac
         for (int s = 0; s < n_steps; ++s) {
             const int slot = s % CB2_PC_RING;
             const uint32_t use = (uint32_t)(s / CB2_PC_RING);
-            mbar_wait((uint32_t)__cvta_generic_to_shared(&mbar_full[pair * CB2_PC_RING + slot]),
-                      use & 1u);
+            mbar_wait_backoff(
+                (uint32_t)__cvta_generic_to_shared(&mbar_full[pair * CB2_PC_RING + slot]), use & 1u);
             const double e_acc = ring[(size_t)slot * SLOT + 2 * NT * 64 + q];
             const double2 *sl = reinterpret_cast<const double2 *>(ring + (size_t)slot * SLOT);
             bool bad = false;

@@ -40,7 +40,8 @@ WORKER = textwrap.dedent("""
     out = dict(rank=td.rank, n_chains=s.n_chains, R=[c.Rminus1 for c in s.progress],
                N=[c.N for c in s.progress], learned=[c.learned for c in s.progress],
                cov00=float(s.fm.get_covariance()[0, 0]), steps=s.n_steps_raw)
-    print("RESULT " + json.dumps(out))
+    with open(os.path.join({outdir!r}, f"rank{{td.rank}}.json"), "w") as f:
+        json.dump(out, f)
     dist.destroy_process_group()
 """)
 
@@ -51,15 +52,14 @@ def test_two_gpus_equal_one_engine_with_all_chains(tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     script = tmp_path / "w.py"
-    script.write_text(WORKER.format(root=ROOT))
+    script.write_text(WORKER.format(root=ROOT, outdir=str(tmp_path)))
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", PYTHONPATH=ROOT)
     p = subprocess.run(
         [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
          "--master-addr", "127.0.0.1", "--master-port", "29631", str(script)],
         capture_output=True, text=True, env=env, timeout=600)
     assert p.returncode == 0, p.stderr[-3000:]
-    res = sorted((json.loads(l.split("RESULT ", 1)[1]) for l in p.stdout.splitlines()
-                  if "RESULT " in l), key=lambda r: r["rank"])
+    res = [json.load(open(tmp_path / f"rank{r}.json")) for r in range(2)]
     assert len(res) == 2 and res[0]["n_chains"] == 128
     assert res[0]["R"] == res[1]["R"] and res[0]["cov00"] == res[1]["cov00"]
     assert res[0]["N"] == res[1]["N"] and len(res[0]["R"]) >= 1
