@@ -141,16 +141,54 @@ __device__ __forceinline__ double draw_accept_exp(const ModelDev &M, uint64_t gi
     return -log(u52(w.x, w.y));
 }
 
+// sin(2 pi u), cos(2 pi u) for u = (k + 1/2) 2^-52 given the 52-bit integer k.  The octant
+// comes straight from the top bits of k and the reduced argument f = 2u - q/2 in
+// [-1/4, 1/4] is assembled exactly from the remaining bits (no FRND/F2I: those run on the
+// slow XU pipe); sin(pi f), cos(pi f) by Taylor series (|pi f| <= 0.786, error < 1 ulp).
+__device__ __forceinline__ void sincos2pi_from_bits(uint64_t k, double &s, double &c) {
+    const int q = (int)((k + (1ull << 49)) >> 50);                 // round(4u), 0..4
+    const long long kk = (long long)k - ((long long)q << 50);      // in [-2^49, 2^49)
+    const double kd = __longlong_as_double((long long)(0x4330000000000000ull |
+                                                       (uint64_t)(kk + (1ll << 51)))) -
+                      6755399441055744.0;                          // 2^52 + 2^51
+    const double f = (kd + 0.5) * 4.440892098500626e-16;           // 2^-51
+    const double x = 3.141592653589793 * f, x2 = x * x;
+    double ps = -7.647163731819816e-13;                            // -1/15!
+    ps = fma(ps, x2, 1.6059043836821613e-10);                      //  1/13!
+    ps = fma(ps, x2, -2.505210838544172e-08);                      // -1/11!
+    ps = fma(ps, x2, 2.7557319223985893e-06);                      //  1/9!
+    ps = fma(ps, x2, -1.984126984126984e-04);                      // -1/7!
+    ps = fma(ps, x2, 8.333333333333333e-03);                       //  1/5!
+    ps = fma(ps, x2, -1.6666666666666666e-01);                     // -1/3!
+    const double sf = fma(x * x2, ps, x);
+    double pc = 4.779477332387385e-14;                             //  1/16!
+    pc = fma(pc, x2, -1.1470745597729725e-11);                     // -1/14!
+    pc = fma(pc, x2, 2.08767569878681e-09);                        //  1/12!
+    pc = fma(pc, x2, -2.755731922398589e-07);                      // -1/10!
+    pc = fma(pc, x2, 2.48015873015873e-05);                        //  1/8!
+    pc = fma(pc, x2, -1.388888888888889e-03);                      // -1/6!
+    pc = fma(pc, x2, 4.1666666666666664e-02);                      //  1/4!
+    pc = fma(pc, x2, -0.5);
+    const double cf = fma(pc, x2, 1.0);
+    switch (q & 3) {
+        case 0: s = sf; c = cf; break;
+        case 1: s = cf; c = -sf; break;
+        case 2: s = -sf; c = -cf; break;
+        default: s = -cf; c = sf; break;
+    }
+}
+
 // pair p of the standard normals consumed by random_SO_N (functions.py:36)
 __device__ __forceinline__ void draw_normal_pair(uint32_t k0, uint32_t k1, uint64_t gid,
                                                  int block, uint32_t epoch, uint32_t p,
                                                  double &z0, double &z1) {
     u32x4 w = philox4x32_10(k0, k1, p, epoch, (uint32_t)gid,
                             CB2_TAG_BASIS | ((uint32_t)block << 8));
-    double u1 = u52(w.x, w.y), u2 = u52(w.z, w.w);
-    double rad = sqrt(-2.0 * log(u1));
+    const double u1 = u52(w.x, w.y);
+    const uint64_t k2 = ((uint64_t)(w.z >> 6) << 26) | (uint64_t)(w.w >> 6);
+    const double rad = sqrt(-2.0 * log(u1));
     double s, c;
-    sincospi(2.0 * u2, &s, &c);
+    sincos2pi_from_bits(k2, s, c);
     z0 = rad * c;
     z1 = rad * s;
 }

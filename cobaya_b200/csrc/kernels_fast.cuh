@@ -1006,22 +1006,21 @@ k_step_pc(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gpac
                 fetch_direction<NT>(M, W, ldg_int2_early(my_plan + s + 1), r, vec, un);
                 dr_next = ldg_f64x2_early(my_draws + s + 1);
             }
-            double wv[NT][2];
-#pragma unroll
-            for (int n = 0; n < NT; ++n) { wv[n][0] = 0.0; wv[n][1] = 0.0; }
-            if (P.tri_like) warp_matvec8<NT, true>(Af, lane, dl, wv);
-            else warp_matvec8<NT, false>(Af, lane, dl, wv);
-            // both products are in registers: only now wait for the consumer to have
-            // released this slot (first pass: free)
+            // wait until the consumer released this slot (first pass: free)
             if (use > 0)
                 mbar_wait((uint32_t)__cvta_generic_to_shared(&mbar_empty[pair * CB2_PC_RING + slot]),
                           (use - 1) & 1u);
             double2 *sl = reinterpret_cast<double2 *>(ring + (size_t)slot * SLOT);
 #pragma unroll
-            for (int n = 0; n < NT; ++n) {
-                sl[n * 32 + lane] = make_double2(dl[n][0], dl[n][1]);
+            for (int n = 0; n < NT; ++n) sl[n * 32 + lane] = make_double2(dl[n][0], dl[n][1]);
+            double wv[NT][2];
+#pragma unroll
+            for (int n = 0; n < NT; ++n) { wv[n][0] = 0.0; wv[n][1] = 0.0; }
+            if (P.tri_like) warp_matvec8<NT, true>(Af, lane, dl, wv);
+            else warp_matvec8<NT, false>(Af, lane, dl, wv);
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
                 sl[(NT + n) * 32 + lane] = make_double2(wv[n][0], wv[n][1]);
-            }
             if (r == 0) ring[(size_t)slot * SLOT + 2 * NT * 64 + q] = e_cur;
             __syncwarp();
             if (lane == 0)
@@ -1065,8 +1064,8 @@ k_step_pc(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gpac
         for (int s = 0; s < n_steps; ++s) {
             const int slot = s % CB2_PC_RING;
             const uint32_t use = (uint32_t)(s / CB2_PC_RING);
-            mbar_wait_backoff(
-                (uint32_t)__cvta_generic_to_shared(&mbar_full[pair * CB2_PC_RING + slot]), use & 1u);
+            mbar_wait((uint32_t)__cvta_generic_to_shared(&mbar_full[pair * CB2_PC_RING + slot]),
+                      use & 1u);
             const double e_acc = ring[(size_t)slot * SLOT + 2 * NT * 64 + q];
             const double2 *sl = reinterpret_cast<const double2 *>(ring + (size_t)slot * SLOT);
             bool bad = false;
