@@ -156,7 +156,7 @@ k_basis_fast(uint32_t key0, uint32_t key1, uint64_t chain_id0, int block, int n,
 // an A fragment.  Same matrix as functions.py:48-58 up to rounding (~1e-15).
 // -------------------------------------------------------------------------------------
 template <int NG>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, 5)
 k_basis_wy(uint32_t key0, uint32_t key1, uint64_t chain_id0, int block, int n,
            const int64_t *__restrict__ vis, int vis_stride, uint32_t e0_fixed, int cnt,
            double *__restrict__ store, int64_t task0, int64_t store_task0) {
