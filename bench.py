@@ -192,11 +192,15 @@ def run_reference_arm(args):
         n_samples = 250  # accepted rows per chain per step (about 0.15 s of run())
         procs = []
         t0 = time.perf_counter()
+        # one chain per core, one thread per process (what an `mpirun -np <cores>` run of the
+        # reference uses): keep BLAS / numba from oversubscribing the cores
+        env = dict(os.environ, OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1",
+                   MKL_NUM_THREADS="1", NUMBA_NUM_THREADS="1")
         for c in range(cores):
             procs.append(subprocess.Popen(
                 [sys.executable, "-c", _REF_WORKER, ROOT, str(n_samples), str(100 + c),
                  str(steps + warm)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
-                text=True))
+                text=True, env=env))
         res = []
         for p in procs:
             o, _ = p.communicate()

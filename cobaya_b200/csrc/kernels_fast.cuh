@@ -275,68 +275,78 @@ k_basis_wy(uint32_t key0, uint32_t key1, uint64_t chain_id0, int block, int n,
         }
     }
     __syncthreads();
-    // ---- sweep on the tensor pipe
-    double hreg[2][NG][2];
+    // ---- accumulate H = Q_0 Q_1 ... Q_{NG-1} from the innermost factor (dorgqr order): with
+    // N = M^T,  M <- Q_g M  is  N <- N - ((N V_g) T_g^T) V_g^T, and only rows/columns >= 8g
+    // of N differ from the identity, so row tiles below 8g are skipped (888 instead of 1280
+    // MMAs at n = 64).  Warp w owns the row tiles {w, NG-1-w} of N (balanced work).
+    const int t0 = w, t1 = NG - 1 - w;
+    const int nslot = (t0 < t1) ? 2 : ((t0 == t1) ? 1 : 0);
+    double nreg[2][NG][2];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int sl = 0; sl < 2; ++sl)
 #pragma unroll
         for (int nt = 0; nt < NG; ++nt)
 #pragma unroll
             for (int h = 0; h < 2; ++h)
-                hreg[mt][nt][h] = (16 * w + 8 * mt + q == 8 * nt + 2 * r + h) ? 1.0 : 0.0;
-    if (16 * w < NP) {
+                nreg[sl][nt][h] = (8 * (sl ? t1 : t0) + q == 8 * nt + 2 * r + h) ? 1.0 : 0.0;
+    if (nslot > 0) {
 #pragma unroll
-        for (int g = 0; g < NG; ++g) {
-            if (8 * g >= n - 1) break;  // no reflectors left
+        for (int gg = 0; gg < NG; ++gg) {
+            const int g = NG - 1 - gg;
+            if (8 * g >= n - 1) continue;  // no reflectors in this group
             const double *Xg = X + (8 * g) * LDX;
-            // Y = H[:, 8g:] V   (two partial accumulators per row tile for ILP)
+            const double *T = Tg + g * 64;
+            const bool act0 = t0 >= g, act1 = (nslot > 1) && (t1 >= g);
+            if (!act0 && !act1) continue;  // warp-uniform
+            // Y = N[:, 8g:] V
             double y[2][2][2];
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
+            for (int sl = 0; sl < 2; ++sl)
 #pragma unroll
-                for (int pa = 0; pa < 2; ++pa) { y[mt][pa][0] = 0.0; y[mt][pa][1] = 0.0; }
+                for (int pa = 0; pa < 2; ++pa) { y[sl][pa][0] = 0.0; y[sl][pa][1] = 0.0; }
 #pragma unroll
             for (int nt = g; nt < NG; ++nt)
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const double b = Xg[q * LDX + 8 * nt + 2 * r + h];  // V[col][reflector q]
-#pragma unroll
-                    for (int mt = 0; mt < 2; ++mt)
-                        dmma8x8x4(y[mt][(nt + h) & 1][0], y[mt][(nt + h) & 1][1], hreg[mt][nt][h], b);
+                    const double bv = Xg[q * LDX + 8 * nt + 2 * r + h];
+                    if (act0) dmma8x8x4(y[0][(nt + h) & 1][0], y[0][(nt + h) & 1][1], nreg[0][nt][h], bv);
+                    if (act1) dmma8x8x4(y[1][(nt + h) & 1][0], y[1][(nt + h) & 1][1], nreg[1][nt][h], bv);
                 }
-            // Z = Y T
+            // Z = Y T^T
             double z[2][2];
-            const double *T = Tg + g * 64;
+            const double tb0 = T[q * 8 + 2 * r], tb1 = T[q * 8 + 2 * r + 1];
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
-                z[mt][0] = 0.0; z[mt][1] = 0.0;
-                const double ya = y[mt][0][0] + y[mt][1][0], yb = y[mt][0][1] + y[mt][1][1];
-                dmma8x8x4(z[mt][0], z[mt][1], ya, T[(2 * r) * 8 + q]);
-                dmma8x8x4(z[mt][0], z[mt][1], yb, T[(2 * r + 1) * 8 + q]);
+            for (int sl = 0; sl < 2; ++sl) {
+                z[sl][0] = 0.0; z[sl][1] = 0.0;
+                if (sl == 0 ? act0 : act1) {
+                    const double ya = y[sl][0][0] + y[sl][1][0], yb = y[sl][0][1] + y[sl][1][1];
+                    dmma8x8x4(z[sl][0], z[sl][1], ya, tb0);
+                    dmma8x8x4(z[sl][0], z[sl][1], yb, tb1);
+                }
             }
-            // H[:, 8g:] -= Z V^T
+            // N[:, 8g:] -= Z V^T
 #pragma unroll
             for (int nt = g; nt < NG; ++nt)
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const double b = Xg[(2 * r + h) * LDX + 8 * nt + q];  // V^T[reflector][col]
-#pragma unroll
-                    for (int mt = 0; mt < 2; ++mt)
-                        dmma8x8x4(hreg[mt][nt][0], hreg[mt][nt][1], -z[mt][h], b);
+                    const double bv = Xg[(2 * r + h) * LDX + 8 * nt + q];
+                    if (act0) dmma8x8x4(nreg[0][nt][0], nreg[0][nt][1], -z[0][h], bv);
+                    if (act1) dmma8x8x4(nreg[1][nt][0], nreg[1][nt][1], -z[1][h], bv);
                 }
         }
+        // R[i][c] = D[i] H[i][c] = D[i] N[c][i]  (functions.py:60), stored as Rt[c*n + i]
+        double *out = store + (size_t)(task - store_task0) * (size_t)n * n;
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-            const int row = 16 * w + 8 * mt + q;
-            if (row < n) {
-                const double d = Dv[row];
-                double *out = store + (size_t)(task - store_task0) * (size_t)n * n;
+        for (int sl = 0; sl < 2; ++sl) {
+            if (sl >= nslot) break;
+            const int c = 8 * (sl ? t1 : t0) + q;
+            if (c < n) {
 #pragma unroll
                 for (int nt = 0; nt < NG; ++nt)
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        const int c = 8 * nt + 2 * r + h;
-                        if (c < n) out[(size_t)c * n + row] = d * hreg[mt][nt][h];
+                        const int i = 8 * nt + 2 * r + h;
+                        if (i < n) out[(size_t)c * n + i] = Dv[i] * nreg[sl][nt][h];
                     }
             }
         }
