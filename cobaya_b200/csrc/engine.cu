@@ -403,7 +403,7 @@ extern "C" int cb2_set_options(cb2_engine *h, double temperature, int64_t burn_i
         FAIL(h, -1, "rows_cap cannot change after cb2_set_state");
     h->temperature = temperature;
     h->burn_in = burn_in;
-    h->max_tries = max_tries;
+    h->max_tries = std::min<int64_t>(max_tries, (int64_t)1 << 59);  // x10 in burn-in fits int64
     h->output_thin = output_thin;
     h->rows_cap = rows_cap;
     h->model_dirty = true;

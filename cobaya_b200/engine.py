@@ -18,6 +18,9 @@ FLAG_ROWS_FULL = 2
 FLAG_INTERNAL = 4
 MOMENTS_HALVES = 0
 MOMENTS_SINGLE_SPLIT = 1
+# `max_tries: inf` is sent as this cap: the stuck test multiplies it by 10 during burn-in
+# (mcmc.py:717-719) and must stay inside int64
+MAX_TRIES_CAP = 2**59
 
 
 class EngineError(RuntimeError):
@@ -93,7 +96,7 @@ class Engine:
             self.set_proposal(fm.T, fm.proposal_scale)
         self._ck(self.lib.cb2_set_options(
             self.h, float(fm.temperature), self.burn_in,
-            int(min(fm.max_tries, 2**62)), int(fm.output_thin), self.rows_cap))
+            int(min(fm.max_tries, MAX_TRIES_CAP)), int(fm.output_thin), self.rows_cap))
 
     # ------------------------------------------------------------------ API
     def set_proposal(self, T, proposal_scale=None):

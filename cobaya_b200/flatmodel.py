@@ -162,7 +162,7 @@ class FlatModel:
     proposal_scale: float = 2.4
     # options
     temperature: float = 1.0
-    max_tries: int = 40 * 1000000
+    max_tries: int = 2**59  # 'no limit'; the sampler front ends set mcmc.yaml's value
     output_thin: int = 1
 
     def __post_init__(self):

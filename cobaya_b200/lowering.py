@@ -114,7 +114,7 @@ def lower_model(model, sampler=None, *, blocks=None, oversampling=None, drag=Fal
         max_tries = sampler.max_tries.value
         output_thin = int(sampler.current_point.output_thin)
     if max_tries is None or not np.isfinite(max_tries):
-        max_tries = 2**62
+        max_tries = 2**59
     return FlatModel(
         names=sampled, prior_kind=kind, lower=lower, upper=upper, loc=loc, pscale=scale,
         periodic=periodic, likes=likes, blocks=blocks, oversampling=oversampling,

@@ -202,7 +202,7 @@ class EnsembleMCMC:
         self.callback_every = NumberWithUnits(opts["callback_every"], "d", scale=scale)
         self.burn_in = NumberWithUnits(opts["burn_in"], "d", scale=scale)
         mt = self.max_tries.value
-        fm.max_tries = int(mt) if np.isfinite(mt) else 2**62
+        fm.max_tries = int(min(mt, 2**59)) if np.isfinite(mt) else 2**59
         self.max_samples = opts["max_samples"]
         if covmat_incomplete and opts["learn_proposal"]:  # mcmc.py:419-429
             opts["learn_proposal_Rminus1_max"] = opts["learn_proposal_Rminus1_max_early"]

@@ -328,16 +328,20 @@ class MCMC(CovmatSampler):
     def n(self, burn_in=False):
         return 0 if self._ens is None else self._ens.n()
 
-    def _fill_collection(self, skip_samples: float = 0.0):
-        """Materialise the (concatenated) chains as a real SampleCollection: a DataFrame
-        with exactly ``collection.columns`` assigned to ``_data``."""
-        data = self._ens.samples(skip_samples=skip_samples)
+    def _collection_from_rows(self, data, target):
         cols = list(self.collection.columns)
         if data.shape[1] != len(cols):
             raise LoggedError(self.log, "Engine row width %d does not match the collection's "
                                         "%d columns", data.shape[1], len(cols))
-        self.collection._data = pd.DataFrame(data, columns=cols)
-        self.collection._cache_reset()
+        target._data = pd.DataFrame(data, columns=cols)
+        target._cache_reset()
+        return target
+
+    def _fill_collection(self):
+        """Materialise the (concatenated) chains as a real SampleCollection: a DataFrame
+        with exactly ``collection.columns`` assigned to ``_data`` (SURVEY.md section 8b);
+        with an ``output`` the chain file ``prefix.<rank+1>.txt`` is written."""
+        self._collection_from_rows(self._ens.samples(), self.collection)
         if self.output:
             self.collection.out_update()
 
@@ -348,9 +352,12 @@ class MCMC(CovmatSampler):
         if to_getdist:
             raise LoggedError(self.log, "to_getdist needs GetDist (not evaluated by the "
                                         "ensemble engine yet).")
-        if skip_samples:
-            self._fill_collection(skip_samples)
-        return self.collection
+        if not skip_samples:
+            return self.collection
+        # skipping is applied to every chain before concatenation (mcmc.py:1127-1143) and
+        # returns a copy; the collection bound to the output files is left untouched
+        return self._collection_from_rows(self._ens.samples(skip_samples=skip_samples),
+                                          self.collection.copy(empty=True))
 
     def products(self, combined: bool = False, skip_samples: float = 0,
                  to_getdist: bool = False) -> dict:

@@ -138,7 +138,7 @@ class OracleModel:
         m.T = _p(k(fm.T))
         m.proposal_scale = fm.proposal_scale
         m.temperature = fm.temperature
-        m.max_tries = int(min(fm.max_tries, 2**62))
+        m.max_tries = int(min(fm.max_tries, 2**59))  # x10 during burn-in must fit int64
         m.output_thin = int(fm.output_thin)
         self.c = m
 

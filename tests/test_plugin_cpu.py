@@ -172,3 +172,58 @@ def test_run_without_gpu_fails_loudly():
     _, _, _, mine = _pair(infos["g2"])
     with pytest.raises(LoggedError, match="no CPU fallback"):
         mine.run()
+
+
+def test_products_and_output_files_roundtrip(tmp_path):
+    """SURVEY 8f row 1 (output side): the plugin materialises real SampleCollection products
+    and, with an `output` prefix, writes chain / covmat / checkpoint files that the
+    reference's own loader reads back (rows here come from the C oracle standing in for the
+    device, the engine itself needs a GPU)."""
+    enable_reference()
+    from cobaya.model import get_model
+    from cobaya.output import get_output, load_samples
+    from cobaya.sampler import get_sampler
+
+    from oracle import oracle as orc
+
+    infos = _infos()
+    info = copy.deepcopy(infos["g2"])
+    opts = dict(info["sampler"]["mcmc"], chains_per_gpu=3)
+    info["sampler"] = {"cobaya_b200.plugin.MCMC": opts}
+    prefix = str(tmp_path / "run")
+    out = get_output(prefix=prefix, resume=False, force=True)
+    model = get_model(info)
+    s = get_sampler(info["sampler"], model, output=out)
+
+    class FakeEnsemble:  # rows with the engine's layout, produced by the oracle
+        def __init__(self, fm, x0):
+            om = orc.OracleModel(fm)
+            self.rows = [orc.OracleChain(om, 7, c, x0[c], burn_in=2).advance(600)[1]
+                         for c in range(len(x0))]
+
+        def samples(self, chains=None, skip_samples=0.0):
+            k = lambda r: int(skip_samples * len(r)) if 0 < skip_samples < 1 else int(skip_samples)
+            return np.concatenate([r[k(r):] for r in self.rows])
+
+    s._ens = FakeEnsemble(s._fm, s._x0)
+    s._fill_collection()
+    s.write_checkpoint()
+    col = s.products()["sample"]
+    n = sum(len(r) for r in s._ens.rows)
+    assert len(col) == n and list(col.columns) == s._fm.columns()
+    # the g2 case samples at temperature 2: compare the statistics of the tempered sample
+    np.testing.assert_allclose(col.mean(tempered=True), np.average(
+        np.concatenate(s._ens.rows)[:, 2:7], axis=0, weights=np.concatenate(s._ens.rows)[:, 0]))
+    half = s.products(skip_samples=0.5)["sample"]
+    assert 0 < len(half) < n
+    import os
+
+    files = sorted(os.listdir(tmp_path))
+    assert "run.1.txt" in files and "run.covmat" in files and "run.checkpoint" in files
+    back = load_samples(prefix, skip=0, combined=True)
+    # the chain file keeps every row; skip_samples only affects the returned copy
+    assert len(back) == n and len(s.collection) == n
+    np.testing.assert_allclose(back[["p0", "p1"]].to_numpy(), col[["p0", "p1"]].to_numpy(),
+                               rtol=1e-7)
+    np.testing.assert_allclose(half[["p0", "p1"]].to_numpy(),
+                               s._ens.samples(skip_samples=0.5)[:, 2:4], rtol=0)
