@@ -18,7 +18,8 @@ LIB_PATH = os.path.join(_HERE, "lib", "libcobaya_b200.so")
 
 EXPORTS = [
     "cb2_abi_version", "cb2_last_error", "cb2_create", "cb2_destroy", "cb2_set_prior",
-    "cb2_clear_likelihoods", "cb2_add_gaussian_mixture", "cb2_add_rosenbrock",
+    "cb2_set_prior_shapes",
+    "cb2_clear_likelihoods", "cb2_add_gaussian_mixture", "cb2_add_rosenbrock", "cb2_add_constant",
     "cb2_set_blocking", "cb2_set_proposal", "cb2_set_options", "cb2_set_state",
     "cb2_get_state", "cb2_logpost", "cb2_advance", "cb2_sync", "cb2_summary",
     "cb2_moments", "cb2_bounds", "cb2_copy_rows", "cb2_row_width", "cb2_n_derived", "cb2_debug_basis",
@@ -59,9 +60,11 @@ def load():
     L.cb2_create.argtypes = [C.c_int, i64, i32, u64, u64, C.POINTER(vp)]
     L.cb2_destroy.argtypes = [vp]
     L.cb2_set_prior.argtypes = [vp] + [vp] * 6 + [dbl]
+    L.cb2_set_prior_shapes.argtypes = [vp, vp, vp, vp]
     L.cb2_clear_likelihoods.argtypes = [vp]
     L.cb2_add_gaussian_mixture.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, i32]
     L.cb2_add_rosenbrock.argtypes = [vp, i32, vp, dbl]
+    L.cb2_add_constant.argtypes = [vp, dbl]
     L.cb2_set_blocking.argtypes = [vp, i32, vp, vp, vp, i32, i32, i32]
     L.cb2_set_proposal.argtypes = [vp, vp, dbl]
     L.cb2_set_options.argtypes = [vp, dbl, i64, i64, i32, i64]

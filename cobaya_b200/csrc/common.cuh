@@ -21,6 +21,36 @@
 
 #define CB2_LOG_2PI 1.8378770664093453
 
+// Shape part f(z; a, b) of the 1-D prior log-densities the reference takes from
+// scipy.stats (cobaya/prior.py:520-525, cobaya/tools.py:611-718):
+//   logpdf(x) = cn + f((x - loc) / scale; a, b),  cn precomputed on the host.
+// Kinds: include/cobaya_b200.h (CB2_PRIOR_*).  Called only inside the support
+// (Prior.logps_internal checks the bounds first, prior.py:752).
+__device__ __forceinline__ double prior1d_shape(int kind, double z, double a, double b) {
+    switch (kind) {
+        case CB2_PRIOR_NORMAL:
+        case CB2_PRIOR_TRUNCNORM:
+        case CB2_PRIOR_HALFNORM: return -z * z / 2;
+        case CB2_PRIOR_EXPON: return -z;
+        case CB2_PRIOR_BETA: {
+            double s = 0.0;
+            if (a != 1.0) s += (a - 1.0) * log(z);
+            if (b != 1.0) s += (b - 1.0) * log1p(-z);
+            return s;
+        }
+        case CB2_PRIOR_GAMMA: return (a != 1.0 ? (a - 1.0) * log(z) : 0.0) - z;
+        case CB2_PRIOR_LOGNORM: {
+            if (!(z > 0.0)) return -CUDART_INF;
+            const double l = log(z);
+            return -l - l * l / (2 * a * a);
+        }
+        case CB2_PRIOR_CAUCHY: return -log1p(z * z);
+        case CB2_PRIOR_LAPLACE: return -fabs(z);
+        case CB2_PRIOR_LOGUNIFORM: return (z > 0.0) ? -log(z) : -CUDART_INF;
+        default: return 0.0;
+    }
+}
+
 struct LikeDev {
     int32_t kind, dim, n_modes, derived;
     int32_t idx_off;     // into Model.ipool
@@ -38,7 +68,11 @@ struct ModelDev {
     const int32_t *prior_kind;  // [D]
     const double *lower, *upper, *loc, *pscale;
     const int32_t *periodic;
-    int32_t any_periodic, any_normal;
+    // shape parameters and normalisation of the non-uniform, non-normal 1-D priors
+    // (cb2_set_prior_shapes); null when every parameter is uniform or normal
+    const double *pa, *pb, *pcn;
+    // any_normal: some parameter has a non-uniform prior; any_generic: some kind >= 2
+    int32_t any_periodic, any_normal, any_generic;
     double uniform_logp;
     // likelihoods
     LikeDev likes[CB2_MAX_LIKES];

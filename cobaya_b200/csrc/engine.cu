@@ -54,9 +54,10 @@ struct cb2_engine {
     std::string err;
     int sm_count = 148;
     // ---- host model
+    bool have_shapes = false;
     bool have_prior = false, have_blocking = false, have_proposal = false, have_state = false;
     std::vector<int32_t> prior_kind, periodic;
-    std::vector<double> lower, upper, loc, pscale;
+    std::vector<double> lower, upper, loc, pscale, pa, pb, pcn;
     double uniform_logp = 0.0;
     std::vector<LikeHost> likes;
     int32_t n_der = 0;
@@ -73,7 +74,7 @@ struct cb2_engine {
     bool model_dirty = true;
     // ---- device model
     DevBuf<int32_t> d_prior_kind, d_periodic, d_ipool, d_i_of_j;
-    DevBuf<double> d_lower, d_upper, d_loc, d_pscale, d_dpool, d_TT;
+    DevBuf<double> d_lower, d_upper, d_loc, d_pscale, d_pa, d_pb, d_pcn, d_dpool, d_TT;
     DevBuf<double> d_fastpack;  // fragment-ordered matrices for the DMMA kernel
     FastPackDesc fast_desc;
     bool fast_ready = false;
@@ -220,7 +221,8 @@ extern "C" int cb2_destroy(cb2_engine *h) {
     cudaStreamSynchronize(h->stream);
     h->d_prior_kind.release(); h->d_periodic.release(); h->d_ipool.release();
     h->d_i_of_j.release(); h->d_lower.release(); h->d_upper.release(); h->d_loc.release();
-    h->d_pscale.release(); h->d_dpool.release(); h->d_TT.release(); h->d_fastpack.release();
+    h->d_pscale.release(); h->d_pa.release(); h->d_pb.release(); h->d_pcn.release();
+    h->d_dpool.release(); h->d_TT.release(); h->d_fastpack.release();
     h->d_x.release(); h->d_logpost.release(); h->d_logprior.release(); h->d_ll.release();
     h->d_der.release(); h->d_rows.release(); h->d_weight.release(); h->d_prior_rej.release();
     h->d_burn_left.release(); h->d_added_w.release(); h->d_n_rows.release();
@@ -245,8 +247,9 @@ extern "C" int cb2_set_prior(cb2_engine *h, const int32_t *kind, const double *l
     if (!h) return -1;
     const int D = h->D;
     for (int i = 0; i < D; ++i) {
-        if (kind[i] != 0 && kind[i] != 1) FAIL(h, -1, "cb2_set_prior: unknown prior kind %d", kind[i]);
-        if (kind[i] == 1 && !(scale[i] > 0)) FAIL(h, -1, "cb2_set_prior: normal scale must be > 0");
+        if (kind[i] < 0 || kind[i] > CB2_PRIOR_LOGUNIFORM)
+            FAIL(h, -1, "cb2_set_prior: unknown prior kind %d", kind[i]);
+        if (kind[i] != 0 && !(scale[i] > 0)) FAIL(h, -1, "cb2_set_prior: prior scale must be > 0");
         if (periodic[i] && !(std::isfinite(lower[i]) && std::isfinite(upper[i])))
             FAIL(h, -1, "cb2_set_prior: periodic parameter %d is not bounded", i);
     }
@@ -257,7 +260,25 @@ extern "C" int cb2_set_prior(cb2_engine *h, const int32_t *kind, const double *l
     h->pscale.assign(scale, scale + D);
     h->periodic.assign(periodic, periodic + D);
     h->uniform_logp = uniform_logp;
+    h->pa.assign(D, 0.0); h->pb.assign(D, 0.0); h->pcn.assign(D, 0.0);
     h->have_prior = true;
+    h->have_shapes = false;
+    h->model_dirty = true;
+    return 0;
+}
+
+extern "C" int cb2_set_prior_shapes(cb2_engine *h, const double *a, const double *b,
+                                    const double *log_norm) {
+    if (!h) return -1;
+    if (!h->have_prior) FAIL(h, -1, "cb2_set_prior_shapes: call cb2_set_prior first");
+    const int D = h->D;
+    for (int i = 0; i < D; ++i)
+        if (h->prior_kind[i] >= 2 && !std::isfinite(log_norm[i]))
+            FAIL(h, -1, "cb2_set_prior_shapes: non-finite normalisation for parameter %d", i);
+    h->pa.assign(a, a + D);
+    h->pb.assign(b, b + D);
+    h->pcn.assign(log_norm, log_norm + D);
+    h->have_shapes = true;
     h->model_dirty = true;
     return 0;
 }
@@ -318,6 +339,22 @@ extern "C" int cb2_add_rosenbrock(cb2_engine *h, int32_t dim, const int32_t *idx
     L.idx.assign(idx, idx + dim);
     for (int i = 0; i < dim; ++i)
         if (idx[i] < 0 || idx[i] >= h->D) FAIL(h, -1, "rosenbrock: parameter index out of range");
+    h->likes.push_back(L);
+    h->model_dirty = true;
+    return 0;
+}
+
+extern "C" int cb2_add_constant(cb2_engine *h, double value) {
+    if (!h) return -1;
+    if ((int)h->likes.size() >= CB2_MAX_LIKES) FAIL(h, -1, "too many likelihoods (max %d)", CB2_MAX_LIKES);
+    if (!std::isfinite(value)) FAIL(h, -1, "constant likelihood: value must be finite");
+    LikeHost L;
+    L.d.kind = 2;
+    L.d.dim = 0;
+    L.d.n_modes = 0;
+    L.d.derived = 0;
+    L.d.scale = value;
+    L.d.der_off = h->n_der;
     h->likes.push_back(L);
     h->model_dirty = true;
     return 0;
@@ -433,6 +470,12 @@ static int build_model(cb2_engine *h) {
     if ((rc = upload(h, h->d_upper, h->upper))) return rc;
     if ((rc = upload(h, h->d_loc, h->loc))) return rc;
     if ((rc = upload(h, h->d_pscale, h->pscale))) return rc;
+    for (int i = 0; i < h->D; ++i)
+        if (h->prior_kind[i] >= 2 && !h->have_shapes)
+            FAIL(h, -1, "prior kind %d needs cb2_set_prior_shapes", h->prior_kind[i]);
+    if ((rc = upload(h, h->d_pa, h->pa))) return rc;
+    if ((rc = upload(h, h->d_pb, h->pb))) return rc;
+    if ((rc = upload(h, h->d_pcn, h->pcn))) return rc;
     if ((rc = upload(h, h->d_i_of_j, h->i_of_j))) return rc;
     if ((rc = upload(h, h->d_TT, h->TT))) return rc;
     std::vector<double> dpool;
@@ -462,10 +505,12 @@ static int build_model(cb2_engine *h) {
     M.prior_kind = h->d_prior_kind.p;
     M.lower = h->d_lower.p; M.upper = h->d_upper.p; M.loc = h->d_loc.p; M.pscale = h->d_pscale.p;
     M.periodic = h->d_periodic.p;
-    M.any_periodic = 0; M.any_normal = 0;
+    M.pa = h->d_pa.p; M.pb = h->d_pb.p; M.pcn = h->d_pcn.p;
+    M.any_periodic = 0; M.any_normal = 0; M.any_generic = 0;
     for (int i = 0; i < h->D; ++i) {
         M.any_periodic |= h->periodic[i] ? 1 : 0;
-        M.any_normal |= h->prior_kind[i] == 1 ? 1 : 0;
+        M.any_normal |= h->prior_kind[i] != 0 ? 1 : 0;
+        M.any_generic |= h->prior_kind[i] >= 2 ? 1 : 0;
     }
     M.uniform_logp = h->uniform_logp;
     M.dpool = h->d_dpool.p;

@@ -47,7 +47,8 @@ static int pack_fast(cb2_engine *h) {
     P.off_c0 = take(nm);
     P.off_w = take(nm);
     P.off_lower = take(DP); P.off_upper = take(DP); P.off_loc = take(DP);
-    P.off_mls = take(DP); P.off_isc = take(DP); P.off_flags = take(DP); P.off_iofj = take(DP);
+    P.off_mls = take(DP); P.off_isc = take(DP); P.off_pa = take(DP); P.off_pb = take(DP);
+    P.off_flags = take(DP); P.off_iofj = take(DP);
     P.total = o;
     {
         bool ident = (D == DP) && (row_width(h) % 2 == 0);
@@ -89,9 +90,12 @@ static int pack_fast(cb2_engine *h) {
             pk[P.off_upper + j] = h->upper[i];
             pk[P.off_loc + j] = h->loc[i];
             pk[P.off_isc + j] = h->pscale[i];
-            pk[P.off_mls + j] = (h->prior_kind[i] == 1)
-                                    ? (-std::log(h->pscale[i]) - CB2_LOG_2PI / 2) : 0.0;
-            iflags[j] = (h->prior_kind[i] == 1 ? 1 : 0) | (h->periodic[i] ? 2 : 0);
+            const int kd = h->prior_kind[i];
+            pk[P.off_mls + j] = (kd == 1) ? (-std::log(h->pscale[i]) - CB2_LOG_2PI / 2)
+                                : (kd >= 2 ? h->pcn[i] : 0.0);
+            pk[P.off_pa + j] = kd >= 2 ? h->pa[i] : 0.0;
+            pk[P.off_pb + j] = kd >= 2 ? h->pb[i] : 0.0;
+            iflags[j] = (kd != 0 ? 1 : 0) | (h->periodic[i] ? 2 : 0) | (kd << 8);
             iiofj[j] = i;
         } else {
             pk[P.off_lower + j] = -INFINITY;

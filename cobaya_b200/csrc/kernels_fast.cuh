@@ -425,8 +425,9 @@ struct FastPackDesc {
     int off_mu;    // [n_modes][DP]  means in sorted coordinates
     int off_c0;    // [n_modes]      d log 2pi + logdet
     int off_w;     // [n_modes]      weights
-    int off_lower, off_upper, off_loc, off_mls, off_isc;  // [DP] each (mls = -log s - log(2pi)/2, isc = s)
-    int off_flags; // [DP] as doubles: bit0 normal prior, bit1 periodic
+    int off_lower, off_upper, off_loc, off_mls, off_isc;  // [DP] each (mls = log-normalisation, isc = s)
+    int off_pa, off_pb;  // [DP] shape parameters of the generic 1-D priors
+    int off_flags; // [DP] as doubles: bit0 non-uniform prior, bit1 periodic, bits 8.. prior kind
     int off_iofj;  // [DP] as doubles: sampler index of sorted j (or -1 for padding)
     int iofj_identity;  // D == DP, i_of_j[j] == j and the row stride keeps 16-byte alignment
     int vec_ok;         // every block with n_b >= 2 has even start and even size
@@ -710,7 +711,12 @@ k_step_fast(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gp
                     }
                     if ((m_norm >> (2 * n + h)) & 1u) {
                         const double zz = (xv - pack[P.off_loc + j]) / pack[P.off_isc + j];
-                        ps += pack[P.off_mls + j] - zz * zz / 2;
+                        if (M.any_generic)
+                            ps += pack[P.off_mls + j] +
+                                  prior1d_shape(pflag[j] >> 8, zz, pack[P.off_pa + j],
+                                                pack[P.off_pb + j]);
+                        else
+                            ps += pack[P.off_mls + j] - zz * zz / 2;
                     }
                 }
                 if (!(xv <= up) || !(xv >= lo) || !isfinite(xv)) bad = true;
@@ -938,7 +944,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
 }
 
 static inline bool pc_step_supported(const ModelDev &M, const FastPackDesc &P) {
-    return P.n_modes == 1 && !M.any_periodic;
+    return P.n_modes == 1 && !M.any_periodic && !M.any_generic;
 }
 
 template <int NT, bool HAS_NORMAL>

@@ -162,10 +162,16 @@ __device__ __forceinline__ double warp_logpost(const ModelDev &M, const double *
     double s = 0.0;
     if (M.any_normal) {
         for (int i = lane; i < D; i += 32)
-            if (M.prior_kind[i] == 1) {
-                double sc = M.pscale[i];
-                double zz = (xs[i] - M.loc[i]) / sc;
-                s += (-log(sc) - CB2_LOG_2PI / 2) - zz * zz / 2;
+            {
+                const int kd = M.prior_kind[i];
+                if (kd == CB2_PRIOR_NORMAL) {
+                    double sc = M.pscale[i];
+                    double zz = (xs[i] - M.loc[i]) / sc;
+                    s += (-log(sc) - CB2_LOG_2PI / 2) - zz * zz / 2;
+                } else if (kd >= 2) {
+                    double zz = (xs[i] - M.loc[i]) / M.pscale[i];
+                    s += M.pcn[i] + prior1d_shape(kd, zz, M.pa[i], M.pb[i]);
+                }
             }
         s = warp_sum(s);
     }
@@ -208,6 +214,8 @@ __device__ __forceinline__ double warp_logpost(const ModelDev &M, const double *
                     val = log(acc) + mx;
                 }
             }
+        } else if (L.kind == 2) {
+            val = L.scale;  // `one` (likelihoods/one/one.py:26-28)
         } else {
             double acc = 0.0;
             for (int i = lane; i + 1 < d; i += 32) {

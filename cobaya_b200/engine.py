@@ -11,7 +11,7 @@ import ctypes as C
 import numpy as np
 
 from . import _cabi
-from .flatmodel import LIKE_GAUSSIAN_MIXTURE, LIKE_ROSENBROCK, FlatModel
+from .flatmodel import LIKE_CONSTANT, LIKE_GAUSSIAN_MIXTURE, LIKE_ROSENBROCK, FlatModel
 
 FLAG_STUCK = 1
 FLAG_ROWS_FULL = 2
@@ -76,6 +76,9 @@ class Engine:
         self._ck(self.lib.cb2_set_prior(
             self.h, p(_i32(fm.prior_kind)), p(_f64(fm.lower)), p(_f64(fm.upper)),
             p(_f64(fm.loc)), p(_f64(fm.pscale)), p(_i32(fm.periodic)), fm.uniform_logp))
+        if np.any(fm.prior_kind >= 2):
+            self._ck(self.lib.cb2_set_prior_shapes(
+                self.h, p(_f64(fm.pa)), p(_f64(fm.pb)), p(_f64(fm.prior_log_norm))))
         self._ck(self.lib.cb2_clear_likelihoods(self.h))
         for lk in fm.likes:
             if lk.kind == LIKE_GAUSSIAN_MIXTURE:
@@ -86,6 +89,8 @@ class Engine:
             elif lk.kind == LIKE_ROSENBROCK:
                 self._ck(self.lib.cb2_add_rosenbrock(self.h, lk.dim, p(_i32(lk.idx)),
                                                      float(lk.scale)))
+            elif lk.kind == LIKE_CONSTANT:
+                self._ck(self.lib.cb2_add_constant(self.h, float(lk.scale)))
             else:
                 raise EngineError(f"unknown likelihood kind {lk.kind}")
         self._ck(self.lib.cb2_set_blocking(

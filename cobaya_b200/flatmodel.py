@@ -25,10 +25,65 @@ from scipy.linalg import lapack as _lapack
 
 LIKE_GAUSSIAN_MIXTURE = 0
 LIKE_ROSENBROCK = 1
+LIKE_CONSTANT = 2
 MAX_BLOCKS = 16
 
 PRIOR_UNIFORM = 0
 PRIOR_NORMAL = 1
+# scipy.stats distributions the reference reaches through ``pdf.logpdf``
+# (prior.py:520-525); numbering = include/cobaya_b200.h CB2_PRIOR_*
+PRIOR_KINDS = {"uniform": 0, "norm": 1, "truncnorm": 2, "halfnorm": 3, "expon": 4, "beta": 5,
+               "gamma": 6, "lognorm": 7, "cauchy": 8, "laplace": 9, "loguniform": 10,
+               "reciprocal": 10}
+
+
+def _log_gauss_mass(a: float, b: float) -> float:
+    """log(Phi(b) - Phi(a)), evaluated on the side where the difference does not cancel."""
+    from scipy.special import log_ndtr, ndtr
+
+    if b <= 0:
+        return float(log_ndtr(b) + np.log1p(-np.exp(log_ndtr(a) - log_ndtr(b))))
+    if a >= 0:
+        return _log_gauss_mass(-b, -a)
+    return float(np.log1p(-ndtr(a) - ndtr(-b)))
+
+
+def prior_log_norm(kind: int, scale: float, a: float, b: float) -> float:
+    """Additive constant ``cn`` of ``logpdf(x) = cn + f((x-loc)/scale; a, b)`` for the
+    engine's generic 1-D priors (f: csrc/common.cuh ``prior1d_shape``)."""
+    from scipy.special import betaln, gammaln
+
+    ls = np.log(scale)
+    half_log_2pi = 0.5 * np.log(2 * np.pi)
+    if kind == 2:
+        if not a < b:
+            raise FlatModelError("truncnorm needs a < b")
+        return float(-half_log_2pi - _log_gauss_mass(a, b) - ls)
+    if kind == 3:
+        return float(0.5 * np.log(2 / np.pi) - ls)
+    if kind == 4:
+        return float(-ls)
+    if kind == 5:
+        if not (a > 0 and b > 0):
+            raise FlatModelError("beta needs a, b > 0")
+        return float(-betaln(a, b) - ls)
+    if kind == 6:
+        if not a > 0:
+            raise FlatModelError("gamma needs a > 0")
+        return float(-gammaln(a) - ls)
+    if kind == 7:
+        if not a > 0:
+            raise FlatModelError("lognorm needs s > 0")
+        return float(-np.log(a) - half_log_2pi - ls)
+    if kind == 8:
+        return float(-np.log(np.pi) - ls)
+    if kind == 9:
+        return float(-np.log(2.0) - ls)
+    if kind == 10:
+        if not 0 < a < b:
+            raise FlatModelError("loguniform needs 0 < a < b")
+        return float(-np.log(np.log(b) - np.log(a)) - ls)
+    return 0.0
 
 
 class FlatModelError(ValueError):
@@ -133,6 +188,27 @@ class LikeSpec:
         return cls(kind=LIKE_ROSENBROCK, idx=np.asarray(idx, dtype=np.int32), name=name,
                    scale=float(scale))
 
+    @classmethod
+    def gaussian(cls, idx, mean, cov, normalized=True, name="gaussian"):
+        """``gaussian`` (likelihoods/gaussian/gaussian.py:96-112): -chi2/2 + log_norm with
+        log_norm = -(k log 2pi + log|cov|)/2, or 0 if not ``normalized`` -- a one-mode
+        mixture whose normalisation is fixed through the log-determinant entry."""
+        lk = cls.gaussian_mixture(idx, np.atleast_1d(mean), np.atleast_2d(cov), name=name)
+        d = lk.dim
+        if normalized:
+            sign, logdet = np.linalg.slogdet(np.atleast_2d(cov))  # gaussian.py:84
+            if sign <= 0:
+                raise FlatModelError("The covariance matrix is not positive definite!")
+            lk.logdet = np.array([logdet])
+        else:
+            lk.logdet = np.array([-d * np.log(2 * np.pi)])
+        return lk
+
+    @classmethod
+    def constant(cls, value=0.0, name="one"):
+        """``one`` (likelihoods/one/one.py:26-28)."""
+        return cls(kind=LIKE_CONSTANT, idx=np.zeros(0, np.int32), name=name, scale=float(value))
+
     @property
     def n_derived(self) -> int:
         return self.dim * self.n_modes if (self.kind == LIKE_GAUSSIAN_MIXTURE and
@@ -151,6 +227,9 @@ class FlatModel:
     pscale: np.ndarray
     periodic: np.ndarray
     likes: list
+    # scipy shape parameters of the generic 1-D priors (kinds >= 2)
+    pa: np.ndarray | None = None
+    pb: np.ndarray | None = None
     # blocking: list of blocks (lists of sampler indices), ascending speed
     blocks: list = None
     oversampling: list = None
@@ -171,6 +250,15 @@ class FlatModel:
         for a in ("lower", "upper", "loc", "pscale"):
             setattr(self, a, np.asarray(getattr(self, a), dtype=np.float64).reshape(D))
         self.periodic = np.asarray(self.periodic, dtype=np.int32).reshape(D)
+        for a in ("pa", "pb"):
+            v = getattr(self, a)
+            setattr(self, a, np.zeros(D) if v is None else
+                    np.asarray(v, dtype=np.float64).reshape(D))
+        if np.any((self.prior_kind < 0) | (self.prior_kind > max(PRIOR_KINDS.values()))):
+            raise FlatModelError("unknown 1-D prior kind")
+        self.prior_log_norm = np.array([
+            prior_log_norm(int(k), s, a, b) if k >= 2 else 0.0
+            for k, s, a, b in zip(self.prior_kind, self.pscale, self.pa, self.pb)])
         if self.blocks is None:
             self.blocks = [list(range(D))]
         if self.oversampling is None:

@@ -15,7 +15,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .flatmodel import (PRIOR_NORMAL, PRIOR_UNIFORM, FlatModel, FlatModelError, LikeSpec)
+from .flatmodel import (PRIOR_KINDS, PRIOR_UNIFORM, FlatModel, FlatModelError, LikeSpec)
 
 
 class UnsupportedModelError(FlatModelError):
@@ -23,7 +23,12 @@ class UnsupportedModelError(FlatModelError):
 
 
 def lower_prior(prior):
-    """cobaya/prior.py:459-545 -> (kind, lower, upper, loc, scale, periodic)."""
+    """cobaya/prior.py:459-545 -> (kind, lower, upper, loc, scale, periodic, a, b).
+
+    ``uniform`` and ``norm`` are the reference's own fast paths (prior.py:514-533); the
+    other recognised scipy.stats distributions (flatmodel.PRIOR_KINDS) are evaluated on
+    the device in closed form.  Each lowered parameter is checked against its own
+    ``pdf.logpdf`` at a few points of the support before it is accepted."""
     D = prior.d()
     if len(getattr(prior, "external", {}) or {}):
         raise UnsupportedModelError(
@@ -32,24 +37,70 @@ def lower_prior(prior):
         )
     kind = np.zeros(D, np.int32)
     loc, scale = np.zeros(D), np.ones(D)
+    pa, pb = np.zeros(D), np.zeros(D)
     lower = np.array(prior._lower_limits, dtype=np.float64)
     upper = np.array(prior._upper_limits, dtype=np.float64)
     for i, pdf in enumerate(prior.pdf):
         name = pdf.dist.name
-        if name == "uniform":
-            kind[i] = PRIOR_UNIFORM
-        elif name == "norm":
-            kind[i] = PRIOR_NORMAL
-            loc[i] = pdf.kwds.get("loc", 0.0)
-            scale[i] = pdf.kwds.get("scale", 1.0)
-        else:
+        if name not in PRIOR_KINDS:
             raise UnsupportedModelError(
                 f"1-D prior '{name}' of parameter '{prior.params[i]}' is not in the "
-                "engine's recognised set (uniform, norm)."
+                f"engine's recognised set ({', '.join(sorted(PRIOR_KINDS))})."
             )
+        kind[i] = PRIOR_KINDS[name]
+        if kind[i] == PRIOR_UNIFORM:
+            continue
+        # rv_frozen keeps shapes in .args and/or .kwds; let scipy sort them out
+        shapes, lc, sc = pdf.dist._parse_args(*pdf.args, **pdf.kwds)
+        loc[i], scale[i] = float(lc), float(sc)
+        if len(shapes) > 0:
+            pa[i] = float(shapes[0])
+        if len(shapes) > 1:
+            pb[i] = float(shapes[1])
+        if len(shapes) > 2:
+            raise UnsupportedModelError(f"1-D prior '{name}': too many shape parameters")
     periodic = np.zeros(D, np.int32)
     periodic[list(prior._periodic_bounds)] = 1
-    return kind, lower, upper, loc, scale, periodic
+    _check_lowered_priors(prior, kind, lower, upper, loc, scale, pa, pb)
+    return kind, lower, upper, loc, scale, periodic, pa, pb
+
+
+def _shape_host(kind, z, a, b):
+    """Host mirror of csrc/common.cuh ``prior1d_shape`` (used only for the self-check)."""
+    if kind in (1, 2, 3):
+        return -z * z / 2
+    if kind == 4:
+        return -z
+    if kind == 5:
+        return (a - 1) * np.log(z) + (b - 1) * np.log1p(-z)
+    if kind == 6:
+        return (a - 1) * np.log(z) - z
+    if kind == 7:
+        return -np.log(z) - np.log(z) ** 2 / (2 * a * a)
+    if kind == 8:
+        return -np.log1p(z * z)
+    if kind == 9:
+        return -abs(z)
+    if kind == 10:
+        return -np.log(z)
+    raise ValueError(kind)
+
+
+def _check_lowered_priors(prior, kind, lower, upper, loc, scale, pa, pb):
+    from .flatmodel import prior_log_norm
+
+    for i, pdf in enumerate(prior.pdf):
+        if kind[i] < 2:
+            continue
+        lo, hi = pdf.ppf(0.2), pdf.ppf(0.8)
+        cn = prior_log_norm(int(kind[i]), scale[i], pa[i], pb[i])
+        for x in (lo, 0.5 * (lo + hi), hi):
+            want = float(pdf.logpdf(x))
+            got = cn + _shape_host(int(kind[i]), (x - loc[i]) / scale[i], pa[i], pb[i])
+            if not np.isclose(got, want, rtol=1e-10, atol=1e-10):
+                raise UnsupportedModelError(
+                    f"1-D prior '{pdf.dist.name}' of parameter '{prior.params[i]}' could not "
+                    f"be lowered consistently (engine {got!r} vs scipy {want!r} at x={x!r}).")
 
 
 def lower_likelihoods(model, sampled):
@@ -68,13 +119,21 @@ def lower_likelihoods(model, sampled):
                     derived_names=list(like.output_params) if like.derived else [],
                 )
             )
+        elif cls == "Gaussian" and hasattr(like, "inv_cov"):
+            idx = [sampled.index(p) for p in like.input_params]
+            likes.append(LikeSpec.gaussian(idx, np.asarray(like.mean), np.asarray(like.cov),
+                                           normalized=bool(getattr(like, "normalized", True)),
+                                           name=name))
+        elif cls == "one" and not getattr(like, "noise", None):
+            likes.append(LikeSpec.constant(0.0, name=name))
         elif cls == "Rosenbrock" and hasattr(like, "b200_scale"):
             idx = [sampled.index(p) for p in like.input_params]
             likes.append(LikeSpec.rosenbrock(idx, scale=like.b200_scale, name=name))
         else:
             raise UnsupportedModelError(
                 f"Likelihood '{name}' ({cls}) cannot be evaluated on the device: the "
-                "engine recognises gaussian_mixture (and the built-in Rosenbrock). "
+                "engine recognises gaussian_mixture, gaussian, one (without noise) and the "
+                "built-in Rosenbrock. "
                 "No CPU fallback is provided."
             )
     return likes
@@ -91,7 +150,7 @@ def lower_model(model, sampler=None, *, blocks=None, oversampling=None, drag=Fal
         raise UnsupportedModelError(
             "Dynamically defined (lambda) input parameters are not supported."
         )
-    kind, lower, upper, loc, scale, periodic = lower_prior(model.prior)
+    kind, lower, upper, loc, scale, periodic, pa, pb = lower_prior(model.prior)
     likes = lower_likelihoods(model, sampled)
     derived_model = [p for p in par.derived_params()]
     derived_engine = [n for lk in likes for n in lk.derived_names]
@@ -117,7 +176,7 @@ def lower_model(model, sampler=None, *, blocks=None, oversampling=None, drag=Fal
         max_tries = 2**59
     return FlatModel(
         names=sampled, prior_kind=kind, lower=lower, upper=upper, loc=loc, pscale=scale,
-        periodic=periodic, likes=likes, blocks=blocks, oversampling=oversampling,
+        periodic=periodic, pa=pa, pb=pb, likes=likes, blocks=blocks, oversampling=oversampling,
         drag=drag, i_last_slow_block=i_last_slow_block,
         drag_interp_steps=drag_interp_steps, proposal_cov=proposal_cov,
         proposal_scale=proposal_scale, temperature=temperature, max_tries=int(max_tries),

@@ -49,12 +49,34 @@ int cb2_create(int device, int64_t n_chains, int32_t D, uint64_t seed,
 int cb2_destroy(cb2_engine *h);
 
 /* Prior.logps_internal inputs (cobaya/prior.py:514-533,733-763): per parameter
- * kind (0 uniform, 1 normal), bounds, normal loc/scale, periodic flag
+ * kind (CB2_PRIOR_*), bounds, loc/scale, periodic flag
  * (prior.py:500-513, reduce_periodic :658-676) and the precomputed
  * -sum(log(upper-lower)) over uniform parameters (prior.py:526-532). */
 int cb2_set_prior(cb2_engine *h, const int32_t *kind, const double *lower,
                   const double *upper, const double *loc, const double *scale,
                   const int32_t *periodic, double uniform_logp);
+
+/* 1-D prior kinds.  0/1 are the reference's own fast paths (uniform: prior.py:526-532;
+ * normal: _fast_norm_logpdf, tools.py:720-729); the others are the scipy.stats
+ * distributions the reference reaches through pdf.logpdf (prior.py:520-525,
+ * tools.py:611-718), evaluated as  log_norm + f((x-loc)/scale; a, b). */
+#define CB2_PRIOR_UNIFORM 0
+#define CB2_PRIOR_NORMAL 1
+#define CB2_PRIOR_TRUNCNORM 2  /* a, b: truncation in standard units; f = -z^2/2 */
+#define CB2_PRIOR_HALFNORM 3   /* f = -z^2/2 */
+#define CB2_PRIOR_EXPON 4      /* f = -z */
+#define CB2_PRIOR_BETA 5       /* f = (a-1) log z + (b-1) log(1-z) */
+#define CB2_PRIOR_GAMMA 6      /* f = (a-1) log z - z */
+#define CB2_PRIOR_LOGNORM 7    /* a = s: f = -log z - log(z)^2 / (2 s^2) */
+#define CB2_PRIOR_CAUCHY 8     /* f = -log(1+z^2) */
+#define CB2_PRIOR_LAPLACE 9    /* f = -|z| */
+#define CB2_PRIOR_LOGUNIFORM 10 /* a, b: support in standard units; f = -log z */
+
+/* Shape parameters a[D], b[D] and log-normalisation log_norm[D] (includes -log(scale))
+ * of the parameters whose kind is >= 2; entries of other parameters are ignored.
+ * Must follow cb2_set_prior (which resets them). */
+int cb2_set_prior_shapes(cb2_engine *h, const double *a, const double *b,
+                         const double *log_norm);
 
 int cb2_clear_likelihoods(cb2_engine *h);
 /* GaussianMixture (cobaya/likelihoods/gaussian_mixture/gaussian_mixture.py:45-163):
@@ -69,6 +91,9 @@ int cb2_add_gaussian_mixture(cb2_engine *h, int32_t dim, const int32_t *idx,
 /* Built-in external-likelihood stand-in for BASELINE.json configs[3]:
  * logp = -scale * sum_i [100 (x_{i+1}-x_i^2)^2 + (1-x_i)^2]. */
 int cb2_add_rosenbrock(cb2_engine *h, int32_t dim, const int32_t *idx, double scale);
+/* `one` (cobaya/likelihoods/one/one.py:26-28): a likelihood with no input parameters
+ * whose log-value is a constant (0 for `one`); keeps its chi2__<name> column. */
+int cb2_add_constant(cb2_engine *h, double value);
 
 /* BlockedProposer.__init__ (cobaya/samplers/mcmc/proposal.py:96-201): blocks in
  * ascending speed given by their sizes, i_of_j (sorted index -> sampler index),

@@ -11,7 +11,7 @@ returns the engine's counter-based Philox draws (same distributions as the
 numpy calls it replaces) so that the chain the reference produces can be
 compared value-for-value with the oracle and the CUDA engine.
 
-Usage:  python oracle/make_golden.py            (rewrites tests/golden/*.npz)
+Usage:  python oracle/make_golden.py [fixture ...]   (rewrites tests/golden/*.npz)
 """
 
 from __future__ import annotations
@@ -264,6 +264,69 @@ def info_g4():
     return info, mean, cov, cov0
 
 
+def info_g5():
+    """11-D: one parameter per recognised scipy.stats 1-D prior (cobaya/prior.py:520-525,
+    tools.py:611-718), two blocks; the likelihood is wide enough that every prior shapes
+    the posterior."""
+    names = ["u", "n", "tn", "hn", "ex", "be", "ga", "ln", "ca", "la", "lu"]
+    priors = {
+        "u": {"min": -1, "max": 2},
+        "n": {"dist": "norm", "loc": 0.3, "scale": 0.7},
+        "tn": {"dist": "truncnorm", "loc": 0.5, "scale": 0.8, "min": -0.4, "max": 1.9},
+        "hn": {"dist": "halfnorm", "loc": 0.1, "scale": 1.3},
+        "ex": {"dist": "expon", "loc": -0.2, "scale": 0.9},
+        "be": {"dist": "beta", "a": 2.5, "b": 1.7, "min": -0.5, "max": 2.5},
+        "ga": {"dist": "gamma", "a": 3.2, "loc": 0.0, "scale": 0.4},
+        "ln": {"dist": "lognorm", "s": 0.6, "loc": -0.1, "scale": 1.1},
+        "ca": {"dist": "cauchy", "loc": 0.2, "scale": 0.5},
+        "la": {"dist": "laplace", "loc": 0.4, "scale": 0.6},
+        "lu": {"dist": "loguniform", "a": 0.05, "b": 20.0},
+    }
+    mean = np.array([0.5, 0.3, 0.6, 0.9, 0.5, 1.2, 1.0, 0.9, 0.2, 0.4, 1.0])
+    rng = np.random.default_rng(55)
+    A = rng.standard_normal((11, 22))
+    C = A @ A.T / 22
+    d = np.sqrt(np.diag(C))
+    cov = 0.35**2 * C / d[:, None] / d[None, :]
+    cov = (cov + cov.T) / 2
+    info = {
+        "params": {p: {"prior": priors[p], "ref": float(m), "proposal": 0.2}
+                   for p, m in zip(names, mean)},
+        "likelihood": {"gaussian_mixture": {"means": [mean.tolist()], "covs": [cov.tolist()],
+                                            "input_params": names, "output_params": []}},
+        "sampler": {"mcmc": {"blocking": [[1, names[:5]], [2, names[5:]]],
+                             "covmat": cov * 0.5, "covmat_params": names,
+                             "learn_proposal": False, "measure_speeds": False,
+                             "burn_in": 0, "seed": 8}},
+    }
+    return info, mean, cov, cov * 0.5
+
+
+def _prior_shapes(model):
+    a, b, loc, scale = [], [], [], []
+    for pdf in model.prior.pdf:
+        shapes, lc, sc = pdf.dist._parse_args(*pdf.args, **pdf.kwds)
+        a.append(float(shapes[0]) if len(shapes) > 0 else 0.0)
+        b.append(float(shapes[1]) if len(shapes) > 1 else 0.0)
+        loc.append(float(lc))
+        scale.append(float(sc))
+    return np.array(a), np.array(b), np.array(loc), np.array(scale)
+
+
+def prior_known_answers(model, mean, n=400, seed=77):
+    """Known answers of Model.logposterior (model.py:579-678) with the scipy priors:
+    points scattered around the likelihood mean, some outside the supports."""
+    rng = np.random.default_rng(seed)
+    X = mean + 0.8 * rng.standard_normal((n, len(mean)))
+    X[::7] = mean + 0.05 * rng.standard_normal((len(X[::7]), len(mean)))
+    lp, ll = np.empty(n), np.empty(n)
+    for i, x in enumerate(X):
+        r = model.logposterior(x)
+        lp[i] = r.logpriors[0]
+        ll[i] = r.loglikes[0] if len(r.loglikes) else np.nan
+    return X, lp, ll
+
+
 def dump_case(name, info_fn, n_proposals, seed, chain_ids):
     info, means, covs, S0 = info_fn()
     out = {}
@@ -296,8 +359,8 @@ def dump_case(name, info_fn, n_proposals, seed, chain_ids):
         periodic=np.array([i in model.prior._periodic_bounds
                            for i in range(model.prior.d())]),
         prior_dist=np.array([pdf.dist.name for pdf in model.prior.pdf]),
-        prior_loc=np.array([pdf.kwds.get("loc", 0.0) for pdf in model.prior.pdf]),
-        prior_scale=np.array([pdf.kwds.get("scale", 1.0) for pdf in model.prior.pdf]),
+        prior_loc=_prior_shapes(model)[2], prior_scale=_prior_shapes(model)[3],
+        prior_a=_prior_shapes(model)[0], prior_b=_prior_shapes(model)[1],
         like_weights=np.atleast_1d(np.asarray(
             model.likelihood["gaussian_mixture"].weights, dtype=np.float64)),
         like_derived=int(bool(model.likelihood["gaussian_mixture"].derived)),
@@ -306,9 +369,56 @@ def dump_case(name, info_fn, n_proposals, seed, chain_ids):
     )
     for b, T in enumerate(pr.transform):
         out[f"transform_{b}"] = T
+    if name.startswith("g5"):
+        X, lp, ll = prior_known_answers(model, np.atleast_2d(means)[0])
+        out.update(kat_x=X, kat_logprior=lp, kat_loglike=ll)
     np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
     print(name, {k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items()
                  if k.startswith("rows_")})
+
+
+def info_g6():
+    """4-D, two more of the reference's internal likelihoods: ``gaussian`` with
+    ``normalized: False`` (likelihoods/gaussian/gaussian.py) and ``one``
+    (likelihoods/one/one.py), a normal and a uniform prior."""
+    rng = np.random.default_rng(66)
+    A = rng.standard_normal((4, 8))
+    cov = 0.1**2 * (A @ A.T / 8)
+    cov = (cov + cov.T) / 2
+    mean = np.array([0.1, -0.2, 0.05, 0.3])
+    names = ["q0", "q1", "q2", "q3"]
+    info = {
+        "params": {p: {"prior": {"min": -1, "max": 1}, "ref": float(m), "proposal": 0.05}
+                   for p, m in zip(names, mean)},
+        "likelihood": {"gaussian": {"mean": mean.tolist(), "cov": cov.tolist(),
+                                    "normalized": False, "input_params": names},
+                       "one": None},
+        "sampler": {"mcmc": {"covmat": cov, "covmat_params": names, "learn_proposal": False,
+                             "measure_speeds": False, "burn_in": 0, "seed": 9}},
+    }
+    info["params"]["q2"]["prior"] = {"dist": "norm", "loc": 0.0, "scale": 0.5}
+    return info, mean, cov
+
+
+def dump_g6(n_proposals=800, seed=106, cid=4):
+    info, mean, cov = info_g6()
+    out = {}
+    for normalized in (False, True):
+        info["likelihood"]["gaussian"]["normalized"] = normalized
+        model, sampler, x0, rows = run_reference(info, n_proposals, seed, cid)
+        tag = "norm" if normalized else "raw"
+        out[f"rows_{tag}"] = rows
+        out[f"final_x_{tag}"] = sampler.current_point.values.copy()
+        out[f"final_weight_{tag}"] = sampler.current_point.weight
+        out["x0"] = x0
+    out.update(columns=np.array(list(sampler.collection.columns)),
+               sampled=np.array(list(model.parameterization.sampled_params())),
+               likes=np.array(list(model.likelihood)),
+               mean=mean, cov=cov, proposal_cov=sampler.proposer.get_covariance(),
+               n_proposals=n_proposals, seed=seed, chain_id=cid,
+               max_tries=sampler.max_tries.value)
+    np.savez_compressed(os.path.join(GOLDEN, "g6_gaussian_one.npz"), **out)
+    print("g6_gaussian_one", out["rows_raw"].shape, out["rows_norm"].shape)
 
 
 def dump_units():
@@ -391,9 +501,23 @@ if __name__ == "__main__":
     import logging
 
     logging.disable(logging.WARNING)
-    dump_units()
-    dump_case("g1_gauss3d", info_g1, 1500, seed=101, chain_ids=[0, 7])
-    dump_case("g2_blocks_mixture", info_g2, 1500, seed=102, chain_ids=[3])
-    dump_case("g3_dragging", info_g3, 400, seed=103, chain_ids=[1])
-    dump_case("g4_block1d", info_g4, 1200, seed=104, chain_ids=[5])
-    dump_checkpoint()
+    only = set(sys.argv[1:])  # optional: names of the fixtures to (re)generate
+
+    def want(name):
+        return not only or name in only
+
+    if want("units"):
+        dump_units()
+    for name, fn, n, seed, cids in [
+        ("g1_gauss3d", info_g1, 1500, 101, [0, 7]),
+        ("g2_blocks_mixture", info_g2, 1500, 102, [3]),
+        ("g3_dragging", info_g3, 400, 103, [1]),
+        ("g4_block1d", info_g4, 1200, 104, [5]),
+        ("g5_scipy_priors", info_g5, 1500, 105, [2]),
+    ]:
+        if want(name):
+            dump_case(name, fn, n, seed=seed, chain_ids=cids)
+    if want("g6_gaussian_one"):
+        dump_g6()
+    if want("checkpoint"):
+        dump_checkpoint()

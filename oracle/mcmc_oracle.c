@@ -188,6 +188,46 @@ int32_t orc_row_width(const orc_model *m) {
     return 2 + m->D + orc_n_derived(m) + 2 + 1 + m->n_like; /* collection.py:154-159 */
 }
 
+/* log(Phi(b) - Phi(a)) for a < b (scipy.stats truncnorm's normalisation, restated from
+ * the published definition: the standard normal mass of [a, b], taken on the tail
+ * side where the subtraction does not cancel). */
+static double std_norm_cdf(double x) { return 0.5 * erfc(-x / sqrt(2.0)); }
+static double log_gauss_mass(double a, double b) {
+    if (b <= 0) return log(std_norm_cdf(b) - std_norm_cdf(a));
+    if (a >= 0) return log(std_norm_cdf(-a) - std_norm_cdf(-b));
+    return log1p(-std_norm_cdf(a) - std_norm_cdf(-b));
+}
+
+/* scipy.stats <dist>(loc, scale, a, b).logpdf(x) for the distributions of
+ * ORC_PRIOR_*: rv_continuous.logpdf = _logpdf((x-loc)/scale, shapes) - log(scale).
+ * Called inside the support only (bounds are checked first, prior.py:752). */
+static double scipy_logpdf_1d(int kind, double x, double loc, double scale, double a, double b) {
+    double z = (x - loc) / scale, ls = log(scale);
+    switch (kind) {
+        case ORC_PRIOR_TRUNCNORM: return -z * z / 2 - LOG_2PI / 2 - log_gauss_mass(a, b) - ls;
+        case ORC_PRIOR_HALFNORM: return 0.5 * log(2.0 / M_PI) - z * z / 2 - ls;
+        case ORC_PRIOR_EXPON: return -z - ls;
+        case ORC_PRIOR_BETA: {
+            double v = -(lgamma(a) + lgamma(b) - lgamma(a + b));
+            if (a != 1.0) v += (a - 1.0) * log(z);
+            if (b != 1.0) v += (b - 1.0) * log1p(-z);
+            return v - ls;
+        }
+        case ORC_PRIOR_GAMMA: return (a != 1.0 ? (a - 1.0) * log(z) : 0.0) - z - lgamma(a) - ls;
+        case ORC_PRIOR_LOGNORM: {
+            if (!(z > 0)) return -INFINITY;
+            double l = log(z);
+            return -l * l / (2 * a * a) - log(a * z * sqrt(2 * M_PI)) - ls;
+        }
+        case ORC_PRIOR_CAUCHY: return -log(M_PI) - log1p(z * z) - ls;
+        case ORC_PRIOR_LAPLACE: return log(0.5) - fabs(z) - ls;
+        case ORC_PRIOR_LOGUNIFORM:
+            if (!(z > 0)) return -INFINITY;
+            return -log(z) - log(log(b) - log(a)) - ls;
+        default: return 0.0;
+    }
+}
+
 /* Prior.logps_internal (prior.py:733-763) with _fast_norm_logpdf (tools.py:720-729) */
 static double logprior_internal(const orc_model *m, const double *x) {
     for (int i = 0; i < m->D; ++i)
@@ -198,6 +238,9 @@ static double logprior_internal(const orc_model *m, const double *x) {
             double m_log_scale = -log(m->pscale[i]) - LOG_2PI / 2;
             double z = (x[i] - m->loc[i]) / m->pscale[i];
             s += m_log_scale - z * z / 2;
+        } else if (m->prior_kind[i] >= 2) {
+            s += scipy_logpdf_1d(m->prior_kind[i], x[i], m->loc[i], m->pscale[i],
+                                 m->pa ? m->pa[i] : 0.0, m->pb ? m->pb[i] : 0.0);
         }
     }
     return m->uniform_logp + s;
@@ -269,6 +312,8 @@ double orc_logpost(const orc_model *m, const double *x, double *logprior,
         if (L->kind == ORC_LIKE_GAUSSIAN_MIXTURE) {
             v = like_gaussian_mixture(L, x, derived ? derived + doff : NULL);
             if (L->derived) doff += L->dim * L->n_modes;
+        } else if (L->kind == ORC_LIKE_CONSTANT) {
+            v = L->scale; /* one.logp_one (likelihoods/one/one.py:26-28) */
         } else {
             v = like_rosenbrock(L, x);
         }

@@ -33,6 +33,7 @@ extern "C" {
 /* likelihood component kinds */
 #define ORC_LIKE_GAUSSIAN_MIXTURE 0
 #define ORC_LIKE_ROSENBROCK 1
+#define ORC_LIKE_CONSTANT 2 /* likelihoods/one/one.py:26-28: logp = scale (0 for `one`) */
 
 typedef struct {
     int32_t kind;      /* ORC_LIKE_* */
@@ -47,14 +48,23 @@ typedef struct {
     double scale;         /* rosenbrock: logp = -scale * sum(...) */
 } orc_like;
 
+/* scipy.stats distributions reached through pdf.logpdf (cobaya/prior.py:520-525);
+ * numbering shared with include/cobaya_b200.h */
+enum { ORC_PRIOR_UNIFORM = 0, ORC_PRIOR_NORMAL = 1, ORC_PRIOR_TRUNCNORM = 2,
+       ORC_PRIOR_HALFNORM = 3, ORC_PRIOR_EXPON = 4, ORC_PRIOR_BETA = 5, ORC_PRIOR_GAMMA = 6,
+       ORC_PRIOR_LOGNORM = 7, ORC_PRIOR_CAUCHY = 8, ORC_PRIOR_LAPLACE = 9,
+       ORC_PRIOR_LOGUNIFORM = 10 };
+
 typedef struct {
     int32_t D;
     /* prior (cobaya/prior.py:514-533,733-763) */
-    const int32_t *prior_kind; /* [D] 0 uniform, 1 normal */
+    const int32_t *prior_kind; /* [D] 0 uniform, 1 normal, 2.. scipy.stats kinds (ORC_PRIOR_*) */
     const double *lower;       /* [D] */
     const double *upper;       /* [D] */
-    const double *loc;         /* [D] normal only */
-    const double *pscale;      /* [D] normal only */
+    const double *loc;         /* [D] non-uniform kinds */
+    const double *pscale;      /* [D] non-uniform kinds */
+    const double *pa;          /* [D] scipy shape parameter a (kinds >= 2), may be NULL */
+    const double *pb;          /* [D] scipy shape parameter b (kinds >= 2), may be NULL */
     const int32_t *periodic;   /* [D] 0/1 */
     double uniform_logp;       /* -sum(log(upper-lower)) over uniform params */
     /* likelihoods */

@@ -43,7 +43,8 @@ class _Model(C.Structure):
     _fields_ = [
         ("D", C.c_int32),
         ("prior_kind", C.c_void_p), ("lower", C.c_void_p), ("upper", C.c_void_p),
-        ("loc", C.c_void_p), ("pscale", C.c_void_p), ("periodic", C.c_void_p),
+        ("loc", C.c_void_p), ("pscale", C.c_void_p), ("pa", C.c_void_p), ("pb", C.c_void_p),
+        ("periodic", C.c_void_p),
         ("uniform_logp", C.c_double),
         ("n_like", C.c_int32), ("likes", C.c_void_p),
         ("n_blocks", C.c_int32),
@@ -111,6 +112,7 @@ class OracleModel:
         m.prior_kind = _p(k(fm.prior_kind, np.int32))
         m.lower = _p(k(fm.lower)); m.upper = _p(k(fm.upper))
         m.loc = _p(k(fm.loc)); m.pscale = _p(k(fm.pscale))
+        m.pa = _p(k(fm.pa)); m.pb = _p(k(fm.pb))
         m.periodic = _p(k(fm.periodic, np.int32))
         m.uniform_logp = fm.uniform_logp
         likes = (_Like * max(1, fm.n_like))()

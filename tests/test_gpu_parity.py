@@ -8,7 +8,7 @@ device/host libm differences); integer quantities (weights, row counts) exact.
 import numpy as np
 import pytest
 
-from tests.util import flat_from_golden, load_golden
+from tests.util import flat_from_golden, flat_g6, load_golden
 
 pytestmark = pytest.mark.gpu
 
@@ -420,6 +420,56 @@ def test_producer_consumer_kernel_blocks_normal_prior_thinning(cuda_lib):
         np.testing.assert_allclose(rows, rows_ref, rtol=RTOL, atol=ATOL)
         np.testing.assert_allclose(st["x"][c], s_ref["x"], rtol=RTOL, atol=ATOL)
         assert st["weight"][c] == s_ref["weight"]
+
+
+@pytest.mark.parametrize("policy", [0, 1])
+def test_scipy_priors_match_reference(cuda_lib, policy):
+    """All recognised scipy.stats 1-D priors (prior.py:520-525): cb2_logpost against
+    Model.logposterior of the reference at 400 points, and one chain against the rows the
+    reference produced (g5), on the DMMA step kernel (policy 0) and the general one (1)."""
+    g = load_golden("g5_scipy_priors")
+    fm = flat_from_golden(g)
+    cid, n = 2, int(g["n_proposals"])
+    eng = _engine(fm, 1, seed=int(g["seed"]), chain_id0=cid, burn_in=int(g["burn_in"]))
+    eng.set_kernel_policy(policy)
+    lp, pr, ll, _ = eng.logpost(g["kat_x"])
+    ok = np.isfinite(g["kat_logprior"])
+    assert 20 < (~ok).sum() < 380
+    assert np.all(pr[~ok] == -np.inf) and np.all(lp[~ok] == -np.inf)
+    np.testing.assert_allclose(pr[ok], g["kat_logprior"][ok], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(ll[ok, 0], g["kat_loglike"][ok], rtol=1e-10)
+    eng.set_state(g[f"x0_{cid}"][None, :])
+    done = 0
+    for k in (3, 64, 500, n):
+        step = min(k, n - done)
+        eng.advance(step)
+        done += step
+    assert eng.last_step_kernel() == (1 if policy == 0 else 0)
+    st = eng.get_state()
+    ref, rows = g[f"rows_{cid}"], eng.rows(0)
+    assert st["flags"][0] == 0 and rows.shape == ref.shape
+    np.testing.assert_array_equal(rows[:, 0], ref[:, 0])
+    np.testing.assert_allclose(rows, ref, rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(st["x"][0], g[f"final_x_{cid}"], rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("normalized", [False, True])
+def test_gaussian_and_one_likelihoods_match_reference(cuda_lib, normalized):
+    """``gaussian`` + ``one`` likelihoods (g6): engine rows vs the reference's."""
+    g = load_golden("g6_gaussian_one")
+    fm = flat_g6(g, normalized)
+    tag = "norm" if normalized else "raw"
+    n = int(g["n_proposals"])
+    eng = _engine(fm, 1, seed=int(g["seed"]), chain_id0=int(g["chain_id"]))
+    eng.set_state(g["x0"][None, :])
+    eng.advance(7)
+    eng.advance(n - 7)
+    ref, rows = g[f"rows_{tag}"], eng.rows(0)
+    assert rows.shape == ref.shape
+    np.testing.assert_array_equal(rows[:, 0], ref[:, 0])
+    np.testing.assert_allclose(rows, ref, rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(eng.get_state()["x"][0], g[f"final_x_{tag}"], rtol=RTOL,
+                               atol=ATOL)
 
 
 def test_confidence_bounds_match_numpy(cuda_lib):

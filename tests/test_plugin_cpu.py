@@ -89,6 +89,58 @@ def test_lowered_model_evaluates_like_reference_logposterior():
             assert v == -np.inf and len(r.loglikes) == 0
 
 
+@pytest.mark.parametrize("case", ["g5", "g6"])
+def test_lowering_of_scipy_priors_and_more_likelihoods(case):
+    """the scipy.stats 1-D priors and the ``gaussian`` / ``one``
+    likelihoods are lowered from the live reference objects; the lowered model (through
+    the C oracle) evaluates like Model.logposterior."""
+    from oracle import oracle as orc
+
+    enable_reference()
+    from oracle import make_golden as mg
+
+    info = (mg.info_g5 if case == "g5" else mg.info_g6)()[0]
+    ref_model, ref, model, mine = _pair(info)
+    fm = mine._fm
+    if case == "g5":
+        assert sorted(set(int(k) for k in fm.prior_kind)) == list(range(11))
+    else:
+        assert [lk.name for lk in fm.likes] == ["gaussian", "one"]
+        assert fm.columns()[-2:] == ["chi2__gaussian", "chi2__one"]
+    om = orc.OracleModel(fm)
+    rng = np.random.default_rng(1)
+    center = np.array([model.prior.reference(random_state=rng) for _ in range(1)])[0]
+    n_in = 0
+    for _ in range(60):
+        p = center + 0.3 * rng.standard_normal(len(center))
+        r = model.logposterior(p)
+        v, lp, ll, der = om.logpost(p)
+        if np.isfinite(r.logpost):
+            n_in += 1
+            np.testing.assert_allclose(lp, r.logprior, rtol=1e-12, atol=1e-12)
+            np.testing.assert_allclose(ll, r.loglikes, rtol=1e-10, atol=1e-12)
+            np.testing.assert_allclose(v, r.logpost, rtol=1e-10)
+        else:
+            assert v == -np.inf
+    assert n_in > 5
+
+
+def test_unsupported_prior_is_refused():
+    enable_reference()
+    from cobaya.log import LoggedError
+    from cobaya.model import get_model
+    from cobaya.sampler import get_sampler
+
+    from oracle import make_golden as mg
+
+    info = mg.info_g6()[0]
+    info["params"]["q1"]["prior"] = {"dist": "weibull_min", "c": 1.5, "loc": -1, "scale": 1}
+    info["sampler"] = {"cobaya_b200.plugin.MCMC": dict(info["sampler"]["mcmc"],
+                                                       chains_per_gpu=2)}
+    with pytest.raises(LoggedError, match="recognised set"):
+        get_sampler(info["sampler"], get_model(info))
+
+
 def test_unknown_option_is_rejected_and_engine_keys_are_accepted():
     enable_reference()
     from cobaya.input import update_info

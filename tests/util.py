@@ -12,7 +12,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
-from cobaya_b200.flatmodel import FlatModel, LikeSpec  # noqa: E402
+from cobaya_b200.flatmodel import PRIOR_KINDS, FlatModel, LikeSpec  # noqa: E402
 
 
 def load_golden(name):
@@ -24,8 +24,9 @@ def flat_from_golden(g) -> FlatModel:
     in the fixture (prior dist names/bounds, mixture means/covs/weights, blocking)."""
     names = [str(s) for s in g["sampled"]]
     D = len(names)
-    kind = np.array([0 if str(d) == "uniform" else 1 for d in g["prior_dist"]], np.int32)
-    assert all(str(d) in ("uniform", "norm") for d in g["prior_dist"])
+    kind = np.array([PRIOR_KINDS[str(d)] for d in g["prior_dist"]], np.int32)
+    pa = g["prior_a"] if "prior_a" in g.files else np.zeros(D)
+    pb = g["prior_b"] if "prior_b" in g.files else np.zeros(D)
     idx = [names.index(str(p)) for p in g["like_input_params"]]
     w = np.asarray(g["like_weights"])
     means = np.atleast_2d(g["means"])
@@ -43,7 +44,8 @@ def flat_from_golden(g) -> FlatModel:
         p += int(n)
     return FlatModel(
         names=names, prior_kind=kind, lower=g["lower"], upper=g["upper"],
-        loc=g["prior_loc"], pscale=g["prior_scale"], periodic=g["periodic"].astype(np.int32),
+        loc=g["prior_loc"], pscale=g["prior_scale"], pa=pa, pb=pb,
+        periodic=g["periodic"].astype(np.int32),
         likes=[lk], blocks=blocks, oversampling=[int(o) for o in g["oversampling"]],
         drag=bool(g["drag"]), i_last_slow_block=int(g["i_last_slow_block"]),
         drag_interp_steps=int(g["drag_interp_steps"]),
@@ -51,3 +53,20 @@ def flat_from_golden(g) -> FlatModel:
         temperature=float(g["temperature"]), max_tries=int(g["max_tries"]),
         output_thin=int(g["output_thin"]),
     )
+
+
+def flat_g6(g, normalized: bool) -> FlatModel:
+    """The g6 fixture: ``gaussian`` (normalized or not) + ``one`` likelihoods, uniform
+    priors on [-1, 1] except a normal prior on q2 (oracle/make_golden.py info_g6)."""
+    names = [str(s) for s in g["sampled"]]
+    D = len(names)
+    kind = np.zeros(D, np.int32); kind[2] = 1
+    lower, upper = np.full(D, -1.0), np.full(D, 1.0)
+    lower[2], upper[2] = -np.inf, np.inf
+    sc = np.ones(D); sc[2] = 0.5
+    likes = [LikeSpec.gaussian(np.arange(D), g["mean"], g["cov"], normalized=normalized,
+                               name="gaussian"), LikeSpec.constant(0.0, name="one")]
+    assert [str(n) for n in g["likes"]] == ["gaussian", "one"]
+    return FlatModel(names=names, prior_kind=kind, lower=lower, upper=upper, loc=np.zeros(D),
+                     pscale=sc, periodic=np.zeros(D, np.int32), likes=likes,
+                     proposal_cov=np.asarray(g["proposal_cov"]), max_tries=int(g["max_tries"]))
