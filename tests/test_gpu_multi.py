@@ -46,6 +46,14 @@ WORKER = textwrap.dedent("""
 """)
 
 
+def _free_port():
+    import socket
+
+    with socket.socket() as so:
+        so.bind(("127.0.0.1", 0))
+        return so.getsockname()[1]
+
+
 def test_two_gpus_equal_one_engine_with_all_chains(tmp_path):
     import torch
 
@@ -56,7 +64,7 @@ def test_two_gpus_equal_one_engine_with_all_chains(tmp_path):
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", PYTHONPATH=ROOT)
     p = subprocess.run(
         [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-         "--master-addr", "127.0.0.1", "--master-port", "29631", str(script)],
+         "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), str(script)],
         capture_output=True, text=True, env=env, timeout=600)
     assert p.returncode == 0, p.stderr[-3000:]
     res = [json.load(open(tmp_path / f"rank{r}.json")) for r in range(2)]

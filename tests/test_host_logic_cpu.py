@@ -13,6 +13,14 @@ import pytest
 from tests.util import ROOT
 
 
+def _free_port():
+    import socket
+
+    with socket.socket() as so:
+        so.bind(("127.0.0.1", 0))
+        return so.getsockname()[1]
+
+
 def test_number_with_units():
     from cobaya_b200.mcmc import NumberWithUnits
 
@@ -131,7 +139,7 @@ def test_world_size_2_gloo_allreduce_gives_identical_verdict_on_every_rank(tmp_p
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", PYTHONPATH=ROOT)
     p = subprocess.run(
         [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-         "--master-addr", "127.0.0.1", "--master-port", "29591", str(script)],
+         "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), str(script)],
         capture_output=True, text=True, env=env, timeout=300)
     assert p.returncode == 0, p.stderr[-2000:]
     import json
