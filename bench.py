@@ -223,13 +223,13 @@ def run_reference_arm(args):
                                                 f"wall {wall:.0f}s"},
                         e2e={"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
                              "d2h_bytes_per_step": 0})
-            print(json.dumps(base))
+            emit(base)
             return
     cb = cpu_oracle_baseline(fm, cov, target_seconds=max(5.0, 2.0 * steps))
     base.update(value=cb["value"], ms_per_step=None, cpu_baseline=cb,
                 e2e={"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
                      "d2h_bytes_per_step": 0})
-    print(json.dumps(base))
+    emit(base)
 
 
 # ------------------------------------------------------------------ GPU arm
@@ -398,10 +398,31 @@ def run_gpu_arm(args):
         "cpu_baseline": cb,
         "wall_s_timed_region": t_wall,
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Libraries (NCCL's version banner, torch warnings) write to file descriptor 1 from
+    native code: point fd 1 at stderr for the whole run and keep the original for the one
+    JSON line the driver parses."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
 
 
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

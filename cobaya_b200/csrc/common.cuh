@@ -212,6 +212,39 @@ __device__ __forceinline__ void sincos2pi_from_bits(uint64_t k, double &s, doubl
     }
 }
 
+// ---- table-driven natural logarithm for the Box-Muller radius of the basis kernels ----
+// u = m 2^e with m in [0.75, 1.5); c_j = 0.75 + j/128 the table point nearest to m
+// (j = 0..96, c_32 = 1 exactly); log u = e ln2 + log c_j + log1p((m - c_j)/c_j), the last
+// term a degree-7 series in |r| <= 1/192 (truncation < 1e-19).  m - c_j is exact, so the
+// result keeps full relative accuracy near u = 1; max error about 1 ulp.  Everything stays
+// on the FMA pipe: exponent and index come from the bit pattern (no I2F/F2I).
+#define CB2_LOGTAB_N 97
+#define CB2_LOGTAB_DOUBLES (3 * CB2_LOGTAB_N)
+__device__ double g_logtab[CB2_LOGTAB_DOUBLES];  // [j] = {c_j, 1/c_j, log c_j}; cb2_create fills it
+
+__device__ __forceinline__ double log_tab(double u, const double *tab) {
+    const uint64_t b = (uint64_t)__double_as_longlong(u);
+    const uint64_t mant = b & 0x000FFFFFFFFFFFFFull;
+    const int hi = (int)(mant >> 51);                         // mantissa >= 1.5: use m/2, e+1
+    const int ex = (int)(b >> 52) - 1023 + hi;
+    const double m = __longlong_as_double((long long)(mant | ((uint64_t)(0x3FF - hi) << 52)));
+    const int j = hi ? (int)((mant + (1ull << 45)) >> 46) - 32
+                     : 32 + (int)((mant + (1ull << 44)) >> 45);
+    const double *t = tab + 3 * j;
+    const double r = (m - t[0]) * t[1];
+    double p = 1.0 / 7.0;
+    p = fma(p, r, -1.0 / 6.0);
+    p = fma(p, r, 0.2);
+    p = fma(p, r, -0.25);
+    p = fma(p, r, 1.0 / 3.0);
+    p = fma(p, r, -0.5);
+    const double l1p = fma(r * r, p, r);
+    const double ed = __longlong_as_double((long long)(0x4330000000000000ull +
+                                                       (uint64_t)(ex + 2048))) -
+                      (4503599627370496.0 + 2048.0);
+    return fma(ed, 0.6931471805599453, t[2] + l1p);
+}
+
 // pair p of the standard normals consumed by random_SO_N (functions.py:36)
 __device__ __forceinline__ void draw_normal_pair(uint32_t k0, uint32_t k1, uint64_t gid,
                                                  int block, uint32_t epoch, uint32_t p,
@@ -221,6 +254,21 @@ __device__ __forceinline__ void draw_normal_pair(uint32_t k0, uint32_t k1, uint6
     const double u1 = u52(w.x, w.y);
     const uint64_t k2 = ((uint64_t)(w.z >> 6) << 26) | (uint64_t)(w.w >> 6);
     const double rad = sqrt(-2.0 * log(u1));
+    double s, c;
+    sincos2pi_from_bits(k2, s, c);
+    z0 = rad * c;
+    z1 = rad * s;
+}
+
+// same pair with the radius logarithm from the shared-memory copy of g_logtab
+__device__ __forceinline__ void draw_normal_pair_tab(uint32_t k0, uint32_t k1, uint64_t gid,
+                                                     int block, uint32_t epoch, uint32_t p,
+                                                     const double *tab, double &z0, double &z1) {
+    u32x4 w = philox4x32_10(k0, k1, p, epoch, (uint32_t)gid,
+                            CB2_TAG_BASIS | ((uint32_t)block << 8));
+    const double u1 = u52(w.x, w.y);
+    const uint64_t k2 = ((uint64_t)(w.z >> 6) << 26) | (uint64_t)(w.w >> 6);
+    const double rad = sqrt(-2.0 * log_tab(u1, tab));
     double s, c;
     sincos2pi_from_bits(k2, s, c);
     z0 = rad * c;

@@ -201,6 +201,20 @@ extern "C" int cb2_create(int device, int64_t n_chains, int32_t D, uint64_t seed
         delete h;
         return -2;
     }
+    {  // logarithm table of the basis kernels (common.cuh log_tab), once per engine/device
+        double tab[CB2_LOGTAB_DOUBLES];
+        for (int j = 0; j < CB2_LOGTAB_N; ++j) {
+            const long double c = 0.75L + (long double)j / 128.0L;
+            tab[3 * j] = (double)c;
+            tab[3 * j + 1] = (double)(1.0L / c);
+            tab[3 * j + 2] = (j == 32) ? 0.0 : (double)logl(c);
+        }
+        if (cudaMemcpyToSymbol(g_logtab, tab, sizeof(tab)) != cudaSuccess) {
+            g_create_error = "cb2_create: could not upload the logarithm table";
+            delete h;
+            return -2;
+        }
+    }
     // default blocking: one block with every parameter
     h->n_blocks = 1;
     h->bsize[0] = D;

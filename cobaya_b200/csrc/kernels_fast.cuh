@@ -149,7 +149,7 @@ k_basis_fast(uint32_t key0, uint32_t key1, uint64_t chain_id0, int block, int n,
 // k_basis_wy<NG>: the same Haar basis with the Householder sweep on the FP64 TENSOR pipe.
 // Reflectors are grouped 8 at a time in compact-WY form (LAPACK dlarft, forward/columnwise):
 //   G_{m0} ... G_{m0+7} = I - V T V^T,  V = [x_{m0} .. x_{m0+7}],  T upper triangular,
-//   T_jj = 1,  T[0:j, j] = -T[0:j,0:j] (V[:,0:j]^T v_j)        (|x_m|^2 = 2  =>  tau = 1)
+//   T_jj = tau_j = 2/|x_j|^2,  T[0:j, j] = -tau_j T[0:j,0:j] (V[:,0:j]^T v_j)
 // and H <- H - ((H V) T) V^T is three small matrix products per group, issued as m8n8k4 DMMA
 // tiles.  4 warps per basis, warp w owns rows 16w..16w+15 of H in C-fragment layout (lane
 // (q,r): H[row q][cols 8nt+2r, +1]); with the even/odd k interleave a C fragment is directly
@@ -168,13 +168,16 @@ k_basis_wy(uint32_t key0, uint32_t key1, uint64_t chain_id0, int block, int n,
     double *inv = Dv + NP;              // [NP]
     double *Sg = inv + NP;              // [NG][8][8] Gram (strict upper) per group
     double *Tg = Sg + NG * 64;          // [NG][8][8] T per group
+    __shared__ int sign_cnt[4];
     const int tid = threadIdx.x, nt_ = blockDim.x;
     const int64_t task = task0 + blockIdx.x;
     const int64_t chain = task / cnt;
     const uint32_t e0 = vis ? (uint32_t)(vis[chain * vis_stride + block] / n) : e0_fixed;
     const uint32_t epoch = e0 + (uint32_t)(task % cnt);
     const uint64_t gid = chain_id0 + (uint64_t)chain;
-    for (int e = tid; e < NP * LDX; e += nt_) X[e] = 0.0;
+    for (int e = tid; e < NP * LDX + 2 * NP; e += nt_) X[e] = 0.0;  // X, Dv, inv (= tau)
+    double *ltab = Sg;  // the logarithm table lives in the (not yet used) Gram/T area
+    for (int e = tid; e < CB2_LOGTAB_DOUBLES; e += nt_) ltab[e] = g_logtab[e];
     __syncthreads();
     const int nn = (n + 2) * (n - 1) / 2;
     {
@@ -187,7 +190,8 @@ k_basis_wy(uint32_t key0, uint32_t key1, uint64_t chain_id0, int block, int n,
         for (int u = 0; u < PPT; ++u) {
             const int p = tid + u * 128;
             if (2 * p < nn)
-                draw_normal_pair(key0, key1, gid, block, epoch, (uint32_t)p, z[u][0], z[u][1]);
+                draw_normal_pair_tab(key0, key1, gid, block, epoch, (uint32_t)p, ltab,
+                                     z[u][0], z[u][1]);
         }
         int m = 0, base = 0;  // base = ix(m); q only grows
 #pragma unroll
@@ -224,23 +228,27 @@ k_basis_wy(uint32_t key0, uint32_t key1, uint64_t chain_id0, int block, int n,
             part = s0 + s1;
         }
         const double norm2 = part + __shfl_xor_sync(0xffffffffu, part, 1);
+        bool negative = false;
         if (m < n - 1 && half == 0) {
             const double x0 = X[m * LDX + m];
             const double d = (x0 != 0.0) ? (x0 > 0 ? 1.0 : -1.0) : 1.0;
             const double x0n = x0 + d * sqrt(norm2);
             X[m * LDX + m] = x0n;
-            inv[m] = 1.0 / sqrt((norm2 - x0 * x0 + x0n * x0n) / 2.0);
+            // the reference normalises x to |x|^2 = 2 (functions.py:54-55); here x stays as
+            // it is and tau_m = 2 / |x|^2 enters through T (dlarft with general tau)
+            inv[m] = 2.0 / (norm2 - x0 * x0 + x0n * x0n);
             Dv[m] = d;
+            negative = d < 0.0;
         }
+        // functions.py:59: D[n-1] = (-1)^(n-1) prod(D[:-1]) -- a parity count
+        const unsigned negs = __ballot_sync(0xffffffffu, negative);
+        if ((tid & 31) == 0) sign_cnt[tid >> 5] = __popc(negs);
     }
     __syncthreads();
-    for (int e = tid; e < (n - 1) * LDX; e += nt_) X[e] *= inv[e / LDX];  // x /= sc
-    if (tid == 0) {  // functions.py:59
-        double prod = 1.0;
-        for (int m = 0; m < n - 1; ++m) prod *= Dv[m];
-        Dv[n - 1] = (((n - 1) & 1) ? -1.0 : 1.0) * prod;
+    if (tid == 0) {
+        const int c = sign_cnt[0] + sign_cnt[1] + sign_cnt[2] + sign_cnt[3] + (n - 1);
+        Dv[n - 1] = (c & 1) ? -1.0 : 1.0;  // read after the next block-wide barrier
     }
-    __syncthreads();
     const int lane = tid & 31, w = tid >> 5, q = lane >> 2, r = lane & 3;
     // Gram S_g = V_g^T V_g of every group on the tensor pipe (A and B fragments coincide:
     // lane (q,r) holds x_{8g+q}[k = r]), then row i of T (dlarft) by lane i
@@ -260,15 +268,16 @@ k_basis_wy(uint32_t key0, uint32_t key1, uint64_t chain_id0, int block, int n,
             const int i = lane;
             double *T = Tg + g * 64;
             double trow[8];
+            const double *tau = inv + 8 * g;  // 0 for the padding reflectors (m >= n-1)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) trow[j] = (j == i) ? 1.0 : 0.0;
+            for (int j = 0; j < 8; ++j) trow[j] = (j == i) ? tau[i] : 0.0;
 #pragma unroll
             for (int j = 1; j < 8; ++j) {
                 double acc = 0.0;
 #pragma unroll
                 for (int l = 0; l < 8; ++l)
                     if (l >= i && l < j) acc = fma(trow[l], S[l * 8 + j], acc);
-                if (i < j) trow[j] = -acc;
+                if (i < j) trow[j] = -tau[j] * acc;
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) T[i * 8 + j] = trow[j];
@@ -341,13 +350,23 @@ k_basis_wy(uint32_t key0, uint32_t key1, uint64_t chain_id0, int block, int n,
             if (sl >= nslot) break;
             const int c = 8 * (sl ? t1 : t0) + q;
             if (c < n) {
+                if ((n & 1) == 0) {  // 16-byte stores: i even, rows of n doubles stay aligned
 #pragma unroll
-                for (int nt = 0; nt < NG; ++nt)
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int i = 8 * nt + 2 * r + h;
-                        if (i < n) out[(size_t)c * n + i] = Dv[i] * nreg[sl][nt][h];
+                    for (int nt = 0; nt < NG; ++nt) {
+                        const int i = 8 * nt + 2 * r;
+                        if (i < n)
+                            *reinterpret_cast<double2 *>(out + (size_t)c * n + i) =
+                                make_double2(Dv[i] * nreg[sl][nt][0], Dv[i + 1] * nreg[sl][nt][1]);
                     }
+                } else {
+#pragma unroll
+                    for (int nt = 0; nt < NG; ++nt)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int i = 8 * nt + 2 * r + h;
+                            if (i < n) out[(size_t)c * n + i] = Dv[i] * nreg[sl][nt][h];
+                        }
+                }
             }
         }
     }
@@ -362,7 +381,8 @@ static int launch_basis_fast_t(cudaStream_t st, uint32_t k0, uint32_t k1, uint64
                                int64_t task0, int64_t store_task0) {
     constexpr int NP = NG * 8;
     if (g_basis_wy) {
-        const size_t smem_wy = (size_t)(NP * (NP + 1) + 2 * NP + 2 * NG * 64) * sizeof(double);
+        const int gram_t = 2 * NG * 64 > CB2_LOGTAB_DOUBLES ? 2 * NG * 64 : CB2_LOGTAB_DOUBLES;
+        const size_t smem_wy = (size_t)(NP * (NP + 1) + 2 * NP + gram_t) * sizeof(double);
         cudaError_t e2 = cudaFuncSetAttribute(k_basis_wy<NG>,
                                               cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               (int)smem_wy);
