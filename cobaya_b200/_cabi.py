@@ -21,7 +21,8 @@ EXPORTS = [
     "cb2_set_prior_shapes",
     "cb2_clear_likelihoods", "cb2_add_gaussian_mixture", "cb2_add_rosenbrock", "cb2_add_constant",
     "cb2_set_blocking", "cb2_set_proposal", "cb2_set_options", "cb2_set_state",
-    "cb2_get_state", "cb2_logpost", "cb2_advance", "cb2_sync", "cb2_summary",
+    "cb2_get_state", "cb2_snapshot_size", "cb2_export_state", "cb2_import_state",
+    "cb2_load_rows", "cb2_logpost", "cb2_advance", "cb2_sync", "cb2_summary",
     "cb2_moments", "cb2_bounds", "cb2_copy_rows", "cb2_row_width", "cb2_n_derived", "cb2_debug_basis",
     "cb2_launch_count", "cb2_timer_start", "cb2_timer_stop", "cb2_last_step_kernel",
     "cb2_set_kernel_policy", "cb2_set_profiling", "cb2_kernel_times", "cb2_debug_message",
@@ -62,6 +63,11 @@ def load():
     L.cb2_set_prior.argtypes = [vp] + [vp] * 6 + [dbl]
     L.cb2_set_prior_shapes.argtypes = [vp, vp, vp, vp]
     L.cb2_clear_likelihoods.argtypes = [vp]
+    L.cb2_snapshot_size.restype = i64
+    L.cb2_snapshot_size.argtypes = [vp]
+    L.cb2_export_state.argtypes = [vp, vp, i64]
+    L.cb2_import_state.argtypes = [vp, vp, i64]
+    L.cb2_load_rows.argtypes = [vp, i64, i64, vp]
     L.cb2_add_gaussian_mixture.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, i32]
     L.cb2_add_rosenbrock.argtypes = [vp, i32, vp, dbl]
     L.cb2_add_constant.argtypes = [vp, dbl]

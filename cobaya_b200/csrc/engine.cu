@@ -631,12 +631,7 @@ static void fill_state_ptrs(cb2_engine *h) {
     S.vis = h->d_vis.p; S.flags = h->d_flags.p; S.rows = h->d_rows.p; S.cap = h->rows_cap;
 }
 
-extern "C" int cb2_set_state(cb2_engine *h, const double *x0) {
-    if (!h) return -1;
-    if (h->rows_cap < 1) FAIL(h, -1, "cb2_set_options must be called before cb2_set_state");
-    CK(h, cudaSetDevice(h->device));
-    int rc = build_model(h);
-    if (rc) return rc;
+static int alloc_state(cb2_engine *h) {
     const int64_t C = h->n_chains;
     const int D = h->D, NL = (int)h->likes.size(), ND = std::max(h->n_der, 1);
     CK(h, h->d_x.ensure((size_t)C * D)); CK(h, h->d_logpost.ensure(C));
@@ -652,6 +647,18 @@ extern "C" int cb2_set_state(cb2_engine *h, const double *x0) {
              nrows * 8.0 / 1e9, (long long)C, (long long)h->rows_cap, row_width(h),
              cudaGetErrorString(e));
     fill_state_ptrs(h);
+    return 0;
+}
+
+extern "C" int cb2_set_state(cb2_engine *h, const double *x0) {
+    if (!h) return -1;
+    if (h->rows_cap < 1) FAIL(h, -1, "cb2_set_options must be called before cb2_set_state");
+    CK(h, cudaSetDevice(h->device));
+    int rc = build_model(h);
+    if (rc) return rc;
+    const int64_t C = h->n_chains;
+    const int D = h->D;
+    if ((rc = alloc_state(h))) return rc;
     CK(h, cudaMemcpyAsync(h->d_x.p, x0, (size_t)C * D * sizeof(double), cudaMemcpyHostToDevice,
                           h->stream));
     StepSmem L = plan_step_smem(h);
@@ -686,6 +693,100 @@ extern "C" int cb2_get_state(cb2_engine *h, double *x, double *logpost, int64_t 
     if (n_rows) CK(h, cudaMemcpy(n_rows, h->d_n_rows.p, C * 8, cudaMemcpyDeviceToHost));
     if (n_accepted) CK(h, cudaMemcpy(n_accepted, h->d_n_acc.p, C * 8, cudaMemcpyDeviceToHost));
     if (flags) CK(h, cudaMemcpy(flags, h->d_flags.p, C * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// ---- snapshot: everything per-chain that the kernels carry from one proposal to the next.
+// Cycler tapes, Haar bases and draws are functions of (seed, chain id, counters) and are
+// regenerated, so a restored engine continues bit-for-bit.
+struct SnapHeader {
+    uint64_t magic;
+    int64_t version, C, D, n_blocks, NL, ND, width, steps_done;
+    uint64_t seed, chain_id0;
+};
+static const uint64_t CB2_SNAP_MAGIC = 0x0031504e53324243ull;  // "CB2SNP1"
+
+struct SnapSection { void *dev; size_t bytes; };
+static std::vector<SnapSection> snap_sections(cb2_engine *h) {
+    const size_t C = (size_t)h->n_chains, D = (size_t)h->D, NL = h->likes.size(),
+                 ND = (size_t)h->n_der, NV = (size_t)h->n_blocks + 1;
+    return {
+        {h->d_x.p, C * D * 8}, {h->d_logpost.p, C * 8}, {h->d_logprior.p, C * 8},
+        {h->d_ll.p, C * NL * 8}, {h->d_der.p, C * ND * 8}, {h->d_weight.p, C * 8},
+        {h->d_prior_rej.p, C * 8}, {h->d_burn_left.p, C * 8}, {h->d_added_w.p, C * 8},
+        {h->d_n_rows.p, C * 8}, {h->d_n_acc.p, C * 8}, {h->d_vis.p, C * NV * 8},
+        {h->d_flags.p, ((C * 4 + 7) / 8) * 8},
+    };
+}
+
+extern "C" int64_t cb2_snapshot_size(cb2_engine *h) {
+    if (!h) return -1;
+    size_t tot = sizeof(SnapHeader);
+    for (const auto &sec : snap_sections(h)) tot += sec.bytes;
+    return (int64_t)tot;
+}
+
+extern "C" int cb2_export_state(cb2_engine *h, void *buf, int64_t nbytes) {
+    if (!h || !h->have_state) return -1;
+    if (nbytes < cb2_snapshot_size(h)) FAIL(h, -1, "cb2_export_state: buffer too small");
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaStreamSynchronize(h->stream));
+    SnapHeader hd = {CB2_SNAP_MAGIC, 1, h->n_chains, h->D, h->n_blocks, (int64_t)h->likes.size(),
+                     h->n_der, row_width(h), h->steps_done, h->seed, h->chain_id0};
+    char *p = (char *)buf;
+    memcpy(p, &hd, sizeof(hd));
+    p += sizeof(hd);
+    for (const auto &sec : snap_sections(h)) {
+        const size_t real = (sec.dev == (void *)h->d_flags.p) ? (size_t)h->n_chains * 4 : sec.bytes;
+        if (real) CK(h, cudaMemcpy(p, sec.dev, real, cudaMemcpyDeviceToHost));
+        if (real < sec.bytes) memset(p + real, 0, sec.bytes - real);
+        p += sec.bytes;
+    }
+    return 0;
+}
+
+extern "C" int cb2_import_state(cb2_engine *h, const void *buf, int64_t nbytes) {
+    if (!h) return -1;
+    if (h->rows_cap < 1) FAIL(h, -1, "cb2_set_options must be called before cb2_import_state");
+    CK(h, cudaSetDevice(h->device));
+    int rc = build_model(h);
+    if (rc) return rc;
+    if (nbytes < (int64_t)sizeof(SnapHeader)) FAIL(h, -1, "cb2_import_state: truncated snapshot");
+    SnapHeader hd;
+    memcpy(&hd, buf, sizeof(hd));
+    if (hd.magic != CB2_SNAP_MAGIC || hd.version != 1)
+        FAIL(h, -1, "cb2_import_state: not a snapshot of this engine version");
+    if (hd.C != h->n_chains || hd.D != h->D || hd.n_blocks != h->n_blocks ||
+        hd.NL != (int64_t)h->likes.size() || hd.ND != h->n_der || hd.width != row_width(h))
+        FAIL(h, -1, "cb2_import_state: snapshot of a different model/blocking "
+                    "(chains %lld/%lld, D %lld/%d, blocks %lld/%d)",
+             (long long)hd.C, (long long)h->n_chains, (long long)hd.D, h->D,
+             (long long)hd.n_blocks, h->n_blocks);
+    if (hd.seed != h->seed || hd.chain_id0 != h->chain_id0)
+        FAIL(h, -1, "cb2_import_state: snapshot was taken with another seed / chain id range");
+    if ((rc = alloc_state(h))) return rc;
+    if (nbytes < cb2_snapshot_size(h)) FAIL(h, -1, "cb2_import_state: truncated snapshot");
+    const char *p = (const char *)buf + sizeof(hd);
+    for (const auto &sec : snap_sections(h)) {
+        const size_t real = (sec.dev == (void *)h->d_flags.p) ? (size_t)h->n_chains * 4 : sec.bytes;
+        if (real) CK(h, cudaMemcpy(sec.dev, p, real, cudaMemcpyHostToDevice));
+        p += sec.bytes;
+    }
+    h->steps_done = hd.steps_done;
+    h->have_state = true;
+    return 0;
+}
+
+extern "C" int cb2_load_rows(cb2_engine *h, int64_t chain, int64_t n, const double *rows) {
+    if (!h || !h->have_state) return -1;
+    if (chain < 0 || chain >= h->n_chains) FAIL(h, -1, "chain index out of range");
+    if (n < 0 || n > h->rows_cap) FAIL(h, -1, "cb2_load_rows: %lld rows exceed rows_cap %lld",
+                                       (long long)n, (long long)h->rows_cap);
+    CK(h, cudaSetDevice(h->device));
+    const int W = row_width(h);
+    if (n > 0)
+        CK(h, cudaMemcpyAsync(h->d_rows.p + (size_t)chain * h->rows_cap * W, rows,
+                              (size_t)n * W * 8, cudaMemcpyHostToDevice, h->stream));
     return 0;
 }
 

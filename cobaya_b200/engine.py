@@ -180,6 +180,32 @@ class Engine:
             raise EngineError(self.lib.cb2_last_error(self.h).decode())
         return out[:got].copy()
 
+    # ---- resuming ---------------------------------------------------------------------
+    def export_state(self) -> np.ndarray:
+        """Opaque per-chain sampler state (cb2_export_state) as a uint8 array."""
+        n = int(self.lib.cb2_snapshot_size(self.h))
+        if n < 0:
+            raise EngineError("cb2_snapshot_size failed")
+        buf = np.zeros(n, np.uint8)
+        self._ck(self.lib.cb2_export_state(self.h, _cabi.ptr(buf), n))
+        return buf
+
+    def import_state(self, blob, rows=None):
+        """Restore a snapshot taken from an identically configured engine; ``rows`` is the
+        list of per-chain row arrays (``self.rows(c)`` of the exporting engine)."""
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        self._ck(self.lib.cb2_import_state(self.h, _cabi.ptr(blob), blob.size))
+        if rows is not None:
+            if len(rows) != self.n_chains:
+                raise EngineError("import_state: one row array per chain is required")
+            keep = []
+            for c, r in enumerate(rows):
+                r = _f64(r)
+                keep.append(r)
+                self._ck(self.lib.cb2_load_rows(self.h, c, r.shape[0] if r.size else 0,
+                                                _cabi.ptr(r) if r.size else None))
+            self.sync()
+
     def debug_basis(self, chain, block, epoch):
         n = int(self.fm.block_sizes[block])
         R = np.empty((n, n))

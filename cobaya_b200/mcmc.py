@@ -170,7 +170,8 @@ class EnsembleMCMC:
     """M = world_size x chains_per_gpu lock-step chains of the adaptive Metropolis sampler."""
 
     def __init__(self, fm: FlatModel, x0: np.ndarray, options: dict | None = None,
-                 dist=None, engine: Engine | None = None, covmat_incomplete: bool = False):
+                 dist=None, engine: Engine | None = None, covmat_incomplete: bool = False,
+                 resume_from: dict | None = None):
         opts = dict(MCMC_DEFAULTS)
         opts.update(ENGINE_DEFAULTS)
         unknown = set(options or {}) - set(opts)
@@ -220,23 +221,101 @@ class EnsembleMCMC:
             import os
 
             device = int(os.environ.get("LOCAL_RANK", "0"))
+        snap = resume_from
+        if snap is not None:
+            self._check_snapshot(snap)
+            self.seed = int(snap["seed"])
+            fm.set_covariance(np.asarray(snap["proposal_cov"]))  # the learned proposal
+            need = int(np.max(snap["n_rows"])) + 2 * self.learn_every.value
+            if self.rows_per_chain < need and opts["rows_per_chain"] is None:
+                self.rows_per_chain = need + (int(self.max_samples)
+                                              if np.isfinite(self.max_samples) else
+                                              64 * self.learn_every.value)
         self.engine = engine or Engine(
             fm, n_chains=self.n_chains_local, seed=self.seed, device=int(device),
             chain_id0=self.dist.rank * self.n_chains_local, rows_cap=self.rows_per_chain,
             burn_in=int(self.burn_in.value))
-        self.engine.set_state(x0)
         self.converged = False
         self.Rminus1_last = np.inf
         self.i_learn = 1
         self.n_steps_raw = 0
         self.progress: list[Checkpoint] = []
+        if snap is None:
+            self.engine.set_state(x0)
+        else:
+            ends = np.cumsum(snap["n_rows"])
+            rows = np.split(np.asarray(snap["rows"]).reshape(-1, fm.row_width), ends[:-1])
+            self.engine.import_state(snap["blob"], rows)
+            self.Rminus1_last = float(snap["Rminus1_last"])
+            self.i_learn = int(snap["i_learn"])
+            self.n_steps_raw = int(snap["n_steps_raw"])
+            self.progress = [
+                Checkpoint(N=int(r[0]), timestamp=str(t), acceptance_rate=float(r[1]),
+                           Rminus1=None if np.isnan(r[2]) else float(r[2]),
+                           Rminus1_cl=None if np.isnan(r[3]) else float(r[3]),
+                           learned=bool(r[4]))
+                for r, t in zip(np.asarray(snap["progress"]).reshape(-1, 5),
+                                snap["progress_timestamps"])]
         lc = opts["launch_cycles"]
         if lc is None:
             lc = max(1, (self.learn_every.value // 2) // max(self.cycle_length, 1))
         self.launch_steps = int(lc) * self.cycle_length
         self._shift = np.asarray(self.dist.all_reduce_sum(x0.sum(axis=0))) / self.n_chains
+        if snap is not None:
+            self._shift = np.asarray(snap["shift"], dtype=np.float64)
         self._mom_buf = None
         self.last_summary = None
+
+    # ------------------------------------------------------------------ resuming
+    SNAPSHOT_VERSION = 1
+
+    def snapshot(self) -> dict:
+        """Everything needed to continue this rank's chains in a new process: the engine's
+        per-chain state and stored rows plus the driver's checkpoint bookkeeping
+        (the ensemble counterpart of mcmc.py:187-214,1045-1078)."""
+        eng = self.engine
+        rows = [eng.rows(c) for c in range(self.n_chains_local)]
+        prog = np.array([[c.N, c.acceptance_rate,
+                          np.nan if c.Rminus1 is None else c.Rminus1,
+                          np.nan if c.Rminus1_cl is None else c.Rminus1_cl,
+                          float(c.learned)] for c in self.progress], dtype=np.float64)
+        return dict(
+            version=self.SNAPSHOT_VERSION, blob=eng.export_state(),
+            n_rows=np.array([len(r) for r in rows], np.int64),
+            rows=np.concatenate(rows) if rows else np.zeros((0, self.fm.row_width)),
+            proposal_cov=self.fm.get_covariance(), seed=np.uint64(self.seed),
+            rank=self.dist.rank, world=self.dist.size, n_chains_local=self.n_chains_local,
+            D=self.fm.D, row_width=self.fm.row_width,
+            converged=bool(self.converged), Rminus1_last=float(self.Rminus1_last),
+            i_learn=int(self.i_learn), n_steps_raw=int(self.n_steps_raw),
+            shift=np.asarray(self._shift, dtype=np.float64),
+            progress=prog.reshape(-1, 5),
+            progress_timestamps=np.array([c.timestamp for c in self.progress], dtype=str),
+        )
+
+    def save_snapshot(self, path: str):
+        with open(path, "wb") as f:
+            np.savez(f, **self.snapshot())
+
+    @staticmethod
+    def load_snapshot(path: str) -> dict:
+        with np.load(path, allow_pickle=False) as z:
+            return {k: z[k] for k in z.files}
+
+    def _check_snapshot(self, snap):
+        if int(snap["version"]) != self.SNAPSHOT_VERSION:
+            raise SamplerError("Snapshot written by another version of the engine.")
+        if int(snap["world"]) != self.dist.size or int(snap["rank"]) != self.dist.rank:
+            raise SamplerError(  # mcmc.py:131-139
+                "Cannot resume a run with a different number of chains: was %d processes "
+                "and now is %d." % (int(snap["world"]), self.dist.size))
+        if int(snap["n_chains_local"]) != self.n_chains_local or int(snap["D"]) != self.fm.D \
+                or int(snap["row_width"]) != self.fm.row_width:
+            raise SamplerError(
+                "Cannot resume: the snapshot holds %d chains of a %d-parameter model "
+                "(%d columns), the input asks for %d chains, %d parameters (%d columns)." % (
+                    int(snap["n_chains_local"]), int(snap["D"]), int(snap["row_width"]),
+                    self.n_chains_local, self.fm.D, self.fm.row_width))
 
     # ------------------------------------------------------------------ helpers
     def _global_summary(self):

@@ -178,10 +178,22 @@ class MCMC(CovmatSampler):
             columns=["N", "timestamp", "acceptance_rate", "Rminus1", "Rminus1_cl"])
         if self.callback_function:
             self.callback_function_callable = get_external_function(self.callback_function)
+        # Resuming (mcmc.py:131-139,187-214): the ensemble continues from the engine
+        # snapshot written next to the chain file at the end of the previous run
+        self._resume_snapshot = None
         if self.output and self.output.is_resuming():
-            raise LoggedError(
-                self.log, "Resuming a run is not yet supported by the B200 ensemble engine "
-                          "(SURVEY.md section 8f row 1).")
+            world = self._world_size()
+            if max(self.mpi_size or 0, 1) != world:
+                raise LoggedError(
+                    self.log, "Cannot resume a run with a different number of chains: "
+                              "was %d and now is %d.", max(self.mpi_size or 0, 1), world)
+            try:
+                self._resume_snapshot = EnsembleMCMC.load_snapshot(self.snapshot_filename())
+            except OSError as e:
+                raise LoggedError(
+                    self.log, "Cannot resume: engine snapshot '%s' not found (%s). It is "
+                              "written when run() ends.", self.snapshot_filename(), e)
+            self.mpi_info("Resuming from previous sample!")
         n_local = int(self.chains_per_gpu)
         # start points: one independent valid point per chain (mcmc.py:215-222)
         D = self.model.prior.d()
@@ -189,11 +201,13 @@ class MCMC(CovmatSampler):
         self._x0 = np.empty((n_local, D))
         self._logpost0 = np.empty(n_local)
         self.log.info("Getting %d initial points...", n_local)
-        for c in range(n_local):
+        for c in range(n_local if self._resume_snapshot is None else 0):
             x, res = self.model.get_valid_point(max_tries=max_tries_init * 100,
                                                 random_state=self._rng)
             self._x0[c] = x
             self._logpost0[c] = res.logpost
+        if self._resume_snapshot is not None:
+            self._x0[:] = np.nan  # replaced by the snapshot's current points in run()
         if self.measure_speeds and not self.blocking:
             n = None if self.measure_speeds is True else int(self.measure_speeds)
             self.model.measure_and_set_speeds(n=n, discard=0, random_state=self._rng)
@@ -203,7 +217,38 @@ class MCMC(CovmatSampler):
         self.collection = SampleCollection(
             self.model, self.output, name=str(1 + mpi.rank()), temperature=self.temperature,
             sample_type="mcmc", is_batch=True)
-        self.write_checkpoint()
+        if not (self.output and self.output.is_resuming()):
+            self.write_checkpoint()
+
+    @staticmethod
+    def _world_size():
+        try:
+            import torch.distributed as tdist
+
+            if tdist.is_available() and tdist.is_initialized():
+                return tdist.get_world_size()
+        except ImportError:
+            pass
+        return 1
+
+    def snapshot_filename(self, rank=None):
+        """Engine snapshot of this process (next to ``prefix.<rank+1>.txt``)."""
+        import os
+
+        rank = self._rank() if rank is None else rank
+        return os.path.join(self.output.folder,
+                            f"{self.output.prefix}.b200_state.{rank + 1}.npz")
+
+    @staticmethod
+    def _rank():
+        try:
+            import torch.distributed as tdist
+
+            if tdist.is_available() and tdist.is_initialized():
+                return tdist.get_rank()
+        except ImportError:
+            pass
+        return 0
 
     def set_proposer_blocking(self):
         """mcmc.py:320-410: blocks/oversampling from the model, dragging gates, thinning."""
@@ -295,7 +340,9 @@ class MCMC(CovmatSampler):
             pass
         try:
             self._ens = EnsembleMCMC(self._fm, self._x0, self._options(), dist=dist,
-                                     covmat_incomplete=self._covmat_incomplete)
+                                     covmat_incomplete=self._covmat_incomplete,
+                                     resume_from=self._resume_snapshot)
+            self._resume_snapshot = None  # rows of the previous run: free the host copy
         except Exception as e:
             raise LoggedError(self.log, "Could not start the B200 engine: %s", e) from e
         ens = self._ens
@@ -322,6 +369,8 @@ class MCMC(CovmatSampler):
                                     c.Rminus1_cl]
         self._fill_collection()
         self.write_checkpoint()
+        if self.output:
+            ens.save_snapshot(self.snapshot_filename())
         self.mpi_info("Sampling complete after %d accepted steps.",
                       ens.last_summary["sum_rows"])
 
@@ -343,6 +392,10 @@ class MCMC(CovmatSampler):
         with an ``output`` the chain file ``prefix.<rank+1>.txt`` is written."""
         self._collection_from_rows(self._ens.samples(), self.collection)
         if self.output:
+            # the file is the concatenation of this process' chains, so more rows per chain
+            # (a resumed run, or products() after more sampling) is not an append: rewrite
+            self.collection._out_delete()
+            self.collection._n_last_out = 0
             self.collection.out_update()
 
     # ------------------------------------------------------------------ products
@@ -387,6 +440,7 @@ class MCMC(CovmatSampler):
             return [(r, None) for r in regexps]
         regexps += [re.compile(output.prefix_regexp_str + re.escape(ext.lstrip(".")) + "$")
                     for ext in [Extension.checkpoint, Extension.progress, Extension.covmat]]
+        regexps += [re.compile(output.prefix_regexp_str + r"b200_state\.\d+\.npz$")]
         return [(r, None) for r in regexps]
 
     @classmethod

@@ -121,6 +121,18 @@ int cb2_set_state(cb2_engine *h, const double *x0);
 int cb2_get_state(cb2_engine *h, double *x, double *logpost, int64_t *weight,
                   int64_t *n_rows, int64_t *n_accepted, uint32_t *flags);
 
+/* Resuming (replaces "last point of the chain file + .checkpoint", cobaya/samplers/mcmc/
+ * mcmc.py:187-214, for an ensemble): the per-chain sampler state -- current point with its
+ * log-posterior pieces, weight, burn-in and thinning counters, visit counters of every
+ * proposer, proposal counter -- as one opaque host buffer of cb2_snapshot_size() bytes.
+ * cb2_import_state replaces cb2_set_state on an engine configured identically (same model,
+ * blocking, options, seed, chain ids) and is followed by cb2_load_rows for every chain
+ * whose stored rows are needed by later checkpoints; the run then continues bit-for-bit. */
+int64_t cb2_snapshot_size(cb2_engine *h);
+int cb2_export_state(cb2_engine *h, void *buf, int64_t nbytes);
+int cb2_import_state(cb2_engine *h, const void *buf, int64_t nbytes);
+int cb2_load_rows(cb2_engine *h, int64_t chain, int64_t n, const double *rows);
+
 /* Model.logposterior (cobaya/model.py:579-678) for n points X[n*D]:
  * logpost[n], logprior[n], loglikes[n*n_like], derived[n*n_derived] (NULL ok). */
 int cb2_logpost(cb2_engine *h, const double *X, int64_t n, double *logpost,

@@ -149,3 +149,53 @@ def test_cobaya_plugin_runs_through_cobaya_run(cuda_lib):
     prog = sampler.products()["progress"]
     assert len(prog) >= 1 and "Rminus1" in prog.columns
     assert len(col) > 1000 and list(col.columns)[:2] == ["weight", "minuslogpost"]
+
+
+def test_cobaya_run_resume_continues_bit_for_bit(cuda_lib, tmp_path):
+    """a run stopped by ``max_samples`` and resumed through ``cobaya.run``
+    (``resume=True``) with a larger limit ends exactly where an uninterrupted run with that
+    limit ends (engine snapshot next to the chain file; mcmc.py:131-139,187-214)."""
+    from tests.refenv import enable_reference
+
+    enable_reference()
+    import copy
+    import os
+
+    from cobaya.run import run
+
+    g = load_golden("g1_gauss3d")
+    mean, cov = g["means"][0], np.asarray(g["covs"]).reshape(3, 3)
+
+    def info(prefix, max_samples):
+        return {
+            "likelihood": {"gaussian_mixture": {"means": [mean], "covs": [cov],
+                                                "input_params_prefix": "a_",
+                                                "output_params_prefix": "", "derived": True}},
+            "params": dict({f"a__{i}": {"prior": {"min": -1, "max": 1}} for i in range(3)},
+                           **{f"_{i}": None for i in range(3)}),
+            "sampler": {"cobaya_b200.plugin.MCMC": {
+                "covmat": np.asarray(g["S0"]), "covmat_params": ["a__0", "a__1", "a__2"],
+                "burn_in": 10, "learn_proposal_Rminus1_max": 30, "Rminus1_stop": 1e-9,
+                "measure_speeds": False, "seed": 5, "chains_per_gpu": 16,
+                "rows_per_chain": 4000, "max_samples": max_samples}},
+            "output": prefix,
+        }
+
+    pa, pb = str(tmp_path / "a" / "run"), str(tmp_path / "b" / "run")
+    _, full = run(copy.deepcopy(info(pa, 900)), force=True)
+    _, first = run(copy.deepcopy(info(pb, 400)), force=True)
+    assert os.path.exists(first.snapshot_filename())
+    assert 400 <= first.n() < 900
+    _, second = run(copy.deepcopy(info(pb, 900)), resume=True)
+    assert second.n_steps_raw == full.n_steps_raw
+    a, b = full.collection.data.to_numpy(), second.collection.data.to_numpy()
+    assert a.shape == b.shape
+    np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(full.proposer.get_covariance(),
+                                  second.proposer.get_covariance())
+    assert len(second.progress) == len(full.progress)
+    # the chain file on disk was rewritten with the longer chains
+    from cobaya.output import load_samples
+
+    back = load_samples(pb, skip=0, combined=True)
+    assert len(back) == len(b)

@@ -124,9 +124,12 @@ WORKER = textwrap.dedent("""
     mn, mx, sm = td.all_reduce_min_max_sum([min(len(r) for r in mine)],
                                            [max(len(r) for r in mine)],
                                            [sum(len(r) for r in mine)])
-    print("RESULT " + json.dumps(dict(rank=td.rank, R=res["Rminus1"], N=res["N"],
-                                      W00=float(res["W"][0, 0]), mn=int(mn[0]),
-                                      mx=int(mx[0]), sm=int(sm[0]))))
+    # one file per rank: the two ranks' stdout lines can interleave
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)),
+                           f"rank{{td.rank}}.json"), "w") as f:
+        json.dump(dict(rank=td.rank, R=res["Rminus1"], N=res["N"],
+                       W00=float(res["W"][0, 0]), mn=int(mn[0]),
+                       mx=int(mx[0]), sm=int(sm[0])), f)
     dist.destroy_process_group()
 """)
 
@@ -144,9 +147,7 @@ def test_world_size_2_gloo_allreduce_gives_identical_verdict_on_every_rank(tmp_p
     assert p.returncode == 0, p.stderr[-2000:]
     import json
 
-    res = [json.loads(l.split("RESULT ", 1)[1]) for l in p.stdout.splitlines()
-           if "RESULT " in l]
-    assert len(res) == 2
+    res = [json.load(open(tmp_path / f"rank{r}.json")) for r in range(2)]
     assert res[0]["R"] == res[1]["R"] and res[0]["W00"] == res[1]["W00"]   # bit-identical
     D, rows = _make_chains(6, 500)
     shift = np.full(D, 0.19)
