@@ -172,12 +172,29 @@ k_basis_wy(uint32_t key0, uint32_t key1, uint64_t chain_id0, int block, int n,
     const int tid = threadIdx.x, nt_ = blockDim.x;
     const int64_t task = task0 + blockIdx.x;
     const int64_t chain = task / cnt;
-    const uint32_t e0 = vis ? (uint32_t)(vis[chain * vis_stride + block] / n) : e0_fixed;
+    // the logarithm table lives in the (not yet used) Gram/T area; its loads are issued first
+    // so that their L2 latency overlaps the zero fill
+    double *ltab = Sg;
+    constexpr int LT_PER = (CB2_LOGTAB_DOUBLES + 127) / 128;
+    double lt[LT_PER];
+#pragma unroll
+    for (int u = 0; u < LT_PER; ++u) {
+        const int e = tid + u * 128;
+        lt[u] = (e < CB2_LOGTAB_DOUBLES) ? g_logtab[e] : 0.0;
+    }
+    uint32_t e0 = e0_fixed;
+    if (vis) {  // visits / n: 32-bit division unless the counter is huge
+        const int64_t v = vis[chain * vis_stride + block];
+        e0 = (v >> 32) ? (uint32_t)(v / n) : (uint32_t)v / (uint32_t)n;
+    }
     const uint32_t epoch = e0 + (uint32_t)(task % cnt);
     const uint64_t gid = chain_id0 + (uint64_t)chain;
     for (int e = tid; e < NP * LDX + 2 * NP; e += nt_) X[e] = 0.0;  // X, Dv, inv (= tau)
-    double *ltab = Sg;  // the logarithm table lives in the (not yet used) Gram/T area
-    for (int e = tid; e < CB2_LOGTAB_DOUBLES; e += nt_) ltab[e] = g_logtab[e];
+#pragma unroll
+    for (int u = 0; u < LT_PER; ++u) {
+        const int e = tid + u * 128;
+        if (e < CB2_LOGTAB_DOUBLES) ltab[e] = lt[u];
+    }
     __syncthreads();
     const int nn = (n + 2) * (n - 1) / 2;
     {
@@ -193,65 +210,37 @@ k_basis_wy(uint32_t key0, uint32_t key1, uint64_t chain_id0, int block, int n,
                 draw_normal_pair_tab(key0, key1, gid, block, epoch, (uint32_t)p, ltab,
                                      z[u][0], z[u][1]);
         }
-        int m = 0, base = 0;  // base = ix(m); q only grows
+        // normal q of the reference's flat array belongs to vector m with
+        // ix(m) = m(2n-m+1)/2 <= q < ix(m+1): m from the root of the quadratic (fp32 is exact
+        // for these magnitudes up to the rounding of sqrt; one fix-up step each way)
+        const int s2 = 2 * n + 1;
 #pragma unroll
         for (int u = 0; u < PPT; ++u) {
             const int p = tid + u * 128;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int q = 2 * p + h;
-                if (q < nn) {
-                    while (q >= base + (n - m)) {
-                        base += n - m;
-                        ++m;
-                    }
-                    X[m * LDX + m + (q - base)] = z[u][h];
+            const int q0 = 2 * p;
+            if (q0 < nn) {
+                int m = (int)(((float)s2 - sqrtf((float)(s2 * s2 - 8 * q0))) * 0.5f);
+                m = min(max(m, 0), n - 2);
+                int base = (m * (s2 - m)) >> 1;
+                if (q0 < base) { --m; base -= n - m; }
+                if (q0 >= base + (n - m)) { base += n - m; ++m; }
+                X[m * LDX + m + (q0 - base)] = z[u][0];
+                if (q0 + 1 < nn) {
+                    if (q0 + 1 >= base + (n - m)) { base += n - m; ++m; }
+                    X[m * LDX + m + (q0 + 1 - base)] = z[u][1];
                 }
             }
         }
     }
     __syncthreads();
-    // functions.py:49-55 -- two threads per vector for the norm
-    {
-        const int m = tid >> 1, half = tid & 1;
-        double part = 0.0;
-        if (m < n - 1) {
-            const double *x = X + m * LDX + m;
-            const int len = n - m;
-            double s0 = 0.0, s1 = 0.0;
-            int i = half;
-            for (; i + 2 < len; i += 4) {
-                s0 = fma(x[i], x[i], s0);
-                s1 = fma(x[i + 2], x[i + 2], s1);
-            }
-            for (; i < len; i += 2) s0 = fma(x[i], x[i], s0);
-            part = s0 + s1;
-        }
-        const double norm2 = part + __shfl_xor_sync(0xffffffffu, part, 1);
-        bool negative = false;
-        if (m < n - 1 && half == 0) {
-            const double x0 = X[m * LDX + m];
-            const double d = (x0 != 0.0) ? (x0 > 0 ? 1.0 : -1.0) : 1.0;
-            const double x0n = x0 + d * sqrt(norm2);
-            X[m * LDX + m] = x0n;
-            // the reference normalises x to |x|^2 = 2 (functions.py:54-55); here x stays as
-            // it is and tau_m = 2 / |x|^2 enters through T (dlarft with general tau)
-            inv[m] = 2.0 / (norm2 - x0 * x0 + x0n * x0n);
-            Dv[m] = d;
-            negative = d < 0.0;
-        }
-        // functions.py:59: D[n-1] = (-1)^(n-1) prod(D[:-1]) -- a parity count
-        const unsigned negs = __ballot_sync(0xffffffffu, negative);
-        if ((tid & 31) == 0) sign_cnt[tid >> 5] = __popc(negs);
-    }
-    __syncthreads();
-    if (tid == 0) {
-        const int c = sign_cnt[0] + sign_cnt[1] + sign_cnt[2] + sign_cnt[3] + (n - 1);
-        Dv[n - 1] = (c & 1) ? -1.0 : 1.0;  // read after the next block-wide barrier
-    }
     const int lane = tid & 31, w = tid >> 5, q = lane >> 2, r = lane & 3;
     // Gram S_g = V_g^T V_g of every group on the tensor pipe (A and B fragments coincide:
-    // lane (q,r) holds x_{8g+q}[k = r]), then row i of T (dlarft) by lane i
+    // lane (q,r) holds x_{8g+q}[k = r]).  It is taken over the normals as drawn: the
+    // diagonal is nu_m = |x_m|^2 (functions.py:50), from which sign, x_m[0] += D sqrt(nu) and
+    // tau_m follow (functions.py:51-55; the reference's normalisation is carried by tau);
+    // for i < j the modified leading element of x_j only changes
+    // S_ij by (x_j[0]' - x_j[0]) x_i[j - i].  Then row i of T (dlarft) by lane i.
+    int n_negative = 0;
     for (int g = w; g < NG; g += 4) {
         double s0 = 0.0, s1 = 0.0;
         const double *xq = X + (8 * g + q) * LDX + 8 * g + r;
@@ -260,9 +249,39 @@ k_basis_wy(uint32_t key0, uint32_t key1, uint64_t chain_id0, int block, int n,
             const double a = xq[4 * kk];
             dmma8x8x4(s0, s1, a, a);
         }
+        // lane (q,r) holds S[q][2r], S[q][2r+1]; the diagonal entry j sits in lane 4j + j/2
+        const double nu_a = __shfl_sync(0xffffffffu, s0, 9 * r);      // j = 2r
+        const double nu_b = __shfl_sync(0xffffffffu, s1, 9 * r + 4);  // j = 2r + 1
+        const int ja = 2 * r, jb = 2 * r + 1, ma = 8 * g + ja, mb = 8 * g + jb;
+        const double xa = X[ma * LDX + ma], xb = X[mb * LDX + mb];
+        const double da = (xa != 0.0) ? (xa > 0 ? 1.0 : -1.0) : 1.0;
+        const double db = (xb != 0.0) ? (xb > 0 ? 1.0 : -1.0) : 1.0;
+        const bool va = ma < n - 1, vb = mb < n - 1;
+        const double ca = va ? da * sqrt(nu_a) : 0.0, cb = vb ? db * sqrt(nu_b) : 0.0;
+        const double *xrow = X + (8 * g + q) * LDX + 8 * g;
+        if (q < ja) s0 = fma(ca, xrow[ja], s0);
+        if (q < jb) s1 = fma(cb, xrow[jb], s1);
         double *S = Sg + g * 64;
         S[q * 8 + 2 * r] = s0;
         S[q * 8 + 2 * r + 1] = s1;
+        __syncwarp();  // every lane has read the leading elements it needs
+        if (q == 0) {
+            if (va) {
+                const double x0n = xa + ca;
+                X[ma * LDX + ma] = x0n;
+                inv[ma] = 2.0 / (nu_a - xa * xa + x0n * x0n);
+                Dv[ma] = da;
+            }
+            if (vb) {
+                const double x0n = xb + cb;
+                X[mb * LDX + mb] = x0n;
+                inv[mb] = 2.0 / (nu_b - xb * xb + x0n * x0n);
+                Dv[mb] = db;
+            }
+        }
+        // functions.py:59: D[n-1] = (-1)^(n-1) prod(D[:-1]) -- a parity count
+        n_negative += __popc(__ballot_sync(0xffffffffu, q == 0 && va && da < 0.0)) +
+                      __popc(__ballot_sync(0xffffffffu, q == 0 && vb && db < 0.0));
         __syncwarp();
         if (lane < 8) {
             const int i = lane;
@@ -283,7 +302,14 @@ k_basis_wy(uint32_t key0, uint32_t key1, uint64_t chain_id0, int block, int n,
             for (int j = 0; j < 8; ++j) T[i * 8 + j] = trow[j];
         }
     }
+    if (lane == 0) sign_cnt[w] = n_negative;
     __syncthreads();
+    {
+        const int c = sign_cnt[0] + sign_cnt[1] + sign_cnt[2] + sign_cnt[3] + (n - 1);
+        if (tid == 0) Dv[n - 1] = (c & 1) ? -1.0 : 1.0;
+    }
+    const double d_last = ((sign_cnt[0] + sign_cnt[1] + sign_cnt[2] + sign_cnt[3] + (n - 1)) & 1)
+                              ? -1.0 : 1.0;
     // ---- accumulate H = Q_0 Q_1 ... Q_{NG-1} from the innermost factor (dorgqr order): with
     // N = M^T,  M <- Q_g M  is  N <- N - ((N V_g) T_g^T) V_g^T, and only rows/columns >= 8g
     // of N differ from the identity, so row tiles below 8g are skipped (888 instead of 1280
@@ -355,8 +381,9 @@ k_basis_wy(uint32_t key0, uint32_t key1, uint64_t chain_id0, int block, int n,
                     for (int nt = 0; nt < NG; ++nt) {
                         const int i = 8 * nt + 2 * r;
                         if (i < n)
-                            *reinterpret_cast<double2 *>(out + (size_t)c * n + i) =
-                                make_double2(Dv[i] * nreg[sl][nt][0], Dv[i + 1] * nreg[sl][nt][1]);
+                            *reinterpret_cast<double2 *>(out + (size_t)c * n + i) = make_double2(
+                                Dv[i] * nreg[sl][nt][0],
+                                (i + 1 == n - 1 ? d_last : Dv[i + 1]) * nreg[sl][nt][1]);
                     }
                 } else {
 #pragma unroll
@@ -364,7 +391,9 @@ k_basis_wy(uint32_t key0, uint32_t key1, uint64_t chain_id0, int block, int n,
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
                             const int i = 8 * nt + 2 * r + h;
-                            if (i < n) out[(size_t)c * n + i] = Dv[i] * nreg[sl][nt][h];
+                            if (i < n)
+                                out[(size_t)c * n + i] =
+                                    (i == n - 1 ? d_last : Dv[i]) * nreg[sl][nt][h];
                         }
                 }
             }

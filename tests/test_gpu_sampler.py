@@ -175,7 +175,8 @@ def test_cobaya_run_resume_continues_bit_for_bit(cuda_lib, tmp_path):
                            **{f"_{i}": None for i in range(3)}),
             "sampler": {"cobaya_b200.plugin.MCMC": {
                 "covmat": np.asarray(g["S0"]), "covmat_params": ["a__0", "a__1", "a__2"],
-                "burn_in": 10, "learn_proposal_Rminus1_max": 30, "Rminus1_stop": 1e-9,
+                "burn_in": 10, "max_tries": 3000, "learn_proposal_Rminus1_max": 30,
+                "Rminus1_stop": 1e-9,
                 "measure_speeds": False, "seed": 5, "chains_per_gpu": 16,
                 "rows_per_chain": 4000, "max_samples": max_samples}},
             "output": prefix,
