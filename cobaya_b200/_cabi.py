@@ -14,7 +14,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libcobaya_b200.so")
+# COBAYA_B200_LIB: another build of the same library (kernel experiments); never a fallback
+LIB_PATH = os.environ.get("COBAYA_B200_LIB") or os.path.join(_HERE, "lib", "libcobaya_b200.so")
 
 EXPORTS = [
     "cb2_abi_version", "cb2_last_error", "cb2_create", "cb2_destroy", "cb2_set_prior",
