@@ -146,6 +146,63 @@ k_basis_fast(uint32_t key0, uint32_t key1, uint64_t chain_id0, int block, int n,
 }
 
 // -------------------------------------------------------------------------------------
+// k_normals: the standard normals random_SO_N consumes (functions.py:36), one CTA per
+// (chain, epoch), written in the reference's flat order (vector m occupies
+// [m(2n-m+1)/2, +n-m)) to out[task * nn_pad ...].  It is integer/ALU work (Philox rounds,
+// bit-assembled uniforms, table logarithm, series sincos) with no tensor-pipe use and a
+// 64-register footprint, so that the engine can run it on a side stream UNDER the step
+// kernel of the previous window (which leaves ~3/4 of the issue slots idle) instead of in
+// front of the Householder sweep.  Same draws as draw_normal_pair_tab in the fused kernels.
+// -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 8)
+k_normals(uint32_t key0, uint32_t key1, uint64_t chain_id0, int block, int n,
+          const int64_t *__restrict__ vis, int vis_stride, uint32_t e0_fixed, int cnt,
+          double *__restrict__ out, int nn_pad) {
+    __shared__ double ltab[CB2_LOGTAB_DOUBLES];
+    const int tid = threadIdx.x;
+    for (int e = tid; e < CB2_LOGTAB_DOUBLES; e += 128) ltab[e] = g_logtab[e];
+    const int64_t task = blockIdx.x;
+    const int64_t chain = task / cnt;
+    uint32_t e0 = e0_fixed;
+    if (vis) {
+        const int64_t v = vis[chain * vis_stride + block];
+        e0 = (v >> 32) ? (uint32_t)(v / n) : (uint32_t)v / (uint32_t)n;
+    }
+    const uint32_t epoch = e0 + (uint32_t)(task % cnt);
+    const uint64_t gid = chain_id0 + (uint64_t)chain;
+    const int npairs = nn_pad >> 1;  // nn_pad = nn rounded up to even
+    double2 *o2 = reinterpret_cast<double2 *>(out + (size_t)task * (size_t)nn_pad);
+    __syncthreads();
+    // two pairs per iteration: independent Philox / log / sincos chains for the scheduler
+    int p = tid;
+    for (; p + 128 < npairs; p += 256) {
+        double a0, a1, b0, b1;
+        draw_normal_pair_tab(key0, key1, gid, block, epoch, (uint32_t)p, ltab, a0, a1);
+        draw_normal_pair_tab(key0, key1, gid, block, epoch, (uint32_t)(p + 128), ltab, b0, b1);
+        o2[p] = make_double2(a0, a1);
+        o2[p + 128] = make_double2(b0, b1);
+    }
+    if (p < npairs) {
+        double a0, a1;
+        draw_normal_pair_tab(key0, key1, gid, block, epoch, (uint32_t)p, ltab, a0, a1);
+        o2[p] = make_double2(a0, a1);
+    }
+}
+
+static inline int launch_normals(cudaStream_t st, uint32_t k0, uint32_t k1, uint64_t chain_id0,
+                                 int block, int n, const int64_t *vis, int vis_stride, int cnt,
+                                 double *out, int64_t n_chains) {
+    const int nn = (n + 2) * (n - 1) / 2, nn_pad = (nn + 1) & ~1;
+    k_normals<<<(unsigned)(n_chains * cnt), 128, 0, st>>>(k0, k1, chain_id0, block, n, vis,
+                                                          vis_stride, 0u, cnt, out, nn_pad);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+static inline size_t normals_per_task(int n) {
+    const int nn = (n + 2) * (n - 1) / 2;
+    return (size_t)((nn + 1) & ~1);
+}
+
+// -------------------------------------------------------------------------------------
 // k_basis_wy<NG>: the same Haar basis with the Householder sweep on the FP64 TENSOR pipe.
 // Reflectors are grouped 8 at a time in compact-WY form (LAPACK dlarft, forward/columnwise):
 //   G_{m0} ... G_{m0+7} = I - V T V^T,  V = [x_{m0} .. x_{m0+7}],  T upper triangular,
@@ -159,7 +216,8 @@ template <int NG>
 __global__ void __launch_bounds__(128, 5)
 k_basis_wy(uint32_t key0, uint32_t key1, uint64_t chain_id0, int block, int n,
            const int64_t *__restrict__ vis, int vis_stride, uint32_t e0_fixed, int cnt,
-           double *__restrict__ store, int64_t task0, int64_t store_task0) {
+           double *__restrict__ store, int64_t task0, int64_t store_task0,
+           const double *__restrict__ normals, int nn_pad) {
     constexpr int NP = NG * 8;
     constexpr int LDX = NP + 1;  // odd row stride: both B-fragment access patterns spread banks
     extern __shared__ __align__(16) double fsm[];
@@ -172,6 +230,38 @@ k_basis_wy(uint32_t key0, uint32_t key1, uint64_t chain_id0, int block, int n,
     const int tid = threadIdx.x, nt_ = blockDim.x;
     const int64_t task = task0 + blockIdx.x;
     const int64_t chain = task / cnt;
+    if (normals) {
+        // normals pre-generated by k_normals (flat reference order): row m of X is the
+        // contiguous run [ix(m), ix(m) + n - m).  All loads of a thread are issued before
+        // the zero fill so that their latency overlaps it.
+        constexpr int RPW = (NP + 3) / 4;  // rows per warp
+        const int lane_ = tid & 31, w_ = tid >> 5;
+        const double *src = normals + (size_t)(task - task0) * (size_t)nn_pad;
+        double v[RPW][2];
+#pragma unroll
+        for (int u = 0; u < RPW; ++u) {
+            const int m = w_ + 4 * u;
+            const int len = n - m, base = (m * (2 * n - m + 1)) >> 1;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int i = lane_ + 32 * h;
+                v[u][h] = (m < n - 1 && i < len) ? __ldg(src + base + i) : 0.0;
+            }
+        }
+        for (int e = tid; e < NP * LDX + 2 * NP; e += nt_) X[e] = 0.0;  // X, Dv, inv (= tau)
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < RPW; ++u) {
+            const int m = w_ + 4 * u;
+            const int len = n - m;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int i = lane_ + 32 * h;
+                if (m < n - 1 && i < len) X[m * LDX + m + i] = v[u][h];
+            }
+        }
+        __syncthreads();
+    } else {
     // the logarithm table lives in the (not yet used) Gram/T area; its loads are issued first
     // so that their L2 latency overlaps the zero fill
     double *ltab = Sg;
@@ -233,6 +323,7 @@ k_basis_wy(uint32_t key0, uint32_t key1, uint64_t chain_id0, int block, int n,
         }
     }
     __syncthreads();
+    }
     const int lane = tid & 31, w = tid >> 5, q = lane >> 2, r = lane & 3;
     // Gram S_g = V_g^T V_g of every group on the tensor pipe (A and B fragments coincide:
     // lane (q,r) holds x_{8g+q}[k = r]).  It is taken over the normals as drawn: the
@@ -407,7 +498,8 @@ template <int NG>
 static int launch_basis_fast_t(cudaStream_t st, uint32_t k0, uint32_t k1, uint64_t chain_id0,
                                int block, int n, const int64_t *vis, int vis_stride,
                                uint32_t e0_fixed, int cnt, double *store, int64_t tasks,
-                               int64_t task0, int64_t store_task0) {
+                               int64_t task0, int64_t store_task0,
+                               const double *normals = nullptr, int nn_pad = 0) {
     constexpr int NP = NG * 8;
     if (g_basis_wy) {
         const int gram_t = 2 * NG * 64 > CB2_LOGTAB_DOUBLES ? 2 * NG * 64 : CB2_LOGTAB_DOUBLES;
@@ -418,7 +510,7 @@ static int launch_basis_fast_t(cudaStream_t st, uint32_t k0, uint32_t k1, uint64
         if (e2 != cudaSuccess) return -1;
         k_basis_wy<NG><<<(unsigned)tasks, 128, smem_wy, st>>>(
             k0, k1, chain_id0, block, n, vis, vis_stride, e0_fixed, cnt, store, task0,
-            store_task0);
+            store_task0, normals, nn_pad);
         return cudaGetLastError() == cudaSuccess ? 0 : -1;
     }
     const int threads = 2 * NP < 32 ? 32 : 2 * NP;
@@ -434,12 +526,14 @@ static int launch_basis_fast_t(cudaStream_t st, uint32_t k0, uint32_t k1, uint64
 static int launch_basis_fast_any(cudaStream_t st, uint32_t k0, uint32_t k1, uint64_t chain_id0,
                                  int block, int n, const int64_t *vis, int vis_stride,
                                  uint32_t e0_fixed, int cnt, double *store, int64_t tasks,
-                                 int64_t task0, int64_t store_task0) {
+                                 int64_t task0, int64_t store_task0,
+                                 const double *normals = nullptr, int nn_pad = 0) {
     const int NG = (n + 7) / 8;
 #define CB2_BF(G)                                                                           \
     case G:                                                                                 \
         return launch_basis_fast_t<G>(st, k0, k1, chain_id0, block, n, vis, vis_stride,     \
-                                      e0_fixed, cnt, store, tasks, task0, store_task0);
+                                      e0_fixed, cnt, store, tasks, task0, store_task0,      \
+                                      normals, nn_pad);
     switch (NG) {
         CB2_BF(1) CB2_BF(2) CB2_BF(3) CB2_BF(4) CB2_BF(5) CB2_BF(6) CB2_BF(7) CB2_BF(8)
     }
@@ -449,9 +543,11 @@ static int launch_basis_fast_any(cudaStream_t st, uint32_t k0, uint32_t k1, uint
 
 static inline int launch_basis_fast(cudaStream_t st, uint32_t k0, uint32_t k1,
                                     uint64_t chain_id0, int block, int n, const int64_t *vis,
-                                    int vis_stride, int cnt, double *store, int64_t n_chains) {
+                                    int vis_stride, int cnt, double *store, int64_t n_chains,
+                                    const double *normals = nullptr) {
     return launch_basis_fast_any(st, k0, k1, chain_id0, block, n, vis, vis_stride, 0u, cnt,
-                                 store, n_chains * cnt, 0, 0);
+                                 store, n_chains * cnt, 0, 0, normals,
+                                 normals ? (int)normals_per_task(n) : 0);
 }
 
 static inline int launch_basis_fast_one(cudaStream_t st, uint32_t k0, uint32_t k1, uint64_t gid,

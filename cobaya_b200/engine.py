@@ -237,8 +237,9 @@ class Engine:
         self._ck(self.lib.cb2_set_profiling(self.h, int(bool(on))))
 
     def kernel_times(self, reset: bool = True):
-        """Per-kernel-class device time (ms) and launch counts: tape, basis, step, moments."""
-        ms = np.zeros(4); n = np.zeros(4, np.int64)
+        """Per-kernel-class device time (ms) and launch counts: tape, basis, step, moments,
+        normals (the latter run on a side stream under the step kernel)."""
+        ms = np.zeros(5); n = np.zeros(5, np.int64)
         self._ck(self.lib.cb2_kernel_times(self.h, _cabi.ptr(ms), _cabi.ptr(n), int(reset)))
-        names = ["tape", "basis", "step", "moments"]
+        names = ["tape", "basis", "step", "moments", "normals"]
         return {k: dict(ms=float(ms[i]), launches=int(n[i])) for i, k in enumerate(names)}

@@ -185,9 +185,10 @@ int cb2_timer_start(cb2_engine *h);
 int cb2_timer_stop(cb2_engine *h, float *ms);
 /* per-kernel-class device time: when profiling is on every launch is bracketed by CUDA
  * events on the engine's stream; ms[k]/n[k] accumulate over launches of class
- * k = 0 cycler tapes, 1 Haar bases, 2 step kernel, 3 moments. */
+ * k = 0 cycler tapes, 1 Haar bases, 2 step kernel, 3 moments, 4 normals of the Haar bases
+ * (stream2 when they are generated under the previous window's step kernel). */
 int cb2_set_profiling(cb2_engine *h, int32_t on);
-int cb2_kernel_times(cb2_engine *h, double ms[4], int64_t n[4], int32_t reset);
+int cb2_kernel_times(cb2_engine *h, double ms[5], int64_t n[5], int32_t reset);
 /* which step kernel the last cb2_advance used: 0 = general warp-per-chain,
  * 1 = DMMA (mma.sync.m8n8k4.f64) register-resident, 2 = DMMA producer/consumer */
 int cb2_last_step_kernel(const cb2_engine *h);
