@@ -26,6 +26,8 @@ __device__ __forceinline__ void dmma8x8x4(double &d0, double &d1, double a, doub
 // Haar basis, n <= 64
 // =====================================================================================
 static inline bool fast_basis_supported(int n) { return n >= 2 && n <= 64; }
+// 64 < n <= 128: compact-WY kernel with 8 warps per basis, normals from k_normals
+static inline bool wy_large_supported(int n) { return n > 64 && n <= 128; }
 
 template <int NG>
 __global__ void __launch_bounds__((NG * 16 < 32) ? 32 : NG * 16, (NG >= 7) ? 4 : 1)
@@ -212,8 +214,10 @@ static inline size_t normals_per_task(int n) {
 // (q,r): H[row q][cols 8nt+2r, +1]); with the even/odd k interleave a C fragment is directly
 // an A fragment.  Same matrix as functions.py:48-58 up to rounding (~1e-15).
 // -------------------------------------------------------------------------------------
-template <int NG>
-__global__ void __launch_bounds__(128, 5)
+// NW warps per basis: 4 for n <= 64; 8 for 64 < n <= 128 (NG = 16 groups, the normals must then
+// come from k_normals).  Warp w owns the row tiles {w, NG-1-w} of N.
+template <int NG, int NW>
+__global__ void __launch_bounds__(NW * 32, (NG <= 8) ? 5 : 1)
 k_basis_wy(uint32_t key0, uint32_t key1, uint64_t chain_id0, int block, int n,
            const int64_t *__restrict__ vis, int vis_stride, uint32_t e0_fixed, int cnt,
            double *__restrict__ store, int64_t task0, int64_t store_task0,
@@ -226,42 +230,54 @@ k_basis_wy(uint32_t key0, uint32_t key1, uint64_t chain_id0, int block, int n,
     double *inv = Dv + NP;              // [NP]
     double *Sg = inv + NP;              // [NG][8][8] Gram (strict upper) per group
     double *Tg = Sg + NG * 64;          // [NG][8][8] T per group
-    __shared__ int sign_cnt[4];
+    __shared__ int sign_cnt[NW];
     const int tid = threadIdx.x, nt_ = blockDim.x;
     const int64_t task = task0 + blockIdx.x;
     const int64_t chain = task / cnt;
     if (normals) {
         // normals pre-generated by k_normals (flat reference order): row m of X is the
-        // contiguous run [ix(m), ix(m) + n - m).  All loads of a thread are issued before
-        // the zero fill so that their latency overlaps it.
-        constexpr int RPW = (NP + 3) / 4;  // rows per warp
+        // contiguous run [ix(m), ix(m) + n - m).  The first batch of loads is issued before
+        // the zero fill so that its latency overlaps it.
+        constexpr int RPW = (NP + NW - 1) / NW;  // rows per warp
+        constexpr int NH = (NP + 31) / 32;       // column chunks of 32
+        constexpr int UB = (RPW * NH <= 32) ? RPW : 4;  // rows in flight per batch
         const int lane_ = tid & 31, w_ = tid >> 5;
         const double *src = normals + (size_t)(task - task0) * (size_t)nn_pad;
-        double v[RPW][2];
+        double v[UB][NH];
+        auto load_rows = [&](int u0) {
 #pragma unroll
-        for (int u = 0; u < RPW; ++u) {
-            const int m = w_ + 4 * u;
-            const int len = n - m, base = (m * (2 * n - m + 1)) >> 1;
+            for (int u = 0; u < UB; ++u) {
+                const int m = w_ + NW * (u0 + u);
+                const int len = n - m, base = (m * (2 * n - m + 1)) >> 1;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int i = lane_ + 32 * h;
-                v[u][h] = (m < n - 1 && i < len) ? __ldg(src + base + i) : 0.0;
+                for (int h = 0; h < NH; ++h) {
+                    const int i = lane_ + 32 * h;
+                    v[u][h] = (u0 + u < RPW && m < n - 1 && i < len) ? __ldg(src + base + i) : 0.0;
+                }
             }
-        }
+        };
+        auto store_rows = [&](int u0) {
+#pragma unroll
+            for (int u = 0; u < UB; ++u) {
+                const int m = w_ + NW * (u0 + u);
+                const int len = n - m;
+#pragma unroll
+                for (int h = 0; h < NH; ++h) {
+                    const int i = lane_ + 32 * h;
+                    if (u0 + u < RPW && m < n - 1 && i < len) X[m * LDX + m + i] = v[u][h];
+                }
+            }
+        };
+        load_rows(0);  // in flight during the zero fill
         for (int e = tid; e < NP * LDX + 2 * NP; e += nt_) X[e] = 0.0;  // X, Dv, inv (= tau)
         __syncthreads();
-#pragma unroll
-        for (int u = 0; u < RPW; ++u) {
-            const int m = w_ + 4 * u;
-            const int len = n - m;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int i = lane_ + 32 * h;
-                if (m < n - 1 && i < len) X[m * LDX + m + i] = v[u][h];
-            }
+        store_rows(0);
+        for (int u0 = UB; u0 < RPW; u0 += UB) {
+            load_rows(u0);
+            store_rows(u0);
         }
         __syncthreads();
-    } else {
+    } else if constexpr (NG <= 8) {
     // the logarithm table lives in the (not yet used) Gram/T area; its loads are issued first
     // so that their L2 latency overlaps the zero fill
     double *ltab = Sg;
@@ -332,7 +348,7 @@ k_basis_wy(uint32_t key0, uint32_t key1, uint64_t chain_id0, int block, int n,
     // for i < j the modified leading element of x_j only changes
     // S_ij by (x_j[0]' - x_j[0]) x_i[j - i].  Then row i of T (dlarft) by lane i.
     int n_negative = 0;
-    for (int g = w; g < NG; g += 4) {
+    for (int g = w; g < NG; g += NW) {
         double s0 = 0.0, s1 = 0.0;
         const double *xq = X + (8 * g + q) * LDX + 8 * g + r;
 #pragma unroll 4
@@ -396,11 +412,15 @@ k_basis_wy(uint32_t key0, uint32_t key1, uint64_t chain_id0, int block, int n,
     if (lane == 0) sign_cnt[w] = n_negative;
     __syncthreads();
     {
-        const int c = sign_cnt[0] + sign_cnt[1] + sign_cnt[2] + sign_cnt[3] + (n - 1);
+        int c = n - 1;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) c += sign_cnt[i];
         if (tid == 0) Dv[n - 1] = (c & 1) ? -1.0 : 1.0;
     }
-    const double d_last = ((sign_cnt[0] + sign_cnt[1] + sign_cnt[2] + sign_cnt[3] + (n - 1)) & 1)
-                              ? -1.0 : 1.0;
+    int c_all = n - 1;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) c_all += sign_cnt[i];
+    const double d_last = (c_all & 1) ? -1.0 : 1.0;
     // ---- accumulate H = Q_0 Q_1 ... Q_{NG-1} from the innermost factor (dorgqr order): with
     // N = M^T,  M <- Q_g M  is  N <- N - ((N V_g) T_g^T) V_g^T, and only rows/columns >= 8g
     // of N differ from the identity, so row tiles below 8g are skipped (888 instead of 1280
@@ -501,26 +521,33 @@ static int launch_basis_fast_t(cudaStream_t st, uint32_t k0, uint32_t k1, uint64
                                int64_t task0, int64_t store_task0,
                                const double *normals = nullptr, int nn_pad = 0) {
     constexpr int NP = NG * 8;
-    if (g_basis_wy) {
+    constexpr int NW = (NG <= 8) ? 4 : NG / 2;
+    if (g_basis_wy || NG > 8) {
+        if (NG > 8 && !normals) return -3;  // large blocks take their normals from k_normals
         const int gram_t = 2 * NG * 64 > CB2_LOGTAB_DOUBLES ? 2 * NG * 64 : CB2_LOGTAB_DOUBLES;
         const size_t smem_wy = (size_t)(NP * (NP + 1) + 2 * NP + gram_t) * sizeof(double);
-        cudaError_t e2 = cudaFuncSetAttribute(k_basis_wy<NG>,
+        cudaError_t e2 = cudaFuncSetAttribute(k_basis_wy<NG, NW>,
                                               cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               (int)smem_wy);
         if (e2 != cudaSuccess) return -1;
-        k_basis_wy<NG><<<(unsigned)tasks, 128, smem_wy, st>>>(
+        k_basis_wy<NG, NW><<<(unsigned)tasks, NW * 32, smem_wy, st>>>(
             k0, k1, chain_id0, block, n, vis, vis_stride, e0_fixed, cnt, store, task0,
             store_task0, normals, nn_pad);
         return cudaGetLastError() == cudaSuccess ? 0 : -1;
     }
-    const int threads = 2 * NP < 32 ? 32 : 2 * NP;
-    const size_t smem = (size_t)(NP * NP + 2 * NP) * sizeof(double);
-    cudaError_t e = cudaFuncSetAttribute(k_basis_fast<NG>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return -1;
-    k_basis_fast<NG><<<(unsigned)tasks, threads, smem, st>>>(
-        k0, k1, chain_id0, block, n, vis, vis_stride, e0_fixed, cnt, store, task0, store_task0);
-    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+    if constexpr (NG <= 8) {
+        const int threads = 2 * NP < 32 ? 32 : 2 * NP;
+        const size_t smem = (size_t)(NP * NP + 2 * NP) * sizeof(double);
+        cudaError_t e = cudaFuncSetAttribute(k_basis_fast<NG>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) return -1;
+        k_basis_fast<NG><<<(unsigned)tasks, threads, smem, st>>>(
+            k0, k1, chain_id0, block, n, vis, vis_stride, e0_fixed, cnt, store, task0,
+            store_task0);
+        return cudaGetLastError() == cudaSuccess ? 0 : -1;
+    }
+    return -1;
 }
 
 static int launch_basis_fast_any(cudaStream_t st, uint32_t k0, uint32_t k1, uint64_t chain_id0,
@@ -528,7 +555,8 @@ static int launch_basis_fast_any(cudaStream_t st, uint32_t k0, uint32_t k1, uint
                                  uint32_t e0_fixed, int cnt, double *store, int64_t tasks,
                                  int64_t task0, int64_t store_task0,
                                  const double *normals = nullptr, int nn_pad = 0) {
-    const int NG = (n + 7) / 8;
+    int NG = (n + 7) / 8;
+    if (NG > 8) NG = (NG + 1) & ~1;  // large blocks: even group counts only (2 tiles per warp)
 #define CB2_BF(G)                                                                           \
     case G:                                                                                 \
         return launch_basis_fast_t<G>(st, k0, k1, chain_id0, block, n, vis, vis_stride,     \
@@ -536,6 +564,7 @@ static int launch_basis_fast_any(cudaStream_t st, uint32_t k0, uint32_t k1, uint
                                       normals, nn_pad);
     switch (NG) {
         CB2_BF(1) CB2_BF(2) CB2_BF(3) CB2_BF(4) CB2_BF(5) CB2_BF(6) CB2_BF(7) CB2_BF(8)
+        CB2_BF(10) CB2_BF(12) CB2_BF(14) CB2_BF(16)
     }
 #undef CB2_BF
     return -1;

@@ -1,0 +1,84 @@
+#!/usr/bin/env python
+"""BASELINE.json configs[4]: D in {8, 32, 128, 512} x chains in {1k, 8k, 64k} (plus the
+headline D = 64), single-mode correlated Gaussian, one block, proposals/s against the HBM
+and FP64 roofs of SURVEY.md section 8d.  One JSON line per cell; device time from CUDA events
+on the engine's stream.
+
+    python tools/dim_sweep.py [--cells 8x1024,64x8192,...] [--cycles 4] > gpurun_out/sweep.jsonl
+"""
+import argparse
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+
+from cobaya_b200.engine import Engine
+from cobaya_b200.flatmodel import FlatModel, synthetic_gaussian_cov
+
+KERNEL = {0: "general", 1: "dmma", 2: "dmma-producer-consumer"}
+
+
+def peaks():
+    hbm, fp64 = 6552.0, 36.9
+    p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                     "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        hbm = float(json.load(open(p)).get("hbm_gbs", hbm))
+    return hbm, fp64  # fp64: tools/fp64_peak.cu on this pool's B200 (profiles/r1_fp64_peak.json)
+
+
+def run_cell(D, C, cycles, seed=1):
+    cov = synthetic_gaussian_cov(D)
+    fm = FlatModel.gaussian(np.zeros(D), cov, proposal_cov=cov)
+    rng = np.random.default_rng(0)
+    L = np.linalg.cholesky(cov)
+    x0 = rng.standard_normal((C, D)) @ L.T
+    n = cycles * D
+    warm = 2 * D
+    cap = int(0.6 * (n + warm)) + 64
+    # keep the row store inside ~40 GB
+    if C * cap * (D + 6) * 8 > 40e9:
+        cap = int(40e9 / (C * (D + 6) * 8))
+    eng = Engine(fm, n_chains=C, seed=seed, rows_cap=cap)
+    eng.set_state(x0)
+    eng.advance(warm)
+    eng.sync()
+    eng.timer_start()
+    eng.advance(n)
+    ms = eng.timer_stop()
+    s = eng.summary()
+    st_rate = s["sum_rows"] / float(C * (n + warm))
+    rate = C * n / (ms * 1e-3)
+    hbm, fp64 = peaks()
+    bytes_pp = 16.0 * D + 8.0 * st_rate * (D + 6)
+    out = {"D": D, "chains": C, "proposals": C * n, "ms": ms, "proposals_per_s": rate,
+           "step_kernel": KERNEL.get(eng.last_step_kernel(), "?"),
+           "stored_row_rate": st_rate,
+           "hbm_frac": bytes_pp * rate / (hbm * 1e9),
+           "fp64_frac": 4.0 * D * D * rate / (fp64 * 1e12),
+           "n_stuck": s["n_stuck"], "n_rows_full": s["n_rows_full"]}
+    eng.close()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cells", default="")
+    ap.add_argument("--cycles", type=int, default=4)
+    a = ap.parse_args()
+    if a.cells:
+        cells = [tuple(int(v) for v in c.split("x")) for c in a.cells.split(",")]
+    else:
+        cells = [(D, C) for D in (8, 32, 64, 128, 512) for C in (1024, 8192, 65536)]
+    for D, C in cells:
+        cyc = a.cycles if D < 512 else max(1, a.cycles // 2)
+        try:
+            print(json.dumps(run_cell(D, C, cyc)), flush=True)
+        except Exception as e:  # report the cell, go on with the grid
+            print(json.dumps({"D": D, "chains": C, "error": str(e)[:300]}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
