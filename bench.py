@@ -374,7 +374,7 @@ def run_gpu_arm(args):
                    "locksteps_per_step": locksteps, "checkpoints_in_timed_region": n_ckpt - ck0,
                    "l2": "working set per step (268 MB of Haar bases + sample rows) exceeds "
                          "the 126 MB L2; no explicit flush",
-                   "step_kernel": {0: "general", 1: "dmma", 2: "dmma-producer-consumer"}.get(
+                   "step_kernel": {0: "general", 1: "dmma", 2: "dmma-producer-consumer", 3: "dmma-streamed"}.get(
                        eng.last_step_kernel(), "?"),
                    "parallelism": f"chains sharded over {world} GPU(s), no data-path "
                                   "collective; NCCL all-reduce of moments per checkpoint"},

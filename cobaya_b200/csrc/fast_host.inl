@@ -111,3 +111,104 @@ static int pack_fast(cb2_engine *h) {
     h->fast_ready = true;
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------
+// pack_stream: constant block of the streamed path (kernels_stream.cuh) for 64 < D <= 128.
+// Same conventions as pack_fast (block-sorted coordinates, DP = 8 NT, B-fragment order); it
+// lives in global memory (the kernels read it through L1/L2), so there is no size limit.
+// ---------------------------------------------------------------------------------------
+static int pack_stream(cb2_engine *h) {
+    h->stream_ready = false;
+    if (h->D <= 64 || !stream_step_supported(h->M, h->likes.size())) return 0;
+    const int D = h->D, NT = (D + 7) / 8, DP = 8 * NT;
+    const LikeHost &L = h->likes[0];
+    const int nm = L.d.n_modes;
+    std::vector<int> ilike_of_i(D, -1);
+    for (int a = 0; a < D; ++a) {
+        if (ilike_of_i[L.idx[a]] != -1) return 0;  // repeated input parameter: general path
+        ilike_of_i[L.idx[a]] = a;
+    }
+    bool tri = true;
+    for (int j = 0; j < D; ++j)
+        if (ilike_of_i[h->i_of_j[j]] != j) tri = false;
+    StreamPackDesc P;
+    memset(&P, 0, sizeof(P));
+    P.NT = NT; P.DP = DP; P.n_modes = nm; P.tri_like = tri ? 1 : 0;
+    P.blocks_T = NT * (NT + 1) / 2;
+    P.blocks_A = tri ? P.blocks_T : NT * NT;
+    int o = 0;
+    auto take = [&](int n) { int r = o; o += (n + 1) & ~1; return r; };
+    P.off_T = take(P.blocks_T * 64);
+    P.off_A = take(nm * P.blocks_A * 64);
+    P.off_mu = take(nm * DP);
+    P.off_c0 = take(nm);
+    P.off_w = take(nm);
+    P.off_lower = take(DP); P.off_upper = take(DP); P.off_loc = take(DP);
+    P.off_mls = take(DP); P.off_isc = take(DP); P.off_pa = take(DP); P.off_pb = take(DP);
+    P.off_kind = take(DP);
+    P.off_d1 = take(h->n_blocks * DP);
+    P.off_w1 = take(h->n_blocks * nm * DP);
+    P.total = o;
+    {
+        bool ident = (D == DP);
+        for (int j = 0; j < D; ++j) ident = ident && (h->i_of_j[j] == j);
+        P.iofj_identity = ident ? 1 : 0;
+    }
+    std::vector<double> pk(P.total, 0.0);
+    std::vector<double> Tm((size_t)DP * DP, 0.0), Am((size_t)DP * DP, 0.0);
+    for (int j = 0; j < D; ++j)
+        for (int k = 0; k <= j; ++k) Tm[(size_t)j * DP + k] = h->Trow[(size_t)j * D + k];
+    pack_frag(pk, P.off_T, Tm, DP, NT, true);
+    for (int km = 0; km < nm; ++km) {
+        std::fill(Am.begin(), Am.end(), 0.0);
+        for (int a = 0; a < D; ++a)
+            for (int j = 0; j < D; ++j) {
+                const int il = ilike_of_i[h->i_of_j[j]];
+                Am[(size_t)a * DP + j] = L.linvT[(size_t)km * D * D + (size_t)il * D + a];
+            }
+        pack_frag(pk, P.off_A + (size_t)km * P.blocks_A * 64, Am, DP, NT, tri);
+        for (int j = 0; j < D; ++j)
+            pk[P.off_mu + km * DP + j] = L.means[(size_t)km * D + ilike_of_i[h->i_of_j[j]]];
+        pk[P.off_c0 + km] = L.c0[km];
+        pk[P.off_w + km] = L.w[km];
+        // 1-parameter blocks: delta = T[:, j0] (RandProposer1D, proposal.py:86-93) and its image
+        for (int b = 0; b < h->n_blocks; ++b) {
+            if (h->bsize[b] != 1) continue;
+            const int j0 = h->jstart[b];
+            for (int j = 0; j < D; ++j) pk[P.off_d1 + (size_t)b * DP + j] = Tm[(size_t)j * DP + j0];
+            for (int a = 0; a < D; ++a) {
+                double acc = 0.0;
+                for (int j = 0; j < D; ++j) acc += Am[(size_t)a * DP + j] * Tm[(size_t)j * DP + j0];
+                pk[P.off_w1 + ((size_t)b * nm + km) * DP + a] = acc;
+            }
+        }
+    }
+    int32_t *ikind = reinterpret_cast<int32_t *>(pk.data() + P.off_kind);
+    for (int j = 0; j < DP; ++j) {
+        if (j < D) {
+            const int i = h->i_of_j[j];
+            pk[P.off_lower + j] = h->lower[i];
+            pk[P.off_upper + j] = h->upper[i];
+            pk[P.off_loc + j] = h->loc[i];
+            pk[P.off_isc + j] = h->pscale[i];
+            const int kd = h->prior_kind[i];
+            pk[P.off_mls + j] = (kd == 1) ? (-std::log(h->pscale[i]) - CB2_LOG_2PI / 2)
+                                : (kd >= 2 ? h->pcn[i] : 0.0);
+            pk[P.off_pa + j] = kd >= 2 ? h->pa[i] : 0.0;
+            pk[P.off_pb + j] = kd >= 2 ? h->pb[i] : 0.0;
+            ikind[2 * j] = kd;
+            ikind[2 * j + 1] = i;
+        } else {
+            pk[P.off_lower + j] = -INFINITY;
+            pk[P.off_upper + j] = INFINITY;
+            pk[P.off_isc + j] = 1.0;
+            ikind[2 * j] = 0;
+            ikind[2 * j + 1] = -1;
+        }
+    }
+    int rc = upload(h, h->d_streampack, pk);
+    if (rc) return rc;
+    h->stream_desc = P;
+    h->stream_ready = true;
+    return 0;
+}

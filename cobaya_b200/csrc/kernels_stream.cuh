@@ -1,0 +1,455 @@
+// kernels_stream.cuh -- the "streamed" Metropolis path for 64 < D <= 128 (sm_100a).
+//
+// By linearity of the proposal map and of the Gaussian's whitening map, everything on the
+// proposal side of a Metropolis step (mcmc.py:545-562) is independent of the chain state:
+//     delta_k = T (D o H)[:, k]          (proposal.py:224, unit radius)
+//     w_k^m   = L_m^-1 P delta_k          (gaussian_mixture.py:148, per mixture mode m)
+// for every direction k of every Haar basis of a window.  They are formed as batched matrix
+// products on the FP64 tensor pipe, 8 directions per warp as the M dimension of m8n8k4 DMMA
+// tiles (k_stream_products), and streamed once through HBM.  The accept chain itself
+// (k_stream_accept, one warp per chain, lanes over coordinates) only needs
+//     x' = x + r delta_k,   y'_m = y_m + r w_k^m,   |y'_m|^2,
+// bounds and 1-D priors of x', the Metropolis test (mcmc.py:670-683) and the bookkeeping /
+// row store (mcmc.py:685-748): O(D) work and 8 D (1 + modes) bytes per proposal, HBM-bound.
+// y_m = L_m^-1 P (x - mu_m) is recomputed from x at every window start (k_stream_whiten).
+// Unlike the register-resident kernels of kernels_fast.cuh nothing here is limited by the
+// registers one warp has for a D-vector, so the same three kernels cover any block layout
+// and up to 4 mixture modes.
+#pragma once
+#include "kernels_fast.cuh"
+
+#define CB2_STREAM_MAX_D 128
+#define CB2_STREAM_MAX_MODES 4
+
+struct StreamPackDesc {
+    int NT, DP;       // DP = 8 NT >= D (block-sorted coordinates, zero padded)
+    int n_modes;
+    int tri_like;     // L^-1 P lower-triangular in sorted coordinates
+    int blocks_T, blocks_A;
+    int off_T;        // fragment-ordered T (lower-triangular blocks), see warp_matvec8
+    int off_A;        // fragment-ordered L_m^-1 P per mode
+    int off_mu;       // [modes][DP]
+    int off_c0, off_w;                                    // [modes]
+    int off_lower, off_upper, off_loc, off_mls, off_isc, off_pa, off_pb;  // [DP]
+    int off_kind;     // [DP] int32 pairs {prior kind, sampler index i_of_j (or -1)}
+    int off_d1;       // [n_blocks][DP]        delta of a 1-parameter block: T[:, j0]
+    int off_w1;       // [n_blocks][modes][DP] its whitened images
+    int iofj_identity;
+    int total;
+};
+
+static inline bool stream_step_supported(const ModelDev &M, size_t n_likes) {
+    if (M.drag || M.D > CB2_STREAM_MAX_D || n_likes != 1 || M.any_periodic) return false;
+    const LikeDev &L = M.likes[0];
+    if (L.kind != 0 || L.dim != M.D || L.derived) return false;
+    return L.n_modes <= CB2_STREAM_MAX_MODES;
+}
+
+// out[nt] += sum over column blocks m in [m_lo, m_hi] of Mat(nt, m) a[m]; B fragments come
+// from global memory (shared by every warp of the GPU: L1/L2 resident), 4 tiles per batch.
+template <int NT, bool TRI>
+__device__ __forceinline__ void warp_matvec8_g(const double *__restrict__ frag, int lane,
+                                               const double (&a)[NT][2], double (&out)[NT][2],
+                                               int m_lo, int m_hi) {
+    const double2 *f2 = reinterpret_cast<const double2 *>(frag) + lane;
+#pragma unroll
+    for (int m = 0; m < NT; ++m) {
+        if (m < m_lo || m > m_hi) continue;  // warp-uniform
+#pragma unroll
+        for (int n0 = TRI ? (m & ~3) : 0; n0 < NT; n0 += 4) {
+            double2 b[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int nt = n0 + u;
+                if (nt < NT && (!TRI || nt >= m)) {
+                    const int blk = TRI ? (nt * (nt + 1)) / 2 + m : nt * NT + m;
+                    b[u] = __ldg(f2 + blk * 32);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int nt = n0 + u;
+                if (nt < NT && (!TRI || nt >= m)) dmma8x8x4(out[nt][0], out[nt][1], a[m][0], b[u].x);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int nt = n0 + u;
+                if (nt < NT && (!TRI || nt >= m)) dmma8x8x4(out[nt][0], out[nt][1], a[m][1], b[u].y);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// k_stream_products: one warp per 8 directions of one stored basis (task = chain x epoch).
+//   basis : [task][k][n_b]      (k_basis_wy / k_basis_general store, R[:, k] contiguous)
+//   delta : [task][k][DP]       T (R[:, k] placed at sorted coordinates j0 .. j0 + n_b)
+//   wout  : [task][k][modes][DP]
+// ---------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(256, 1)
+k_stream_products(const double *__restrict__ pack, StreamPackDesc P, const double *__restrict__ basis,
+                  int n_b, int j0, int64_t n_tasks, double *__restrict__ delta,
+                  double *__restrict__ wout) {
+    constexpr int DP = NT * 8;
+    const int lane = threadIdx.x & 31, q = lane >> 2, r = lane & 3;
+    const int kgroups = (n_b + 7) >> 3;
+    const int64_t wt = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (wt >= n_tasks * kgroups) return;
+    const int64_t task = wt / kgroups;
+    const int k = (int)(wt % kgroups) * 8 + q;
+    const bool kvalid = k < n_b;
+    const double *Rk = basis + ((size_t)task * n_b + (kvalid ? k : 0)) * (size_t)n_b;
+    const bool vec = ((n_b | j0) & 1) == 0;
+    double un[NT][2];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+        const int j = 8 * n + 2 * r - j0;
+        un[n][0] = 0.0;
+        un[n][1] = 0.0;
+        if (kvalid) {
+            if (vec) {
+                if (j >= 0 && j < n_b) {
+                    const double2 v2 = __ldg(reinterpret_cast<const double2 *>(Rk + j));
+                    un[n][0] = v2.x;
+                    un[n][1] = v2.y;
+                }
+            } else {
+                if (j >= 0 && j < n_b) un[n][0] = __ldg(Rk + j);
+                if (j + 1 >= 0 && j + 1 < n_b) un[n][1] = __ldg(Rk + j + 1);
+            }
+        }
+    }
+    const int m_lo = j0 >> 3, m_hi = (j0 + n_b - 1) >> 3;
+    double dl[NT][2];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) { dl[n][0] = 0.0; dl[n][1] = 0.0; }
+    warp_matvec8_g<NT, true>(pack + P.off_T, lane, un, dl, m_lo, m_hi);
+    const size_t row = (size_t)task * n_b + k;
+    if (kvalid) {
+        double2 *o = reinterpret_cast<double2 *>(delta + row * DP) + r;
+#pragma unroll
+        for (int n = 0; n < NT; ++n) o[4 * n] = make_double2(dl[n][0], dl[n][1]);
+    }
+    for (int km = 0; km < P.n_modes; ++km) {
+        double wv[NT][2];
+#pragma unroll
+        for (int n = 0; n < NT; ++n) { wv[n][0] = 0.0; wv[n][1] = 0.0; }
+        const double *Ak = pack + P.off_A + (size_t)km * P.blocks_A * 64;
+        // delta vanishes above the block (T is lower triangular in sorted coordinates)
+        if (P.tri_like) warp_matvec8_g<NT, true>(Ak, lane, dl, wv, m_lo, NT - 1);
+        else warp_matvec8_g<NT, false>(Ak, lane, dl, wv, m_lo, NT - 1);
+        if (kvalid) {
+            double2 *o = reinterpret_cast<double2 *>(wout + (row * P.n_modes + km) * DP) + r;
+#pragma unroll
+            for (int n = 0; n < NT; ++n) o[4 * n] = make_double2(wv[n][0], wv[n][1]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// k_stream_whiten: y_m = L_m^-1 P (x - mu_m) of every chain at window start, 8 chains per warp
+// on the tensor pipe.  ys : [chain][modes][DP]
+// ---------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(256, 1)
+k_stream_whiten(const double *__restrict__ pack, StreamPackDesc P, const double *__restrict__ x,
+                int D, int64_t n_chains, double *__restrict__ ys) {
+    constexpr int DP = NT * 8;
+    const int lane = threadIdx.x & 31, q = lane >> 2, r = lane & 3;
+    const int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (tile * 8 >= n_chains) return;
+    const int64_t chain_raw = tile * 8 + q;
+    const bool active = chain_raw < n_chains;
+    const int64_t chain = active ? chain_raw : n_chains - 1;
+    const int2 *kind = reinterpret_cast<const int2 *>(pack + P.off_kind);
+    double xs[NT][2];
+#pragma unroll
+    for (int n = 0; n < NT; ++n)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int i = __ldg(&kind[8 * n + 2 * r + h]).y;
+            xs[n][h] = (i >= 0) ? x[chain * D + i] : 0.0;
+        }
+    for (int km = 0; km < P.n_modes; ++km) {
+        const double *mu = pack + P.off_mu + km * DP;
+        double z[NT][2], y[NT][2];
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+            const double2 m2 = __ldg(reinterpret_cast<const double2 *>(mu + 8 * n + 2 * r));
+            z[n][0] = xs[n][0] - m2.x;
+            z[n][1] = xs[n][1] - m2.y;
+            y[n][0] = 0.0;
+            y[n][1] = 0.0;
+        }
+        const double *Ak = pack + P.off_A + (size_t)km * P.blocks_A * 64;
+        if (P.tri_like) warp_matvec8_g<NT, true>(Ak, lane, z, y, 0, NT - 1);
+        else warp_matvec8_g<NT, false>(Ak, lane, z, y, 0, NT - 1);
+        if (active) {
+            double2 *o = reinterpret_cast<double2 *>(ys + ((size_t)chain * P.n_modes + km) * DP) + r;
+#pragma unroll
+            for (int n = 0; n < NT; ++n) o[4 * n] = make_double2(y[n][0], y[n][1]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// k_stream_accept: the serial accept chain of a window, one warp per chain.  Lane l owns the
+// sorted coordinates l + 32 c, c < NC.
+// ---------------------------------------------------------------------------------------
+struct StreamWindow {
+    const double *delta[CB2_MAX_BLOCKS];  // per block (n_b >= 2): [task][k][DP]
+    const double *wv[CB2_MAX_BLOCKS];     // [task][k][modes][DP]
+};
+
+__device__ __forceinline__ double warp_sum_all(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int NC, int NM>
+__global__ void __launch_bounds__(128)
+k_stream_accept(ModelDev M, ChainState S, StreamWindow SW, const double *__restrict__ pack,
+                StreamPackDesc P, const double2 *__restrict__ draws,
+                const int2 *__restrict__ plan, const double *__restrict__ ys_in,
+                int64_t n_chains, int n_steps) {
+    const int lane = threadIdx.x & 31;
+    const int64_t chain = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (chain >= n_chains) return;
+    const int D = M.D, DP = P.DP;
+    const int2 *kind = reinterpret_cast<const int2 *>(pack + P.off_kind);
+    double xs[NC], ys[NM][NC], lo[NC], up[NC];
+    int iof[NC], knd[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        const int j = lane + 32 * c;
+        iof[c] = -1; knd[c] = 0; xs[c] = 0.0; lo[c] = -CUDART_INF; up[c] = CUDART_INF;
+        if (j < DP) {
+            const int2 kk = __ldg(&kind[j]);
+            knd[c] = kk.x; iof[c] = kk.y;
+            lo[c] = __ldg(pack + P.off_lower + j);
+            up[c] = __ldg(pack + P.off_upper + j);
+            if (kk.y >= 0) xs[c] = S.x[chain * D + kk.y];
+        }
+#pragma unroll
+        for (int m = 0; m < NM; ++m)
+            ys[m][c] = (j < DP && m < P.n_modes) ? ys_in[((size_t)chain * P.n_modes + m) * DP + j] : 0.0;
+    }
+    double logpost = S.logpost[chain], logprior = S.logprior[chain], loglike = S.ll[chain];
+    long long weight = S.weight[chain], prior_rej = S.prior_rej[chain],
+              burn_left = S.burn_left[chain], added_w = S.added_w[chain],
+              n_rows = S.n_rows[chain], n_acc = S.n_acc[chain];
+    uint32_t flags = 0;
+    const double2 *my_draws = draws + chain * (int64_t)n_steps;
+    const int2 *my_plan = plan + chain * (int64_t)n_steps;
+    const bool temp_one = M.temperature == 1.0;
+
+    // the proposal-side vectors of step s + 1 are loaded during step s
+    double dn[NC], wn[NM][NC];
+    double2 dr;
+    auto fetch = [&](int s) {
+        const int2 pl = __ldg(my_plan + s);
+        dr = __ldg(my_draws + s);
+        const int b = pl.y;
+        const double *dp, *wp;
+        if (M.bsize[b] >= 2) {
+            dp = SW.delta[b] + (size_t)pl.x * DP;
+            wp = SW.wv[b] + (size_t)pl.x * P.n_modes * DP;
+        } else {
+            dp = pack + P.off_d1 + (size_t)b * DP;
+            wp = pack + P.off_w1 + (size_t)b * P.n_modes * DP;
+        }
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const int j = lane + 32 * c;
+            dn[c] = (j < DP) ? __ldg(dp + j) : 0.0;
+#pragma unroll
+            for (int m = 0; m < NM; ++m)
+                wn[m][c] = (j < DP && m < P.n_modes) ? __ldg(wp + (size_t)m * DP + j) : 0.0;
+        }
+    };
+    fetch(0);
+    for (int s = 0; s < n_steps; ++s) {
+        const double rs = dr.x * M.proposal_scale, e_acc = dr.y;
+        double dl[NC], wl[NM][NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            dl[c] = dn[c];
+#pragma unroll
+            for (int m = 0; m < NM; ++m) wl[m][c] = wn[m][c];
+        }
+        if (s + 1 < n_steps) fetch(s + 1);
+        // ---- trial point, bounds and priors (prior.py:733-763)
+        bool bad = false;
+        double ps = 0.0, qs[NM];
+#pragma unroll
+        for (int m = 0; m < NM; ++m) qs[m] = 0.0;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const double xt = fma(rs, dl[c], xs[c]);
+            if (!(xt <= up[c]) || !(xt >= lo[c]) || !isfinite(xt)) bad = true;
+            if (M.any_normal && knd[c] != 0) {
+                const int j = lane + 32 * c;
+                const double zz = (xt - __ldg(pack + P.off_loc + j)) / __ldg(pack + P.off_isc + j);
+                if (knd[c] == 1) ps += __ldg(pack + P.off_mls + j) - zz * zz / 2;
+                else ps += __ldg(pack + P.off_mls + j) +
+                           prior1d_shape(knd[c], zz, __ldg(pack + P.off_pa + j),
+                                         __ldg(pack + P.off_pb + j));
+            }
+            dl[c] = xt;  // keep the trial coordinates
+#pragma unroll
+            for (int m = 0; m < NM; ++m) {
+                const double yt = fma(rs, wl[m][c], ys[m][c]);
+                qs[m] = fma(yt, yt, qs[m]);
+                wl[m][c] = yt;
+            }
+        }
+        bad = __any_sync(0xffffffffu, bad);
+        if (M.any_normal) ps = warp_sum_all(ps);
+        const double t_prior = bad ? -CUDART_INF : (M.uniform_logp + ps);
+        // ---- GaussianMixture.logp (gaussian_mixture.py:138-163)
+        double t_like;
+        {
+            double lp[NM];
+#pragma unroll
+            for (int m = 0; m < NM; ++m)
+                lp[m] = (m < P.n_modes)
+                            ? -0.5 * (__ldg(pack + P.off_c0 + m) + warp_sum_all(qs[m]))
+                            : -CUDART_INF;
+            if (NM == 1 || P.n_modes == 1) t_like = lp[0];
+            else {
+                double mx = lp[0];
+#pragma unroll
+                for (int m = 1; m < NM; ++m) mx = fmax(mx, lp[m]);
+                if (mx == -CUDART_INF) t_like = -CUDART_INF;
+                else {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int m = 0; m < NM; ++m)
+                        if (m < P.n_modes) acc += __ldg(pack + P.off_w + m) * exp(lp[m] - mx);
+                    t_like = log(acc) + mx;
+                }
+            }
+        }
+        const double t_post = bad ? -CUDART_INF : (t_prior + t_like);
+        // ---- metropolis_accept (mcmc.py:670-683)
+        bool acc;
+        if (t_post == -CUDART_INF) acc = false;
+        else if (t_post > logpost) acc = true;
+        else {
+            const double dlp = logpost - t_post;
+            acc = e_acc > (temp_one ? dlp : dlp / M.temperature);
+        }
+        // ---- process_accept_or_reject (mcmc.py:685-748); the whole warp is one chain
+        if (acc) {
+            if (burn_left <= 0) {
+                long long wst = weight;
+                bool store = true;
+                if (M.output_thin > 1) {
+                    added_w += weight;
+                    if (added_w >= M.output_thin) {
+                        wst = added_w / M.output_thin;
+                        added_w %= M.output_thin;
+                    } else store = false;
+                }
+                if (store) {
+                    if (n_rows >= S.cap) flags |= CB2_FLAG_ROWS_FULL;
+                    else {
+                        double *row = S.rows + ((size_t)chain * S.cap + n_rows) * M.width;
+                        if (lane == 0) {
+                            row[0] = (double)wst;
+                            row[1] = temp_one ? -logpost : -(logpost / M.temperature);
+                        } else if (lane == 1) {
+                            row[2 + D] = -logprior;
+                            row[3 + D] = -logprior;
+                        } else if (lane == 2) {
+                            row[4 + D] = -2 * loglike;
+                            row[5 + D] = -2 * loglike;
+                        }
+#pragma unroll
+                        for (int c = 0; c < NC; ++c)
+                            if (iof[c] >= 0) row[2 + iof[c]] = xs[c];
+                        n_rows += 1;
+                    }
+                }
+            } else burn_left -= 1;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                xs[c] = dl[c];
+#pragma unroll
+                for (int m = 0; m < NM; ++m) ys[m][c] = wl[m][c];
+            }
+            logpost = t_post; logprior = t_prior; loglike = t_like;
+            weight = 1; prior_rej = 0; n_acc += 1;
+        } else {
+            weight += 1;
+            if (t_prior == -CUDART_INF) prior_rej += 1;
+            const long long sgn = (burn_left > 0) - (burn_left < 0);
+            if (weight - prior_rej > M.max_tries * (1 + 9 * sgn)) flags |= CB2_FLAG_STUCK;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+        if (iof[c] >= 0) S.x[chain * D + iof[c]] = xs[c];
+    if (lane == 0) {
+        S.logpost[chain] = logpost; S.logprior[chain] = logprior; S.ll[chain] = loglike;
+        S.weight[chain] = weight; S.prior_rej[chain] = prior_rej;
+        S.burn_left[chain] = burn_left; S.added_w[chain] = added_w;
+        S.n_rows[chain] = n_rows; S.n_acc[chain] = n_acc;
+        if (flags) atomicOr(&S.flags[chain], flags);
+    }
+}
+
+// ---------------------------------------------------------------- launchers
+static int launch_stream_products(cudaStream_t st, const double *pack, const StreamPackDesc &P,
+                                  const double *basis, int n_b, int j0, int64_t n_tasks,
+                                  double *delta, double *wout) {
+    const int64_t wts = n_tasks * ((n_b + 7) / 8);
+    const unsigned grid = (unsigned)((wts + 7) / 8);
+#define CB2_SP(N)                                                                            \
+    case N:                                                                                  \
+        k_stream_products<N><<<grid, 256, 0, st>>>(pack, P, basis, n_b, j0, n_tasks, delta,  \
+                                                   wout);                                    \
+        break;
+    switch (P.NT) {
+        CB2_SP(9) CB2_SP(10) CB2_SP(11) CB2_SP(12) CB2_SP(13) CB2_SP(14) CB2_SP(15) CB2_SP(16)
+        default: return -1;
+    }
+#undef CB2_SP
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+static int launch_stream_whiten(cudaStream_t st, const double *pack, const StreamPackDesc &P,
+                                const double *x, int D, int64_t n_chains, double *ys) {
+    const int64_t tiles = (n_chains + 7) / 8;
+    const unsigned grid = (unsigned)((tiles + 7) / 8);
+#define CB2_SW(N)                                                                        \
+    case N:                                                                              \
+        k_stream_whiten<N><<<grid, 256, 0, st>>>(pack, P, x, D, n_chains, ys);           \
+        break;
+    switch (P.NT) {
+        CB2_SW(9) CB2_SW(10) CB2_SW(11) CB2_SW(12) CB2_SW(13) CB2_SW(14) CB2_SW(15) CB2_SW(16)
+        default: return -1;
+    }
+#undef CB2_SW
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+static int launch_stream_accept(cudaStream_t st, const ModelDev &M, const ChainState &S,
+                                const StreamWindow &SW, const double *pack,
+                                const StreamPackDesc &P, const double2 *draws, const int2 *plan,
+                                const double *ys, int64_t n_chains, int n_steps) {
+    const unsigned grid = (unsigned)((n_chains + 3) / 4);
+    const int NC = (P.DP + 31) / 32;
+    const int NM = P.n_modes == 1 ? 1 : (P.n_modes == 2 ? 2 : 4);
+#define CB2_SA(C_, M_)                                                                      \
+    if (NC == C_ && NM == M_) {                                                             \
+        k_stream_accept<C_, M_><<<grid, 128, 0, st>>>(M, S, SW, pack, P, draws, plan, ys,   \
+                                                      n_chains, n_steps);                   \
+        return cudaGetLastError() == cudaSuccess ? 0 : -2;                                  \
+    }
+    CB2_SA(3, 1) CB2_SA(3, 2) CB2_SA(3, 4) CB2_SA(4, 1) CB2_SA(4, 2) CB2_SA(4, 4)
+#undef CB2_SA
+    return -1;
+}

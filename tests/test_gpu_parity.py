@@ -376,6 +376,8 @@ def test_config5_dimension_sweep_parity(cuda_lib, D, n):
     eng = _engine(fm, C, seed=D, chain_id0=3, rows_cap=n)
     eng.set_state(x0)
     eng.advance(n)
+    # D <= 64: producer/consumer DMMA kernel; D <= 128: streamed kernels; else general
+    assert eng.last_step_kernel() == (2 if D <= 64 else (3 if D <= 128 else 0))
     st = eng.get_state()
     ref = _oracle_rows(fm, D, range(3, 3 + C), x0, n, 0)
     for c in range(C):
@@ -384,6 +386,48 @@ def test_config5_dimension_sweep_parity(cuda_lib, D, n):
         assert rows.shape == rows_ref.shape
         np.testing.assert_allclose(rows, rows_ref, rtol=RTOL, atol=ATOL)
         np.testing.assert_allclose(st["x"][c], s_ref["x"], rtol=RTOL, atol=ATOL)
+
+
+def test_streamed_kernels_blocks_modes_priors(cuda_lib):
+    """The streamed path (k_stream_products / k_stream_whiten / k_stream_accept) for
+    64 < D <= 128: three blocks (one of a single parameter) with oversampling and thinning,
+    a 3-mode mixture over permuted parameters, a normal and a scipy-family prior, burn-in and
+    temperature, several advance calls that cut windows inside proposal cycles."""
+    from cobaya_b200.flatmodel import FlatModel, LikeSpec
+
+    rng = np.random.default_rng(11)
+    D = 100
+    covs = [_mixture_cov(D, rng, scale=0.05) for _ in range(3)]
+    means = [rng.uniform(-0.05, 0.05, D) for _ in range(3)]
+    lk = LikeSpec.gaussian_mixture(rng.permutation(D), means, covs, weights=[0.5, 0.3, 0.2])
+    kind = np.zeros(D, np.int32); kind[3] = 1
+    lower = np.full(D, -1.0); upper = np.full(D, 1.0)
+    lower[3], upper[3] = -np.inf, np.inf
+    sc = np.ones(D); sc[3] = 0.3
+    perm = list(rng.permutation(D))
+    blocks = [[int(perm[0])], [int(v) for v in perm[1:41]], [int(v) for v in perm[41:]]]
+    fm = FlatModel(names=[f"p{i}" for i in range(D)], prior_kind=kind, lower=lower, upper=upper,
+                   loc=np.zeros(D), pscale=sc, periodic=np.zeros(D, np.int32), likes=[lk],
+                   blocks=blocks, oversampling=[1, 2, 3],
+                   proposal_cov=np.diag(np.full(D, 0.03**2)), temperature=1.5, output_thin=2)
+    C, n = 6, 640
+    x0 = rng.uniform(-0.02, 0.02, (C, D))
+    eng = _engine(fm, C, seed=17, chain_id0=900, rows_cap=n, burn_in=3)
+    eng.set_state(x0)
+    for k in (1, 130, 258, 251):
+        eng.advance(k)
+    assert eng.last_step_kernel() == 3
+    st = eng.get_state()
+    assert not st["flags"].any()
+    ref = _oracle_rows(fm, 17, range(900, 900 + C), x0, n, 3)
+    for c in range(C):
+        rc, rows_ref, s_ref = ref[c]
+        rows = eng.rows(c)
+        assert rows.shape == rows_ref.shape, f"chain {c}"
+        np.testing.assert_array_equal(rows[:, 0], rows_ref[:, 0])
+        np.testing.assert_allclose(rows, rows_ref, rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(st["x"][c], s_ref["x"], rtol=RTOL, atol=ATOL)
+        assert st["weight"][c] == s_ref["weight"]
 
 
 def test_producer_consumer_kernel_blocks_normal_prior_thinning(cuda_lib):

@@ -17,7 +17,7 @@ import numpy as np
 from cobaya_b200.engine import Engine
 from cobaya_b200.flatmodel import FlatModel, synthetic_gaussian_cov
 
-KERNEL = {0: "general", 1: "dmma", 2: "dmma-producer-consumer"}
+KERNEL = {0: "general", 1: "dmma", 2: "dmma-producer-consumer", 3: "dmma-streamed"}
 
 
 def peaks():
