@@ -121,19 +121,43 @@ static int pack_stream(cb2_engine *h) {
     h->stream_ready = false;
     if (h->D <= 64 || !stream_step_supported(h->M, h->likes.size())) return 0;
     const int D = h->D, NT = (D + 7) / 8, DP = 8 * NT;
-    const LikeHost &L = h->likes[0];
-    const int nm = L.d.n_modes;
-    std::vector<int> ilike_of_i(D, -1);
-    for (int a = 0; a < D; ++a) {
-        if (ilike_of_i[L.idx[a]] != -1) return 0;  // repeated input parameter: general path
-        ilike_of_i[L.idx[a]] = a;
+    const int NL = (int)h->likes.size();
+    // whitened coordinate a = aoff[l] + a' for component l; every sampled parameter must be
+    // an input of exactly one component
+    std::vector<int> like_of_i(D, -1), il_of_i(D, -1), aoff(NL + 1, 0);
+    int nm = 1;
+    for (int l = 0; l < NL; ++l) {
+        const LikeHost &L = h->likes[l];
+        aoff[l + 1] = aoff[l] + L.d.dim;
+        nm = std::max(nm, (int)L.d.n_modes);
+        for (int a = 0; a < L.d.dim; ++a) {
+            if (like_of_i[L.idx[a]] != -1) return 0;  // shared / repeated parameter: general path
+            like_of_i[L.idx[a]] = l;
+            il_of_i[L.idx[a]] = a;
+        }
     }
-    bool tri = true;
-    for (int j = 0; j < D; ++j)
-        if (ilike_of_i[h->i_of_j[j]] != j) tri = false;
+    for (int i = 0; i < D; ++i)
+        if (like_of_i[i] < 0) return 0;
     StreamPackDesc P;
     memset(&P, 0, sizeof(P));
-    P.NT = NT; P.DP = DP; P.n_modes = nm; P.tri_like = tri ? 1 : 0;
+    P.NT = NT; P.DP = DP; P.n_modes = nm; P.n_like = NL;
+    for (int l = 0; l < NL; ++l) P.like_modes[l] = h->likes[l].d.n_modes;
+    // embedded matrices A^m[a][j] (block diagonal over the components); a component with
+    // fewer modes repeats its last one (never read by the accept kernel)
+    std::vector<std::vector<double>> Am(nm, std::vector<double>((size_t)DP * DP, 0.0));
+    bool tri = true;
+    for (int km = 0; km < nm; ++km)
+        for (int j = 0; j < D; ++j) {
+            const int i = h->i_of_j[j], l = like_of_i[i], il = il_of_i[i];
+            const LikeHost &L = h->likes[l];
+            const int d = L.d.dim, kl = std::min(km, (int)L.d.n_modes - 1);
+            for (int a = 0; a < d; ++a) {
+                const double v = L.linvT[(size_t)kl * d * d + (size_t)il * d + a];
+                Am[km][(size_t)(aoff[l] + a) * DP + j] = v;
+                if (aoff[l] + a < j && v != 0.0) tri = false;
+            }
+        }
+    P.tri_like = tri ? 1 : 0;
     P.blocks_T = NT * (NT + 1) / 2;
     P.blocks_A = tri ? P.blocks_T : NT * NT;
     int o = 0;
@@ -141,8 +165,9 @@ static int pack_stream(cb2_engine *h) {
     P.off_T = take(P.blocks_T * 64);
     P.off_A = take(nm * P.blocks_A * 64);
     P.off_mu = take(nm * DP);
-    P.off_c0 = take(nm);
-    P.off_w = take(nm);
+    P.off_c0 = take(CB2_STREAM_MAX_LIKES * CB2_STREAM_MAX_MODES);
+    P.off_w = take(CB2_STREAM_MAX_LIKES * CB2_STREAM_MAX_MODES);
+    P.off_likeof = take(DP / 2 + 1);
     P.off_lower = take(DP); P.off_upper = take(DP); P.off_loc = take(DP);
     P.off_mls = take(DP); P.off_isc = take(DP); P.off_pa = take(DP); P.off_pb = take(DP);
     P.off_kind = take(DP);
@@ -155,22 +180,18 @@ static int pack_stream(cb2_engine *h) {
         P.iofj_identity = ident ? 1 : 0;
     }
     std::vector<double> pk(P.total, 0.0);
-    std::vector<double> Tm((size_t)DP * DP, 0.0), Am((size_t)DP * DP, 0.0);
+    std::vector<double> Tm((size_t)DP * DP, 0.0);
     for (int j = 0; j < D; ++j)
         for (int k = 0; k <= j; ++k) Tm[(size_t)j * DP + k] = h->Trow[(size_t)j * D + k];
     pack_frag(pk, P.off_T, Tm, DP, NT, true);
     for (int km = 0; km < nm; ++km) {
-        std::fill(Am.begin(), Am.end(), 0.0);
-        for (int a = 0; a < D; ++a)
-            for (int j = 0; j < D; ++j) {
-                const int il = ilike_of_i[h->i_of_j[j]];
-                Am[(size_t)a * DP + j] = L.linvT[(size_t)km * D * D + (size_t)il * D + a];
-            }
-        pack_frag(pk, P.off_A + (size_t)km * P.blocks_A * 64, Am, DP, NT, tri);
-        for (int j = 0; j < D; ++j)
-            pk[P.off_mu + km * DP + j] = L.means[(size_t)km * D + ilike_of_i[h->i_of_j[j]]];
-        pk[P.off_c0 + km] = L.c0[km];
-        pk[P.off_w + km] = L.w[km];
+        pack_frag(pk, P.off_A + (size_t)km * P.blocks_A * 64, Am[km], DP, NT, tri);
+        for (int j = 0; j < D; ++j) {
+            const int i = h->i_of_j[j], l = like_of_i[i];
+            const LikeHost &L = h->likes[l];
+            const int kl = std::min(km, (int)L.d.n_modes - 1);
+            pk[P.off_mu + km * DP + j] = L.means[(size_t)kl * L.d.dim + il_of_i[i]];
+        }
         // 1-parameter blocks: delta = T[:, j0] (RandProposer1D, proposal.py:86-93) and its image
         for (int b = 0; b < h->n_blocks; ++b) {
             if (h->bsize[b] != 1) continue;
@@ -178,9 +199,20 @@ static int pack_stream(cb2_engine *h) {
             for (int j = 0; j < D; ++j) pk[P.off_d1 + (size_t)b * DP + j] = Tm[(size_t)j * DP + j0];
             for (int a = 0; a < D; ++a) {
                 double acc = 0.0;
-                for (int j = 0; j < D; ++j) acc += Am[(size_t)a * DP + j] * Tm[(size_t)j * DP + j0];
+                for (int j = 0; j < D; ++j)
+                    acc += Am[km][(size_t)a * DP + j] * Tm[(size_t)j * DP + j0];
                 pk[P.off_w1 + ((size_t)b * nm + km) * DP + a] = acc;
             }
+        }
+    }
+    int32_t *ilikeof = reinterpret_cast<int32_t *>(pk.data() + P.off_likeof);
+    for (int a = 0; a < DP; ++a) ilikeof[a] = -1;
+    for (int l = 0; l < NL; ++l) {
+        const LikeHost &L = h->likes[l];
+        for (int a = aoff[l]; a < aoff[l + 1]; ++a) ilikeof[a] = l;
+        for (int km = 0; km < (int)L.d.n_modes; ++km) {
+            pk[P.off_c0 + l * CB2_STREAM_MAX_MODES + km] = L.c0[km];
+            pk[P.off_w + l * CB2_STREAM_MAX_MODES + km] = L.w[km];
         }
     }
     int32_t *ikind = reinterpret_cast<int32_t *>(pk.data() + P.off_kind);

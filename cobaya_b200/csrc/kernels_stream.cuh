@@ -3,7 +3,9 @@
 // By linearity of the proposal map and of the Gaussian's whitening map, everything on the
 // proposal side of a Metropolis step (mcmc.py:545-562) is independent of the chain state:
 //     delta_k = T (D o H)[:, k]          (proposal.py:224, unit radius)
-//     w_k^m   = L_m^-1 P delta_k          (gaussian_mixture.py:148, per mixture mode m)
+//     w_k^m   = L_m^-1 P delta_k          (gaussian_mixture.py:148, per mixture mode m; several
+//                                          components over disjoint parameters are embedded
+//                                          block-diagonally in one D x D matrix per mode)
 // for every direction k of every Haar basis of a window.  They are formed as batched matrix
 // products on the FP64 tensor pipe, 8 directions per warp as the M dimension of m8n8k4 DMMA
 // tiles (k_stream_products), and streamed once through HBM.  The accept chain itself
@@ -20,6 +22,7 @@
 
 #define CB2_STREAM_MAX_D 128
 #define CB2_STREAM_MAX_MODES 4
+#define CB2_STREAM_MAX_LIKES 3
 
 struct StreamPackDesc {
     int NT, DP;       // DP = 8 NT >= D (block-sorted coordinates, zero padded)
@@ -29,7 +32,10 @@ struct StreamPackDesc {
     int off_T;        // fragment-ordered T (lower-triangular blocks), see warp_matvec8
     int off_A;        // fragment-ordered L_m^-1 P per mode
     int off_mu;       // [modes][DP]
-    int off_c0, off_w;                                    // [modes]
+    int n_like;       // Gaussian-mixture components over disjoint parameter sets (<= 3)
+    int like_modes[CB2_STREAM_MAX_LIKES];
+    int off_c0, off_w;                                    // [like][CB2_STREAM_MAX_MODES]
+    int off_likeof;   // [DP] int32: component owning whitened coordinate a (-1: padding)
     int off_lower, off_upper, off_loc, off_mls, off_isc, off_pa, off_pb;  // [DP]
     int off_kind;     // [DP] int32 pairs {prior kind, sampler index i_of_j (or -1)}
     int off_d1;       // [n_blocks][DP]        delta of a 1-parameter block: T[:, j0]
@@ -38,11 +44,18 @@ struct StreamPackDesc {
     int total;
 };
 
+// one or more gaussian_mixture components (no derived parameters) whose input parameters
+// are disjoint and together cover all D sampled parameters (checked in pack_stream)
 static inline bool stream_step_supported(const ModelDev &M, size_t n_likes) {
-    if (M.drag || M.D > CB2_STREAM_MAX_D || n_likes != 1 || M.any_periodic) return false;
-    const LikeDev &L = M.likes[0];
-    if (L.kind != 0 || L.dim != M.D || L.derived) return false;
-    return L.n_modes <= CB2_STREAM_MAX_MODES;
+    if (M.drag || M.D > CB2_STREAM_MAX_D || M.any_periodic) return false;
+    if (n_likes < 1 || n_likes > CB2_STREAM_MAX_LIKES) return false;
+    int dims = 0;
+    for (size_t l = 0; l < n_likes; ++l) {
+        const LikeDev &L = M.likes[l];
+        if (L.kind != 0 || L.derived || L.n_modes > CB2_STREAM_MAX_MODES) return false;
+        dims += L.dim;
+    }
+    return dims == M.D;
 }
 
 // out[nt] += sum over column blocks m in [m_lo, m_hi] of Mat(nt, m) a[m]; B fragments come
@@ -208,7 +221,7 @@ __device__ __forceinline__ double warp_sum_all(double v) {
     return v;
 }
 
-template <int NC, int NM>
+template <int NC, int NM, int NL>
 __global__ void __launch_bounds__(128)
 k_stream_accept(ModelDev M, ChainState S, StreamWindow SW, const double *__restrict__ pack,
                 StreamPackDesc P, const double2 *__restrict__ draws,
@@ -219,12 +232,14 @@ k_stream_accept(ModelDev M, ChainState S, StreamWindow SW, const double *__restr
     if (chain >= n_chains) return;
     const int D = M.D, DP = P.DP;
     const int2 *kind = reinterpret_cast<const int2 *>(pack + P.off_kind);
+    const int *likeof = reinterpret_cast<const int *>(pack + P.off_likeof);
     double xs[NC], ys[NM][NC], lo[NC], up[NC];
-    int iof[NC], knd[NC];
+    int iof[NC], knd[NC], lko[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
         const int j = lane + 32 * c;
         iof[c] = -1; knd[c] = 0; xs[c] = 0.0; lo[c] = -CUDART_INF; up[c] = CUDART_INF;
+        lko[c] = (NL > 1 && j < DP) ? __ldg(&likeof[j]) : 0;
         if (j < DP) {
             const int2 kk = __ldg(&kind[j]);
             knd[c] = kk.x; iof[c] = kk.y;
@@ -236,7 +251,9 @@ k_stream_accept(ModelDev M, ChainState S, StreamWindow SW, const double *__restr
         for (int m = 0; m < NM; ++m)
             ys[m][c] = (j < DP && m < P.n_modes) ? ys_in[((size_t)chain * P.n_modes + m) * DP + j] : 0.0;
     }
-    double logpost = S.logpost[chain], logprior = S.logprior[chain], loglike = S.ll[chain];
+    double logpost = S.logpost[chain], logprior = S.logprior[chain], loglike[NL];
+#pragma unroll
+    for (int l = 0; l < NL; ++l) loglike[l] = S.ll[chain * NL + l];
     long long weight = S.weight[chain], prior_rej = S.prior_rej[chain],
               burn_left = S.burn_left[chain], added_w = S.added_w[chain],
               n_rows = S.n_rows[chain], n_acc = S.n_acc[chain];
@@ -282,9 +299,11 @@ k_stream_accept(ModelDev M, ChainState S, StreamWindow SW, const double *__restr
         if (s + 1 < n_steps) fetch(s + 1);
         // ---- trial point, bounds and priors (prior.py:733-763)
         bool bad = false;
-        double ps = 0.0, qs[NM];
+        double ps = 0.0, qs[NL][NM];
 #pragma unroll
-        for (int m = 0; m < NM; ++m) qs[m] = 0.0;
+        for (int l = 0; l < NL; ++l)
+#pragma unroll
+            for (int m = 0; m < NM; ++m) qs[l][m] = 0.0;
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
             const double xt = fma(rs, dl[c], xs[c]);
@@ -301,36 +320,45 @@ k_stream_accept(ModelDev M, ChainState S, StreamWindow SW, const double *__restr
 #pragma unroll
             for (int m = 0; m < NM; ++m) {
                 const double yt = fma(rs, wl[m][c], ys[m][c]);
-                qs[m] = fma(yt, yt, qs[m]);
+                const double y2 = yt * yt;
                 wl[m][c] = yt;
+                // whitened coordinate a = lane + 32 c belongs to one component
+#pragma unroll
+                for (int l = 0; l < NL; ++l)
+                    if (NL == 1 || lko[c] == l) qs[l][m] += y2;
             }
         }
         bad = __any_sync(0xffffffffu, bad);
         if (M.any_normal) ps = warp_sum_all(ps);
         const double t_prior = bad ? -CUDART_INF : (M.uniform_logp + ps);
-        // ---- GaussianMixture.logp (gaussian_mixture.py:138-163)
-        double t_like;
-        {
+        // ---- GaussianMixture.logp (gaussian_mixture.py:138-163), one term per component
+        double t_ll[NL], t_like = 0.0;
+#pragma unroll
+        for (int l = 0; l < NL; ++l) {
+            const int nm = P.like_modes[l];
             double lp[NM];
 #pragma unroll
             for (int m = 0; m < NM; ++m)
-                lp[m] = (m < P.n_modes)
-                            ? -0.5 * (__ldg(pack + P.off_c0 + m) + warp_sum_all(qs[m]))
-                            : -CUDART_INF;
-            if (NM == 1 || P.n_modes == 1) t_like = lp[0];
+                lp[m] = (m < nm) ? -0.5 * (__ldg(pack + P.off_c0 + l * CB2_STREAM_MAX_MODES + m) +
+                                           warp_sum_all(qs[l][m]))
+                                 : -CUDART_INF;
+            if (NM == 1 || nm == 1) t_ll[l] = lp[0];
             else {
                 double mx = lp[0];
 #pragma unroll
                 for (int m = 1; m < NM; ++m) mx = fmax(mx, lp[m]);
-                if (mx == -CUDART_INF) t_like = -CUDART_INF;
+                if (mx == -CUDART_INF) t_ll[l] = -CUDART_INF;
                 else {
                     double acc = 0.0;
 #pragma unroll
                     for (int m = 0; m < NM; ++m)
-                        if (m < P.n_modes) acc += __ldg(pack + P.off_w + m) * exp(lp[m] - mx);
-                    t_like = log(acc) + mx;
+                        if (m < nm)
+                            acc += __ldg(pack + P.off_w + l * CB2_STREAM_MAX_MODES + m) *
+                                   exp(lp[m] - mx);
+                    t_ll[l] = log(acc) + mx;
                 }
             }
+            t_like += t_ll[l];
         }
         const double t_post = bad ? -CUDART_INF : (t_prior + t_like);
         // ---- metropolis_accept (mcmc.py:670-683)
@@ -364,8 +392,13 @@ k_stream_accept(ModelDev M, ChainState S, StreamWindow SW, const double *__restr
                             row[2 + D] = -logprior;
                             row[3 + D] = -logprior;
                         } else if (lane == 2) {
-                            row[4 + D] = -2 * loglike;
-                            row[5 + D] = -2 * loglike;
+                            double tot = 0.0;
+#pragma unroll
+                            for (int l = 0; l < NL; ++l) {
+                                tot += loglike[l];
+                                row[5 + D + l] = -2 * loglike[l];
+                            }
+                            row[4 + D] = -2 * tot;
                         }
 #pragma unroll
                         for (int c = 0; c < NC; ++c)
@@ -380,7 +413,9 @@ k_stream_accept(ModelDev M, ChainState S, StreamWindow SW, const double *__restr
 #pragma unroll
                 for (int m = 0; m < NM; ++m) ys[m][c] = wl[m][c];
             }
-            logpost = t_post; logprior = t_prior; loglike = t_like;
+            logpost = t_post; logprior = t_prior;
+#pragma unroll
+            for (int l = 0; l < NL; ++l) loglike[l] = t_ll[l];
             weight = 1; prior_rej = 0; n_acc += 1;
         } else {
             weight += 1;
@@ -393,7 +428,9 @@ k_stream_accept(ModelDev M, ChainState S, StreamWindow SW, const double *__restr
     for (int c = 0; c < NC; ++c)
         if (iof[c] >= 0) S.x[chain * D + iof[c]] = xs[c];
     if (lane == 0) {
-        S.logpost[chain] = logpost; S.logprior[chain] = logprior; S.ll[chain] = loglike;
+        S.logpost[chain] = logpost; S.logprior[chain] = logprior;
+#pragma unroll
+        for (int l = 0; l < NL; ++l) S.ll[chain * NL + l] = loglike[l];
         S.weight[chain] = weight; S.prior_rej[chain] = prior_rej;
         S.burn_left[chain] = burn_left; S.added_w[chain] = added_w;
         S.n_rows[chain] = n_rows; S.n_acc[chain] = n_acc;
@@ -443,13 +480,16 @@ static int launch_stream_accept(cudaStream_t st, const ModelDev &M, const ChainS
     const unsigned grid = (unsigned)((n_chains + 3) / 4);
     const int NC = (P.DP + 31) / 32;
     const int NM = P.n_modes == 1 ? 1 : (P.n_modes == 2 ? 2 : 4);
-#define CB2_SA(C_, M_)                                                                      \
-    if (NC == C_ && NM == M_) {                                                             \
-        k_stream_accept<C_, M_><<<grid, 128, 0, st>>>(M, S, SW, pack, P, draws, plan, ys,   \
-                                                      n_chains, n_steps);                   \
+    const int NL = P.n_like;
+#define CB2_SA(C_, M_, L_)                                                                  \
+    if (NC == C_ && NM == M_ && NL == L_) {                                                 \
+        k_stream_accept<C_, M_, L_><<<grid, 128, 0, st>>>(M, S, SW, pack, P, draws, plan,   \
+                                                          ys, n_chains, n_steps);           \
         return cudaGetLastError() == cudaSuccess ? 0 : -2;                                  \
     }
-    CB2_SA(3, 1) CB2_SA(3, 2) CB2_SA(3, 4) CB2_SA(4, 1) CB2_SA(4, 2) CB2_SA(4, 4)
+#define CB2_SA_L(C_, M_) CB2_SA(C_, M_, 1) CB2_SA(C_, M_, 2) CB2_SA(C_, M_, 3)
+    CB2_SA_L(3, 1) CB2_SA_L(3, 2) CB2_SA_L(3, 4) CB2_SA_L(4, 1) CB2_SA_L(4, 2) CB2_SA_L(4, 4)
+#undef CB2_SA_L
 #undef CB2_SA
     return -1;
 }

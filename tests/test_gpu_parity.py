@@ -317,7 +317,7 @@ def test_config3_128d_three_modes_two_speed_blocks(cuda_lib):
     eng.set_state(x0)
     eng.advance(333)
     eng.advance(n - 333)
-    assert eng.last_step_kernel() == 0  # D > 64: general kernel
+    assert eng.last_step_kernel() == 3  # 64 < D <= 128: streamed kernels, two components
     st = eng.get_state()
     assert not st["flags"].any()
     ref = _oracle_rows(fm, 4, range(8192 * 7, 8192 * 7 + C), x0, n, 0)
