@@ -49,6 +49,18 @@ def peaks():
 FP64_NOMINAL_TFLOPS = 37.0  # 148 SM x 64 FP64 FMA/clk x 2 x 1.965 GHz (nominal, HGX B200)
 
 
+def fp64_peak():
+    """FP64 datapath peak: tools/fp64_peak.cu (m8n8k4 DMMA, 32 warps/SM, 8 independent
+    accumulators) measured on this pool's B200s; nominal figure if the record is missing."""
+    p = os.path.join(ROOT, "profiles", "r1_fp64_peak.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["mma_m8n8k4_ilp8_w32"]["tflops"]), \
+                "measured (tools/fp64_peak.cu, profiles/r1_fp64_peak.json)"
+    except Exception:
+        return FP64_NOMINAL_TFLOPS, "nominal"
+
+
 def build_problem(seed=1):
     from cobaya_b200.flatmodel import FlatModel, synthetic_gaussian_cov
 
@@ -365,6 +377,7 @@ def run_gpu_arm(args):
         except Exception:
             traffic = None
     flops = 4 * D * D * C * locksteps * K / (hot_ms * 1e-3) / 1e12
+    fp64_pk, fp64_src = fp64_peak()
     cb = cpu_oracle_baseline(fm, cov) if not args.no_cpu_baseline else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
@@ -391,10 +404,11 @@ def run_gpu_arm(args):
                                        for k in kt},
                      "share_of_step": {k: kt[k]["ms"] / ms_dev for k in kt},
                      "proposals_per_step_launch": props_per_launch, "launches": n_l,
-                     "fp64": {"tflops": flops, "nominal_peak_tflops": FP64_NOMINAL_TFLOPS,
-                              "frac": flops / FP64_NOMINAL_TFLOPS,
+                     "fp64": {"tflops": flops, "peak_tflops": fp64_pk,
+                              "peak_source": fp64_src, "frac": flops / fp64_pk,
                               "flops_per_proposal": 4 * D * D,
-                              "note": "binding roof above D~23 (SURVEY.md 8d)"}},
+                              "note": "binding roof above D~23 (SURVEY.md 8d); DMMA and "
+                                      "vector FP64 share one datapath"}},
         "cpu_baseline": cb,
         "wall_s_timed_region": t_wall,
     }

@@ -23,6 +23,7 @@ rank) as closely as lock-step allows:
 from __future__ import annotations
 
 import datetime
+import os
 import logging
 import re
 from dataclasses import dataclass, field
@@ -294,8 +295,11 @@ class EnsembleMCMC:
         )
 
     def save_snapshot(self, path: str):
-        with open(path, "wb") as f:
+        """Written to a temporary name and renamed: a crash never leaves a torn snapshot."""
+        tmp = path + ".tmp"
+        with open(tmp, "wb") as f:
             np.savez(f, **self.snapshot())
+        os.replace(tmp, path)
 
     @staticmethod
     def load_snapshot(path: str) -> dict:
@@ -348,8 +352,10 @@ class EnsembleMCMC:
                 f"(rows_per_chain={self.rows_per_chain}); increase rows_per_chain.")
 
     # ------------------------------------------------------------------ run loop
-    def run(self, callback=None):
-        """MCMC.run (mcmc.py:451-528) for the ensemble."""
+    def run(self, callback=None, on_checkpoint=None):
+        """MCMC.run (mcmc.py:451-528) for the ensemble.  ``on_checkpoint(self)`` is called
+        after every convergence check (where the reference writes its checkpoint,
+        mcmc.py:1029-1032) -- the plugin uses it for the timed output of mcmc.py:473-481."""
         log.info("Sampling! (%d chains on %d GPU(s))", self.n_chains, self.dist.size)
         g = self._global_summary()
         while g["min_rows"] < self.max_samples and not self.converged:
@@ -362,6 +368,8 @@ class EnsembleMCMC:
             if self.check_ready(g):
                 self.check_convergence_and_learn_proposal()
                 self.i_learn += 1
+                if on_checkpoint is not None:
+                    on_checkpoint(self)
         if g["min_rows"] >= self.max_samples:
             log.info("Reached maximum number of accepted steps allowed (%s). Stopping.",
                      self.max_samples)

@@ -22,6 +22,7 @@ GPU.  Models outside the recognised set raise ``LoggedError`` (no CPU fallback).
 from __future__ import annotations
 
 import sys
+import time
 from collections.abc import Callable, Sequence
 from itertools import chain
 from typing import Any
@@ -33,7 +34,7 @@ from cobaya.collection import SampleCollection, apply_temperature_cov, remove_te
 from cobaya.conventions import Extension, OutPar, get_version
 from cobaya.log import LoggedError
 from cobaya.sampler import CovmatSampler
-from cobaya.tools import get_external_function
+from cobaya.tools import NumberWithUnits, get_external_function
 from cobaya.yaml import yaml_dump_file
 
 from .flatmodel import FlatModelError
@@ -192,7 +193,7 @@ class MCMC(CovmatSampler):
             except OSError as e:
                 raise LoggedError(
                     self.log, "Cannot resume: engine snapshot '%s' not found (%s). It is "
-                              "written when run() ends.", self.snapshot_filename(), e)
+                              "written at timed outputs and when run() ends.", self.snapshot_filename(), e)
             self.mpi_info("Resuming from previous sample!")
         n_local = int(self.chains_per_gpu)
         # start points: one independent valid point per chain (mcmc.py:215-222)
@@ -355,8 +356,32 @@ class MCMC(CovmatSampler):
                 self.callback_function_callable(self)
                 self.last_point_callback = ens.n()
 
+        # Timed output (mcmc.py:473-481): at a convergence check, if `output_every` seconds
+        # have passed, the engine snapshot, .progress/.checkpoint/.covmat are rewritten, so
+        # a killed run resumes from there instead of from scratch.  `output_every` without
+        # a unit counts accepted steps per chain (mcmc.py:696-698).
+        out_every = NumberWithUnits(self.output_every, "s", dtype=int)
+        last_out = {"t": time.time(), "n": 0}
+
+        def _ck(_):
+            if not self.output:
+                return
+            if out_every.unit:
+                due = time.time() >= last_out["t"] + out_every.value
+            else:
+                due = ens.last_summary["min_rows"] >= last_out["n"] + max(1, out_every.value)
+            if not due:
+                return
+            self.converged = ens.converged
+            self.Rminus1_last = ens.Rminus1_last
+            self._sync_progress(ens)
+            self.write_checkpoint()
+            ens.save_snapshot(self.snapshot_filename())
+            last_out["t"] = time.time()
+            last_out["n"] = ens.last_summary["min_rows"]
+
         try:
-            ens.run(callback=_cb)
+            ens.run(callback=_cb, on_checkpoint=_ck)
         except LoggedError:
             raise
         except Exception as e:
@@ -364,15 +389,18 @@ class MCMC(CovmatSampler):
         self.n_steps_raw = ens.n_steps_raw
         self.converged = ens.converged
         self.Rminus1_last = ens.Rminus1_last
-        for i, c in enumerate(ens.progress, start=1):
-            self.progress.loc[i] = [c.N, c.timestamp, c.acceptance_rate, c.Rminus1,
-                                    c.Rminus1_cl]
+        self._sync_progress(ens)
         self._fill_collection()
         self.write_checkpoint()
         if self.output:
             ens.save_snapshot(self.snapshot_filename())
         self.mpi_info("Sampling complete after %d accepted steps.",
                       ens.last_summary["sum_rows"])
+
+    def _sync_progress(self, ens):
+        for i, c in enumerate(ens.progress, start=1):
+            self.progress.loc[i] = [c.N, c.timestamp, c.acceptance_rate, c.Rminus1,
+                                    c.Rminus1_cl]
 
     def n(self, burn_in=False):
         return 0 if self._ens is None else self._ens.n()
@@ -426,6 +454,24 @@ class MCMC(CovmatSampler):
                 "converged": bool(self.converged), "Rminus1_last": self.Rminus1_last,
                 "burn_in": 0, "mpi_size": mpi.get_mpi_size()}}}
             yaml_dump_file(self.checkpoint_filename(), info, error_if_exists=False)
+            self._write_progress_file()
+
+    def _write_progress_file(self):
+        """``prefix.progress`` in the reference's format (mcmc.py:163-181,1067-1077).  The
+        reference appends one line per checkpoint; the table is rewritten as a whole here
+        (same content), since timed outputs may skip checkpoints."""
+        if self.progress is None or self.progress.empty:
+            return
+        header_fmt = {"N": 6 * " " + "N", "timestamp": 17 * " " + "timestamp"}
+        head = "# " + " ".join(header_fmt.get(col, ((7 + 8) - len(col)) * " " + col)
+                               for col in self.progress.columns)
+        body = self.progress.to_string(header=False, index=False,
+                                       formatters={"N": "{:9f}".format})
+        tmp = self.progress_filename() + ".tmp"
+        with open(tmp, "w", encoding="utf-8") as f:
+            f.write(head + "\n" + body + "\n")
+        import os
+        os.replace(tmp, self.progress_filename())
 
     def converge_info_changed(self, old_info, new_info):
         keys = ["Rminus1_stop", "Rminus1_cl_stop", "Rminus1_cl_level", "max_samples"]

@@ -200,3 +200,48 @@ def test_cobaya_run_resume_continues_bit_for_bit(cuda_lib, tmp_path):
 
     back = load_samples(pb, skip=0, combined=True)
     assert len(back) == len(b)
+
+
+@pytest.mark.gpu
+def test_timed_output_writes_snapshot_and_progress_during_the_run(cuda_lib, tmp_path):
+    """mcmc.py:473-481,1045-1078: with ``output_every`` due at every convergence check the
+    engine snapshot, ``.progress``, ``.checkpoint`` and ``.covmat`` exist while the run is
+    still going (seen from the callback), so a killed run can be resumed."""
+    from tests.refenv import enable_reference
+
+    enable_reference()
+    import os
+
+    from cobaya.run import run
+
+    g = load_golden("g1_gauss3d")
+    mean, cov = g["means"][0], np.asarray(g["covs"]).reshape(3, 3)
+    seen = {"snap": 0, "progress_lines": 0}
+
+    def cb(sampler):
+        if os.path.exists(sampler.snapshot_filename()):
+            seen["snap"] += 1
+            with open(sampler.progress_filename()) as f:
+                seen["progress_lines"] = max(seen["progress_lines"], len(f.readlines()))
+            assert os.path.exists(sampler.checkpoint_filename())
+
+    info = {
+        "likelihood": {"gaussian_mixture": {"means": [mean], "covs": [cov],
+                                            "input_params_prefix": "a_",
+                                            "output_params_prefix": "", "derived": True}},
+        "params": dict({f"a__{i}": {"prior": {"min": -1, "max": 1}} for i in range(3)},
+                       **{f"_{i}": None for i in range(3)}),
+        "sampler": {"cobaya_b200.plugin.MCMC": {
+            "covmat": np.asarray(g["S0"]), "covmat_params": ["a__0", "a__1", "a__2"],
+            "max_tries": 3000, "learn_proposal_Rminus1_max": 30, "Rminus1_stop": 1e-9,
+            "measure_speeds": False, "seed": 5, "chains_per_gpu": 16, "rows_per_chain": 4000,
+            "max_samples": 900, "output_every": "0s", "callback_function": cb,
+            "callback_every": 1}},
+        "output": str(tmp_path / "run"),
+    }
+    _, smp = run(info, force=True)
+    assert seen["snap"] > 0, "no snapshot was written before the run ended"
+    assert seen["progress_lines"] >= 2  # header + at least one checkpoint
+    with open(smp.progress_filename()) as f:
+        lines = f.readlines()
+    assert lines[0].startswith("#") and len(lines) == 1 + len(smp.progress)
