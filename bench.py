@@ -452,6 +452,13 @@ def main():
         run_reference_arm(args)
     else:
         run_gpu_arm(args)
+        try:  # torchrun ranks: leave NCCL cleanly
+            import torch.distributed as tdist
+
+            if tdist.is_available() and tdist.is_initialized():
+                tdist.destroy_process_group()
+        except Exception:
+            pass
 
 
 if __name__ == "__main__":
