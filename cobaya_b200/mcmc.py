@@ -114,6 +114,9 @@ class _NoDist:
     def all_reduce_min_max_sum(self, mins, maxs, sums):
         return mins, maxs, sums
 
+    def all_gather_object(self, obj):
+        return [obj]
+
 
 class TorchDist:
     """One process per GPU (torchrun): NCCL all-reduce of the per-GPU sufficient statistics
@@ -142,6 +145,11 @@ class TorchDist:
     def all_reduce_tensor_(self, t):
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
         return t
+
+    def all_gather_object(self, obj):
+        out = [None] * self.size
+        self.dist.all_gather_object(out, obj, group=self.group)
+        return out
 
     def all_reduce_min_max_sum(self, mins, maxs, sums):
         tt = self.torch

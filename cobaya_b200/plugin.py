@@ -429,15 +429,42 @@ class MCMC(CovmatSampler):
     # ------------------------------------------------------------------ products
     def samples(self, combined: bool = False, skip_samples: float = 0,
                 to_getdist: bool = False):
-        """mcmc.py:1092-1144: here all local chains are already concatenated."""
-        if to_getdist:
-            raise LoggedError(self.log, "to_getdist needs GetDist (not evaluated by the "
-                                        "ensemble engine yet).")
+        """mcmc.py:1092-1144.  Without arguments: this process' chains, concatenated (the
+        collection bound to the output file).  ``combined``: the chains of all processes
+        (call it from every process).  ``to_getdist``: one :class:`getdist.MCSamples` built
+        by the reference's own ``SampleCollection.to_getdist`` (collection.py:1163-1248)
+        from one collection per chain, so GetDist sees the chains separately, as it does the
+        reference's MPI chains."""
+        if self.temperature != 1 and not to_getdist:
+            self.mpi_warning(
+                "The MCMC chain(s) are stored with temperature != 1. Keep that in mind when "
+                "operating on them, or detemper (in-place) with "
+                "products()['sample'].reset_temperature()'.")
+        if not (combined or to_getdist):
+            if not skip_samples:
+                return self.collection
+            # skipping is applied to every chain before concatenation (mcmc.py:1127-1143)
+            # and returns a copy; the collection bound to the output files is untouched
+            return self._collection_from_rows(self._ens.samples(skip_samples=skip_samples),
+                                              self.collection.copy(empty=True))
         if not skip_samples:
-            return self.collection
-        # skipping is applied to every chain before concatenation (mcmc.py:1127-1143) and
-        # returns a copy; the collection bound to the output files is left untouched
-        return self._collection_from_rows(self._ens.samples(skip_samples=skip_samples),
+            self.mpi_warning("When combining chains, it is recommended to remove some "
+                             "initial fraction, e.g. 'skip_samples=0.3'")
+        ens = self._ens
+        if to_getdist:
+            try:
+                import getdist  # noqa: F401
+            except ImportError as e:
+                raise LoggedError(self.log, "to_getdist=True needs GetDist (%s)", e) from e
+            per_chain = [ens.chain_rows(c, skip_samples) for c in range(ens.n_chains_local)]
+            gathered = ens.dist.all_gather_object(per_chain)
+            colls = [self._collection_from_rows(rows, self.collection.copy(empty=True))
+                     for rank_rows in gathered for rows in rank_rows if len(rows)]
+            if not colls:
+                raise LoggedError(self.log, "No samples to export.")
+            return colls[0].to_getdist(combine_with=colls[1:])
+        gathered = ens.dist.all_gather_object(ens.samples(skip_samples=skip_samples))
+        return self._collection_from_rows(np.concatenate(gathered),
                                           self.collection.copy(empty=True))
 
     def products(self, combined: bool = False, skip_samples: float = 0,

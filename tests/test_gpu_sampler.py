@@ -245,3 +245,50 @@ def test_timed_output_writes_snapshot_and_progress_during_the_run(cuda_lib, tmp_
     with open(smp.progress_filename()) as f:
         lines = f.readlines()
     assert lines[0].startswith("#") and len(lines) == 1 + len(smp.progress)
+
+
+@pytest.mark.gpu
+def test_samples_combined_and_to_getdist_through_the_reference_exporter(cuda_lib, monkeypatch):
+    """mcmc.py:1092-1144 / collection.py:1163-1248: ``to_getdist=True`` hands GetDist one
+    chain per ensemble chain (skip applied per chain) through the reference's own
+    ``SampleCollection.to_getdist``; ``combined=True`` returns all chains in one collection.
+    GetDist itself is not installed here: ``MCSamples`` is replaced by a recorder."""
+    from tests.refenv import enable_reference
+
+    enable_reference()
+    import cobaya.collection as cc
+    from cobaya.run import run
+
+    class Recorder:
+        def __init__(self, **kw):
+            self.kw = kw
+
+    monkeypatch.setattr(cc, "MCSamples", Recorder)
+    g = load_golden("g1_gauss3d")
+    mean, cov = g["means"][0], np.asarray(g["covs"]).reshape(3, 3)
+    info = {
+        "likelihood": {"gaussian_mixture": {"means": [mean], "covs": [cov],
+                                            "input_params_prefix": "a_",
+                                            "output_params_prefix": "", "derived": True}},
+        "params": dict({f"a__{i}": {"prior": {"min": -1, "max": 1}} for i in range(3)},
+                       **{f"_{i}": None for i in range(3)}),
+        "sampler": {"cobaya_b200.plugin.MCMC": {
+            "covmat": np.asarray(g["S0"]), "covmat_params": ["a__0", "a__1", "a__2"],
+            "max_tries": 3000, "Rminus1_stop": 1e-9, "measure_speeds": False, "seed": 5,
+            "chains_per_gpu": 16, "rows_per_chain": 2000, "max_samples": 300}},
+    }
+    _, smp = run(info)
+    mc = smp.samples(to_getdist=True, skip_samples=0.25)
+    assert isinstance(mc, Recorder)
+    kw = mc.kw
+    assert len(kw["samples"]) == 16 and len(kw["weights"]) == 16 and len(kw["loglikes"]) == 16
+    ens = smp._ens
+    for c in range(16):
+        rows = ens.chain_rows(c, 0.25)
+        np.testing.assert_array_equal(kw["weights"][c], rows[:, 0])
+        np.testing.assert_array_equal(kw["loglikes"][c], rows[:, 1])
+        np.testing.assert_array_equal(kw["samples"][c], rows[:, 2:])
+    assert kw["names"][:3] == ["a__0", "a__1", "a__2"] and kw["names"][3].endswith("*")
+    comb = smp.samples(combined=True, skip_samples=0.25)
+    assert len(comb) == sum(len(w) for w in kw["weights"])
+    assert smp.products(to_getdist=True, skip_samples=0.25)["sample"].kw["sampler"] == "mcmc"
