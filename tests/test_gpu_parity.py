@@ -51,7 +51,7 @@ def test_logpost_matches_reference_known_answers(cuda_lib):
 
 
 @pytest.mark.parametrize("policy", [0, 4, 1])
-@pytest.mark.parametrize("n", [2, 3, 7, 16, 41, 64, 65, 72, 100, 128])
+@pytest.mark.parametrize("n", [2, 3, 7, 16, 41, 64, 65, 72, 100, 128, 136, 256, 512])
 def test_random_so_n_matches_reference_rvs(cuda_lib, n, policy):
     """Device Haar basis vs the reference's numba _rvs on the same normals (golden)."""
     from cobaya_b200.flatmodel import FlatModel
@@ -61,7 +61,8 @@ def test_random_so_n_matches_reference_rvs(cuda_lib, n, policy):
     fm = FlatModel.gaussian(np.zeros(D), np.eye(D) * 0.01, blocks=[[0], list(range(1, D))],
                             oversampling=[1, 1], proposal_cov=np.eye(D) * 0.01)
     eng = _engine(fm, 20, seed=1234)
-    # 0: compact-WY DMMA sweep (4 warps for n <= 64, 8 warps + k_normals for n <= 128),
+    # 0: compact-WY DMMA sweep (4 warps for n <= 64, 8 warps + k_normals for n <= 128, N in
+    #    global memory for n <= 512),
     # 4: DFMA sweep, 1: general kernel
     eng.set_kernel_policy(policy)
     R = eng.debug_basis(chain=17, block=1, epoch=5)
@@ -70,8 +71,9 @@ def test_random_so_n_matches_reference_rvs(cuda_lib, n, policy):
     else:
         from oracle import oracle as orc
         ref = orc.random_SO_N(n, 1234, 17, 1, 5)
-    np.testing.assert_allclose(R, ref, rtol=0, atol=5e-14)
-    np.testing.assert_allclose(R @ R.T, np.eye(n), atol=1e-13)
+    # rounding grows with the number of reflectors applied
+    np.testing.assert_allclose(R, ref, rtol=0, atol=5e-14 * max(1, n // 64))
+    np.testing.assert_allclose(R @ R.T, np.eye(n), atol=1e-13 * max(1, n // 64))
     assert abs(np.linalg.det(R) - 1) < 1e-12
 
 
