@@ -157,9 +157,10 @@ static int pack_stream(cb2_engine *h) {
                 if (aoff[l] + a < j && v != 0.0) tri = false;
             }
         }
+    const bool frag = D <= CB2_STREAM_FRAG_MAX_D;  // above: plain matrices for cuBLAS
     P.tri_like = tri ? 1 : 0;
-    P.blocks_T = NT * (NT + 1) / 2;
-    P.blocks_A = tri ? P.blocks_T : NT * NT;
+    P.blocks_T = frag ? NT * (NT + 1) / 2 : 0;
+    P.blocks_A = frag ? (tri ? P.blocks_T : NT * NT) : 0;
     int o = 0;
     auto take = [&](int n) { int r = o; o += (n + 1) & ~1; return r; };
     P.off_T = take(P.blocks_T * 64);
@@ -183,9 +184,21 @@ static int pack_stream(cb2_engine *h) {
     std::vector<double> Tm((size_t)DP * DP, 0.0);
     for (int j = 0; j < D; ++j)
         for (int k = 0; k <= j; ++k) Tm[(size_t)j * DP + k] = h->Trow[(size_t)j * D + k];
-    pack_frag(pk, P.off_T, Tm, DP, NT, true);
+    if (frag) pack_frag(pk, P.off_T, Tm, DP, NT, true);
+    else {
+        // column-major copies: Tcm[j + i DP] = T[j][i], Acm[a + j DP] = (L^-1 P)[a][j]
+        std::vector<double> Tcm((size_t)DP * DP), Acm((size_t)DP * DP);
+        for (int j = 0; j < DP; ++j)
+            for (int i = 0; i < DP; ++i) {
+                Tcm[(size_t)j + (size_t)i * DP] = Tm[(size_t)j * DP + i];
+                Acm[(size_t)j + (size_t)i * DP] = Am[0][(size_t)j * DP + i];
+            }
+        int rcu;
+        if ((rcu = upload(h, h->d_Tcm, Tcm))) return rcu;
+        if ((rcu = upload(h, h->d_Acm, Acm))) return rcu;
+    }
     for (int km = 0; km < nm; ++km) {
-        pack_frag(pk, P.off_A + (size_t)km * P.blocks_A * 64, Am[km], DP, NT, tri);
+        if (frag) pack_frag(pk, P.off_A + (size_t)km * P.blocks_A * 64, Am[km], DP, NT, tri);
         for (int j = 0; j < D; ++j) {
             const int i = h->i_of_j[j], l = like_of_i[i];
             const LikeHost &L = h->likes[l];

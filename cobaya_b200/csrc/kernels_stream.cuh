@@ -20,7 +20,8 @@
 #pragma once
 #include "kernels_fast.cuh"
 
-#define CB2_STREAM_MAX_D 128
+#define CB2_STREAM_MAX_D 512   /* 64 < D <= 128: DMMA products; above: plain GEMMs (cuBLAS) */
+#define CB2_STREAM_FRAG_MAX_D 128
 #define CB2_STREAM_MAX_MODES 4
 #define CB2_STREAM_MAX_LIKES 3
 
@@ -55,6 +56,9 @@ static inline bool stream_step_supported(const ModelDev &M, size_t n_likes) {
         if (L.kind != 0 || L.derived || L.n_modes > CB2_STREAM_MAX_MODES) return false;
         dims += L.dim;
     }
+    // above 128 parameters: one component with one mode (the accept kernel keeps 6 D-vectors
+    // of a chain in the registers of one warp)
+    if (M.D > CB2_STREAM_FRAG_MAX_D && (n_likes != 1 || M.likes[0].n_modes != 1)) return false;
     return dims == M.D;
 }
 
@@ -437,6 +441,203 @@ k_stream_accept(ModelDev M, ChainState S, StreamWindow SW, const double *__restr
         S.n_rows[chain] = n_rows; S.n_acc[chain] = n_acc;
         if (flags) atomicOr(&S.flags[chain], flags);
     }
+}
+
+// ---------------------------------------------------------------------------------------
+// 128 < D <= 512: the proposal-side products are plain D x D x (directions) GEMMs with one
+// shared matrix and go to cuBLAS (cublasDgemm, FP64 tensor pipe); only the glue is here.
+// k_stream_center: z[chain][j] = x_sorted[j] - mu[j] (input of the whitening GEMM).
+// k_stream_accept_big<NC>: k_stream_accept for one single-mode component with the per-coordinate
+// constants read from the constant block instead of registers (NC up to 16 coordinates per lane).
+// ---------------------------------------------------------------------------------------
+__global__ void k_stream_center(const double *__restrict__ pack, StreamPackDesc P,
+                                const double *__restrict__ x, int D, int64_t n_chains,
+                                double *__restrict__ z) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_chains * P.DP) return;
+    const int64_t chain = e / P.DP;
+    const int j = (int)(e % P.DP);
+    const int i = __ldg(reinterpret_cast<const int2 *>(pack + P.off_kind) + j).y;
+    z[e] = (i >= 0) ? x[chain * D + i] - __ldg(pack + P.off_mu + j) : 0.0;
+}
+
+template <int NC>
+__global__ void __launch_bounds__(128)
+k_stream_accept_big(ModelDev M, ChainState S, StreamWindow SW, const double *__restrict__ pack,
+                    StreamPackDesc P, const double2 *__restrict__ draws,
+                    const int2 *__restrict__ plan, const double *__restrict__ ys_in,
+                    int64_t n_chains, int n_steps) {
+    const int lane = threadIdx.x & 31;
+    const int64_t chain = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (chain >= n_chains) return;
+    const int D = M.D, DP = P.DP;
+    const int2 *kind = reinterpret_cast<const int2 *>(pack + P.off_kind);
+    const double *lower = pack + P.off_lower, *upper = pack + P.off_upper;
+    double xs[NC], ys[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        const int j = lane + 32 * c;
+        xs[c] = 0.0;
+        ys[c] = 0.0;
+        if (j < DP) {
+            const int i = __ldg(&kind[j]).y;
+            if (i >= 0) xs[c] = S.x[chain * D + i];
+            ys[c] = ys_in[(size_t)chain * DP + j];
+        }
+    }
+    double logpost = S.logpost[chain], logprior = S.logprior[chain], loglike = S.ll[chain];
+    long long weight = S.weight[chain], prior_rej = S.prior_rej[chain],
+              burn_left = S.burn_left[chain], added_w = S.added_w[chain],
+              n_rows = S.n_rows[chain], n_acc = S.n_acc[chain];
+    uint32_t flags = 0;
+    const double2 *my_draws = draws + chain * (int64_t)n_steps;
+    const int2 *my_plan = plan + chain * (int64_t)n_steps;
+    const bool temp_one = M.temperature == 1.0;
+    const double c0 = __ldg(pack + P.off_c0);
+    double dn[NC], wn[NC];
+    double2 dr;
+    auto fetch = [&](int s) {
+        const int2 pl = __ldg(my_plan + s);
+        dr = __ldg(my_draws + s);
+        const int b = pl.y;
+        const double *dp, *wp;
+        if (M.bsize[b] >= 2) {
+            dp = SW.delta[b] + (size_t)pl.x * DP;
+            wp = SW.wv[b] + (size_t)pl.x * DP;
+        } else {
+            dp = pack + P.off_d1 + (size_t)b * DP;
+            wp = pack + P.off_w1 + (size_t)b * DP;
+        }
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const int j = lane + 32 * c;
+            dn[c] = (j < DP) ? __ldg(dp + j) : 0.0;
+            wn[c] = (j < DP) ? __ldg(wp + j) : 0.0;
+        }
+    };
+    fetch(0);
+    for (int s = 0; s < n_steps; ++s) {
+        const double rs = dr.x * M.proposal_scale, e_acc = dr.y;
+        // trial point first (it replaces the fetched vectors), then the next fetch
+        double xt[NC], yt[NC];
+        bool bad = false;
+        double ps = 0.0, qs = 0.0;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const int j = lane + 32 * c;
+            const double t = fma(rs, dn[c], xs[c]);
+            xt[c] = t;
+            if (j < DP) {
+                if (!(t <= __ldg(upper + j)) || !(t >= __ldg(lower + j)) || !isfinite(t)) bad = true;
+                if (M.any_normal) {
+                    const int kd = __ldg(&kind[j]).x;
+                    if (kd != 0) {
+                        const double zz = (t - __ldg(pack + P.off_loc + j)) / __ldg(pack + P.off_isc + j);
+                        if (kd == 1) ps += __ldg(pack + P.off_mls + j) - zz * zz / 2;
+                        else ps += __ldg(pack + P.off_mls + j) +
+                                   prior1d_shape(kd, zz, __ldg(pack + P.off_pa + j),
+                                                 __ldg(pack + P.off_pb + j));
+                    }
+                }
+            }
+            const double y = fma(rs, wn[c], ys[c]);
+            yt[c] = y;
+            qs = fma(y, y, qs);
+        }
+        if (s + 1 < n_steps) fetch(s + 1);
+        bad = __any_sync(0xffffffffu, bad);
+        if (M.any_normal) ps = warp_sum_all(ps);
+        const double t_prior = bad ? -CUDART_INF : (M.uniform_logp + ps);
+        const double t_like = -0.5 * (c0 + warp_sum_all(qs));
+        const double t_post = bad ? -CUDART_INF : (t_prior + t_like);
+        bool acc;
+        if (t_post == -CUDART_INF) acc = false;
+        else if (t_post > logpost) acc = true;
+        else {
+            const double dlp = logpost - t_post;
+            acc = e_acc > (temp_one ? dlp : dlp / M.temperature);
+        }
+        if (acc) {
+            if (burn_left <= 0) {
+                long long wst = weight;
+                bool store = true;
+                if (M.output_thin > 1) {
+                    added_w += weight;
+                    if (added_w >= M.output_thin) {
+                        wst = added_w / M.output_thin;
+                        added_w %= M.output_thin;
+                    } else store = false;
+                }
+                if (store) {
+                    if (n_rows >= S.cap) flags |= CB2_FLAG_ROWS_FULL;
+                    else {
+                        double *row = S.rows + ((size_t)chain * S.cap + n_rows) * M.width;
+                        if (lane == 0) {
+                            row[0] = (double)wst;
+                            row[1] = temp_one ? -logpost : -(logpost / M.temperature);
+                        } else if (lane == 1) {
+                            row[2 + D] = -logprior;
+                            row[3 + D] = -logprior;
+                        } else if (lane == 2) {
+                            row[4 + D] = -2 * loglike;
+                            row[5 + D] = -2 * loglike;
+                        }
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) {
+                            const int j = lane + 32 * c;
+                            if (j < DP) {
+                                const int i = __ldg(&kind[j]).y;
+                                if (i >= 0) row[2 + i] = xs[c];
+                            }
+                        }
+                        n_rows += 1;
+                    }
+                }
+            } else burn_left -= 1;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) { xs[c] = xt[c]; ys[c] = yt[c]; }
+            logpost = t_post; logprior = t_prior; loglike = t_like;
+            weight = 1; prior_rej = 0; n_acc += 1;
+        } else {
+            weight += 1;
+            if (t_prior == -CUDART_INF) prior_rej += 1;
+            const long long sgn = (burn_left > 0) - (burn_left < 0);
+            if (weight - prior_rej > M.max_tries * (1 + 9 * sgn)) flags |= CB2_FLAG_STUCK;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        const int j = lane + 32 * c;
+        if (j < DP) {
+            const int i = __ldg(&kind[j]).y;
+            if (i >= 0) S.x[chain * D + i] = xs[c];
+        }
+    }
+    if (lane == 0) {
+        S.logpost[chain] = logpost; S.logprior[chain] = logprior; S.ll[chain] = loglike;
+        S.weight[chain] = weight; S.prior_rej[chain] = prior_rej;
+        S.burn_left[chain] = burn_left; S.added_w[chain] = added_w;
+        S.n_rows[chain] = n_rows; S.n_acc[chain] = n_acc;
+        if (flags) atomicOr(&S.flags[chain], flags);
+    }
+}
+
+static int launch_stream_accept_big(cudaStream_t st, const ModelDev &M, const ChainState &S,
+                                    const StreamWindow &SW, const double *pack,
+                                    const StreamPackDesc &P, const double2 *draws,
+                                    const int2 *plan, const double *ys, int64_t n_chains,
+                                    int n_steps) {
+    const unsigned grid = (unsigned)((n_chains + 3) / 4);
+    const int NC = (P.DP + 31) / 32;
+#define CB2_SAB(C_)                                                                          \
+    if (NC <= C_) {                                                                          \
+        k_stream_accept_big<C_><<<grid, 128, 0, st>>>(M, S, SW, pack, P, draws, plan, ys,    \
+                                                      n_chains, n_steps);                    \
+        return cudaGetLastError() == cudaSuccess ? 0 : -2;                                   \
+    }
+    CB2_SAB(6) CB2_SAB(8) CB2_SAB(12) CB2_SAB(16)
+#undef CB2_SAB
+    return -1;
 }
 
 // ---------------------------------------------------------------- launchers

@@ -366,7 +366,7 @@ def test_config4_30d_rosenbrock_dragging(cuda_lib):
         assert st["weight"][c] == s_ref["weight"]
 
 
-@pytest.mark.parametrize("D,n", [(32, 200), (128, 260), (512, 40)])
+@pytest.mark.parametrize("D,n", [(32, 200), (128, 260), (200, 450), (512, 40), (512, 600)])
 def test_config5_dimension_sweep_parity(cuda_lib, D, n):
     """configs[4]: the D sweep as a parity case (single mode, one block)."""
     from cobaya_b200.flatmodel import FlatModel, synthetic_gaussian_cov
@@ -378,8 +378,9 @@ def test_config5_dimension_sweep_parity(cuda_lib, D, n):
     eng = _engine(fm, C, seed=D, chain_id0=3, rows_cap=n)
     eng.set_state(x0)
     eng.advance(n)
-    # D <= 64: producer/consumer DMMA kernel; D <= 128: streamed kernels; else general
-    assert eng.last_step_kernel() == (2 if D <= 64 else (3 if D <= 128 else 0))
+    # D <= 64: producer/consumer DMMA kernel; above: streamed kernels (DMMA products up to
+    # D = 128, cuBLAS GEMMs up to D = 512)
+    assert eng.last_step_kernel() == (2 if D <= 64 else 3)
     st = eng.get_state()
     ref = _oracle_rows(fm, D, range(3, 3 + C), x0, n, 0)
     for c in range(C):
