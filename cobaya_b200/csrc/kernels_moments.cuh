@@ -422,3 +422,147 @@ __global__ void k_reduce_bounds(const double *__restrict__ bounds, int64_t n_tas
     out[1 + (which ? 2 * D : 0) + par] = s1;
     out[1 + (which ? 2 * D : 0) + D + par] = s2;
 }
+
+// =====================================================================================
+// The same SYRK for 64 < D <= 256: the D x D output is cut into 64 x 64 blocks; a CTA
+// (8 warps) owns one block pair (ib >= jb; the mirror image is written at the end) for its
+// share of the tasks.  grid = (task CTAs, block pairs).  Rows are staged for all D
+// coordinates, so every pair re-reads its tasks' rows (the kernel is FP64-bound: 2 D^2 FLOP
+// against 8 D B per row).  Scalars and the mean vector are written by pair 0.
+// =====================================================================================
+#define CB2_MOMB_VALS 32   // CB2_MOM_BATCH * 256 / 256
+
+__global__ void __launch_bounds__(256, 1)
+k_task_moments_dmma_blk(const double *__restrict__ rows, int64_t cap, int width, int D, int DP,
+                        const MomentTask *__restrict__ tasks, int64_t n_tasks,
+                        const double *__restrict__ shift, double *__restrict__ partials) {
+    extern __shared__ __align__(16) double msm[];
+    const int LDX = DP + 4;
+    double *xt = msm;                          // [CB2_MOM_BATCH][LDX]
+    double *wt = xt + CB2_MOM_BATCH * LDX;     // [CB2_MOM_BATCH]
+    double *refv = wt + CB2_MOM_BATCH, *s1v = refv + DP, *mrel = s1v + DP, *msv = mrel + DP;
+    __shared__ double sw_s;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int q = lane >> 2, r = lane & 3;
+    const int DD = D * D;
+    // block pair index -> (ib, jb), jb <= ib
+    int ib = 0, jb = (int)blockIdx.y;
+    while (jb > ib) { jb -= ib + 1; ++ib; }
+    const bool lead = blockIdx.y == 0;
+    double *P = partials + (size_t)blockIdx.x * (size_t)(3 + D + 2 * DD);
+    const int per = DP >> 3;                   // values per thread and batch
+    double sc[8][2], smm[8][2];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) { sc[n][0] = sc[n][1] = smm[n][0] = smm[n][1] = 0.0; }
+    double accM = 0.0, accN = 0.0, accNa = 0.0, accm = 0.0;
+    for (int64_t t = blockIdx.x; t < n_tasks; t += gridDim.x) {
+        const MomentTask T = tasks[t];
+        const double *base = rows + (size_t)T.chain * cap * width;
+        double s2[8][2];
+#pragma unroll
+        for (int n = 0; n < 8; ++n) { s2[n][0] = 0.0; s2[n][1] = 0.0; }
+        double s1 = 0.0, swl = 0.0;
+        __syncthreads();
+        if (tid < DP) refv[tid] = (tid < D) ? base[(size_t)T.first * width + 2 + tid] : 0.0;
+        __syncthreads();
+        double vals[CB2_MOMB_VALS], wnext = 0.0;
+        auto fetch = [&](int64_t r0) {
+            const int nb = (int)min((int64_t)CB2_MOM_BATCH, T.last - r0);
+#pragma unroll
+            for (int u = 0; u < CB2_MOMB_VALS; ++u) {
+                if (u < per) {
+                    const int e = tid + u * 256;
+                    const int k = e / DP, d = e % DP;
+                    vals[u] = (k < nb && d < D) ? base[(size_t)(r0 + k) * width + 2 + d] : 0.0;
+                }
+            }
+            if (tid < CB2_MOM_BATCH) wnext = (tid < nb) ? base[(size_t)(r0 + tid) * width] : 0.0;
+        };
+        if (T.first < T.last) fetch(T.first);
+        for (int64_t r0 = T.first; r0 < T.last; r0 += CB2_MOM_BATCH) {
+            const int nb = (int)min((int64_t)CB2_MOM_BATCH, T.last - r0);
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < CB2_MOMB_VALS; ++u) {
+                if (u < per) {
+                    const int e = tid + u * 256;
+                    const int k = e / DP, d = e % DP;
+                    xt[k * LDX + d] = (k < nb && d < D) ? vals[u] - refv[d] : 0.0;
+                }
+            }
+            if (tid < CB2_MOM_BATCH) wt[tid] = wnext;
+            __syncthreads();
+            if (r0 + CB2_MOM_BATCH < T.last) fetch(r0 + CB2_MOM_BATCH);
+            if (tid < DP) {
+#pragma unroll 8
+                for (int k = 0; k < CB2_MOM_BATCH; ++k) s1 = fma(wt[k], xt[k * LDX + tid], s1);
+            }
+            if (tid == 0)
+                for (int k = 0; k < CB2_MOM_BATCH; ++k) swl += wt[k];
+#pragma unroll
+            for (int kk = 0; kk < CB2_MOM_BATCH / 4; ++kk) {
+                const int k = 4 * kk + r;
+                const double a = wt[k] * xt[k * LDX + 64 * ib + 8 * wid + q];
+#pragma unroll
+                for (int n = 0; n < 8; ++n)
+                    mom_dmma(s2[n][0], s2[n][1], a, xt[k * LDX + 64 * jb + 8 * n + q]);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) sw_s = swl;
+        if (tid < DP) s1v[tid] = s1;
+        __syncthreads();
+        const double sw = sw_s;
+        if (tid < DP) {
+            const double mr = s1v[tid] / sw;
+            mrel[tid] = mr;
+            const double ms = (tid < D) ? (refv[tid] + mr) - (shift ? shift[tid] : 0.0) : 0.0;
+            msv[tid] = ms;
+            accm += ms;
+        }
+        __syncthreads();
+        const double f = T.N / sw;
+        const int i = 64 * ib + 8 * wid + q;
+#pragma unroll
+        for (int n = 0; n < 8; ++n)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = 64 * jb + 8 * n + 2 * r + h;
+                if (i < DP && j < DP) {
+                    sc[n][h] += f * s2[n][h] - T.N * (mrel[i] * mrel[j]);
+                    smm[n][h] += msv[i] * msv[j];
+                }
+            }
+        if (tid == 0) {
+            accM += 1.0;
+            accN += T.N;
+            accNa += T.N * ((double)(T.last - T.first) / sw);
+        }
+    }
+    __syncthreads();
+    {
+        const int i = 64 * ib + 8 * wid + q;
+#pragma unroll
+        for (int n = 0; n < 8; ++n)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = 64 * jb + 8 * n + 2 * r + h;
+                if (i < D && j < D) {
+                    P[3 + D + i * D + j] = smm[n][h];
+                    P[3 + D + DD + i * D + j] = sc[n][h];
+                    if (ib != jb) {
+                        P[3 + D + j * D + i] = smm[n][h];
+                        P[3 + D + DD + j * D + i] = sc[n][h];
+                    }
+                }
+            }
+    }
+    if (lead) {
+        if (tid < D) P[3 + tid] = accm;
+        if (tid == 0) {
+            P[0] = accM;
+            P[1] = accN;
+            P[2] = accNa;
+        }
+    }
+}

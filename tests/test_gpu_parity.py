@@ -150,7 +150,7 @@ def test_ensemble_matches_oracle(cuda_lib, D, n_chains, n, policy):
         assert st["n_accepted"][c] == s_ref["n_accepted"]
 
 
-@pytest.mark.parametrize("policy,D", [(0, 6), (1, 6), (0, 64), (0, 20)])
+@pytest.mark.parametrize("policy,D", [(0, 6), (1, 6), (0, 64), (0, 20), (0, 100), (0, 136)])
 def test_moments_match_numpy(cuda_lib, policy, D):
     """cb2_moments (multi-chain halves rule) vs SampleCollection.mean/cov arithmetic
     restated with numpy on the same rows, and R-1 to 1e-4 as BASELINE.json asks."""
