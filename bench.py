@@ -373,7 +373,10 @@ def run_gpu_arm(args):
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            # ncu figure of a 64-proposal window, scaled to the proposals of one launch now
+            traffic = int(tj["dram_bytes_per_launch"] * props_per_launch /
+                          float(tj.get("proposals_per_profiled_launch", props_per_launch)))
         except Exception:
             traffic = None
     flops = 4 * D * D * C * locksteps * K / (hot_ms * 1e-3) / 1e12
