@@ -424,6 +424,171 @@ __global__ void k_reduce_bounds(const double *__restrict__ bounds, int64_t n_tas
 }
 
 // =====================================================================================
+// Symmetric variant for D <= 64 (NT even): S2 is symmetric, so only the tiles on and below
+// the diagonal are accumulated (NT(NT+1)/2 instead of NT^2 MMAs per k-step) and mirrored at
+// the end.  NT/2 warps per CTA; warp w owns the row tiles t0 = w and t1 = NT-1-w, i.e. NT+1
+// tiles: slots 0..t0 are (t0, n = slot), slots t0+1..NT are (t1, n = slot - t0 - 1).
+// =====================================================================================
+template <int NT>
+__global__ void __launch_bounds__(NT * 16, (NT >= 7) ? 3 : 1)
+k_task_moments_dmma_sym(const double *__restrict__ rows, int64_t cap, int width, int D,
+                        const MomentTask *__restrict__ tasks, int64_t n_tasks,
+                        const double *__restrict__ shift, double *__restrict__ partials) {
+    constexpr int DP = NT * 8;
+    constexpr int LDX = DP + 4;
+    constexpr int NTH = NT * 16;                   // threads
+    constexpr int PER = CB2_MOM_BATCH * DP / NTH;  // staged values per thread
+    constexpr int NS = NT + 1;                     // tile slots per warp
+    __shared__ double xt[CB2_MOM_BATCH][LDX];
+    __shared__ double wt[CB2_MOM_BATCH];
+    __shared__ double refv[DP], s1v[DP], mrel[DP], msv[DP];
+    __shared__ double sw_s;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int q = lane >> 2, r = lane & 3;
+    const int DD = D * D;
+    const int t0 = wid, t1 = NT - 1 - wid;         // t0 < t1
+    double *P = partials + (size_t)blockIdx.x * (size_t)(3 + D + 2 * DD);
+    double sc[NS][2], smm[NS][2];
+#pragma unroll
+    for (int n = 0; n < NS; ++n) { sc[n][0] = sc[n][1] = smm[n][0] = smm[n][1] = 0.0; }
+    double accM = 0.0, accN = 0.0, accNa = 0.0;
+    double accm[(DP + NTH - 1) / NTH];
+#pragma unroll
+    for (int u = 0; u < (DP + NTH - 1) / NTH; ++u) accm[u] = 0.0;
+    for (int64_t t = blockIdx.x; t < n_tasks; t += gridDim.x) {
+        const MomentTask T = tasks[t];
+        const double *base = rows + (size_t)T.chain * cap * width;
+        double s2[NS][2];
+#pragma unroll
+        for (int n = 0; n < NS; ++n) { s2[n][0] = 0.0; s2[n][1] = 0.0; }
+        double s1[(DP + NTH - 1) / NTH], swl = 0.0;
+#pragma unroll
+        for (int u = 0; u < (DP + NTH - 1) / NTH; ++u) s1[u] = 0.0;
+        __syncthreads();
+        for (int d = tid; d < DP; d += NTH)
+            refv[d] = (d < D) ? base[(size_t)T.first * width + 2 + d] : 0.0;
+        __syncthreads();
+        double vals[PER], wnext = 0.0;
+        auto fetch = [&](int64_t r0) {
+            const int nb = (int)min((int64_t)CB2_MOM_BATCH, T.last - r0);
+#pragma unroll
+            for (int u = 0; u < PER; ++u) {
+                const int e = tid + u * NTH;
+                const int k = e / DP, d = e % DP;
+                vals[u] = (k < nb && d < D) ? base[(size_t)(r0 + k) * width + 2 + d] : 0.0;
+            }
+            if (tid < CB2_MOM_BATCH) wnext = (tid < nb) ? base[(size_t)(r0 + tid) * width] : 0.0;
+        };
+        if (T.first < T.last) fetch(T.first);
+        for (int64_t r0 = T.first; r0 < T.last; r0 += CB2_MOM_BATCH) {
+            const int nb = (int)min((int64_t)CB2_MOM_BATCH, T.last - r0);
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < PER; ++u) {
+                const int e = tid + u * NTH;
+                const int k = e / DP, d = e % DP;
+                xt[k][d] = (k < nb && d < D) ? vals[u] - refv[d] : 0.0;
+            }
+            if (tid < CB2_MOM_BATCH) wt[tid] = wnext;
+            __syncthreads();
+            if (r0 + CB2_MOM_BATCH < T.last) fetch(r0 + CB2_MOM_BATCH);
+#pragma unroll
+            for (int u = 0; u < (DP + NTH - 1) / NTH; ++u) {
+                const int d = tid + u * NTH;
+                if (d < DP) {
+#pragma unroll 8
+                    for (int k = 0; k < CB2_MOM_BATCH; ++k) s1[u] = fma(wt[k], xt[k][d], s1[u]);
+                }
+            }
+            if (tid == 0)
+                for (int k = 0; k < CB2_MOM_BATCH; ++k) swl += wt[k];
+#pragma unroll
+            for (int kk = 0; kk < CB2_MOM_BATCH / 4; ++kk) {
+                const int k = 4 * kk + r;
+                const double wk = wt[k];
+                const double a0 = wk * xt[k][8 * t0 + q], a1 = wk * xt[k][8 * t1 + q];
+#pragma unroll
+                for (int sl = 0; sl < NS; ++sl) {
+                    const bool first = sl <= t0;
+                    const int n = first ? sl : sl - t0 - 1;
+                    mom_dmma(s2[sl][0], s2[sl][1], first ? a0 : a1, xt[k][8 * n + q]);
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) sw_s = swl;
+#pragma unroll
+        for (int u = 0; u < (DP + NTH - 1) / NTH; ++u) {
+            const int d = tid + u * NTH;
+            if (d < DP) s1v[d] = s1[u];
+        }
+        __syncthreads();
+        const double sw = sw_s;
+#pragma unroll
+        for (int u = 0; u < (DP + NTH - 1) / NTH; ++u) {
+            const int d = tid + u * NTH;
+            if (d < DP) {
+                const double mr = s1v[d] / sw;
+                mrel[d] = mr;
+                const double ms = (d < D) ? (refv[d] + mr) - (shift ? shift[d] : 0.0) : 0.0;
+                msv[d] = ms;
+                accm[u] += ms;
+            }
+        }
+        __syncthreads();
+        const double f = T.N / sw;
+#pragma unroll
+        for (int sl = 0; sl < NS; ++sl) {
+            const bool first = sl <= t0;
+            const int i = 8 * (first ? t0 : t1) + q;
+            const int n = first ? sl : sl - t0 - 1;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = 8 * n + 2 * r + h;
+                sc[sl][h] += f * s2[sl][h] - T.N * (mrel[i] * mrel[j]);
+                smm[sl][h] += msv[i] * msv[j];
+            }
+        }
+        if (tid == 0) {
+            accM += 1.0;
+            accN += T.N;
+            accNa += T.N * ((double)(T.last - T.first) / sw);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int sl = 0; sl < NS; ++sl) {
+        const bool first = sl <= t0;
+        const int ti = first ? t0 : t1;
+        const int i = 8 * ti + q;
+        const int n = first ? sl : sl - t0 - 1;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int j = 8 * n + 2 * r + h;
+            if (i < D && j < D) {
+                // diagonal tiles hold both triangles already; off-diagonal ones are mirrored
+                P[3 + D + i * D + j] = smm[sl][h];
+                P[3 + D + DD + i * D + j] = sc[sl][h];
+                if (n != ti) {
+                    P[3 + D + j * D + i] = smm[sl][h];
+                    P[3 + D + DD + j * D + i] = sc[sl][h];
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < (DP + NTH - 1) / NTH; ++u) {
+        const int d = tid + u * NTH;
+        if (d < D) P[3 + d] = accm[u];
+    }
+    if (tid == 0) {
+        P[0] = accM;
+        P[1] = accN;
+        P[2] = accNa;
+    }
+}
+
+// =====================================================================================
 // The same SYRK for 64 < D <= 256: the D x D output is cut into 64 x 64 blocks; a CTA
 // (8 warps) owns one block pair (ib >= jb; the mirror image is written at the end) for its
 // share of the tasks.  grid = (task CTAs, block pairs).  Rows are staged for all D
