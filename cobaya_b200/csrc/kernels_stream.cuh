@@ -165,6 +165,106 @@ k_stream_products(const double *__restrict__ pack, StreamPackDesc P, const doubl
 }
 
 // ---------------------------------------------------------------------------------------
+// k_stream_products1: the single-mode, triangular-L^-1 case with the two column sweeps
+// interleaved.  After column m of T the tile delta[m] is final: it is stored and immediately
+// feeds column m of L^-1 P, after which w[m] is final too.  Direction tiles are loaded two
+// columns ahead instead of all at once, so a warp keeps 2 (not 3) D-vectors of accumulators
+// live and 12 instead of 8 warps fit an SM.
+// ---------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(128, 3)
+k_stream_products1(const double *__restrict__ pack, StreamPackDesc P,
+                   const double *__restrict__ basis, int n_b, int j0, int64_t n_tasks,
+                   double *__restrict__ delta, double *__restrict__ wout) {
+    constexpr int DP = NT * 8;
+    const int lane = threadIdx.x & 31, q = lane >> 2, r = lane & 3;
+    const int kgroups = (n_b + 7) >> 3;
+    const int64_t wt = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (wt >= n_tasks * kgroups) return;
+    const int64_t task = wt / kgroups;
+    const int k = (int)(wt % kgroups) * 8 + q;
+    const bool kvalid = k < n_b;
+    const double *Rk = basis + ((size_t)task * n_b + (kvalid ? k : 0)) * (size_t)n_b;
+    const bool vec = ((n_b | j0) & 1) == 0;
+    const int m_lo = j0 >> 3, m_hi = (j0 + n_b - 1) >> 3;
+    auto load_un = [&](int m, double &u0, double &u1) {
+        const int j = 8 * m + 2 * r - j0;
+        u0 = 0.0;
+        u1 = 0.0;
+        if (kvalid && m >= m_lo && m <= m_hi) {
+            if (vec) {
+                if (j >= 0 && j < n_b) {
+                    const double2 v2 = ldg_f64x2_early(reinterpret_cast<const double2 *>(Rk + j));
+                    u0 = v2.x;
+                    u1 = v2.y;
+                }
+            } else {
+                if (j >= 0 && j < n_b) u0 = ldg_f64_early(Rk + j);
+                if (j + 1 >= 0 && j + 1 < n_b) u1 = ldg_f64_early(Rk + j + 1);
+            }
+        }
+    };
+    const double2 *fT = reinterpret_cast<const double2 *>(pack + P.off_T) + lane;
+    const double2 *fA = reinterpret_cast<const double2 *>(pack + P.off_A) + lane;
+    const size_t row = (size_t)task * n_b + (kvalid ? k : 0);
+    double2 *od = reinterpret_cast<double2 *>(delta + row * DP) + r;
+    double2 *ow = reinterpret_cast<double2 *>(wout + row * DP) + r;
+    double dl[NT][2], wv[NT][2], un[NT][2];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) { dl[n][0] = dl[n][1] = wv[n][0] = wv[n][1] = 0.0; }
+    load_un(0, un[0][0], un[0][1]);
+    if (NT > 1) load_un(1, un[1][0], un[1][1]);
+#pragma unroll
+    for (int m = 0; m < NT; ++m) {
+        if (m + 2 < NT) load_un(m + 2, un[m + 2][0], un[m + 2][1]);
+        if (m >= m_lo && m <= m_hi) {  // warp-uniform
+#pragma unroll
+            for (int n0 = (m & ~3); n0 < NT; n0 += 4) {
+                double2 b[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int nt = n0 + u;
+                    if (nt < NT && nt >= m) b[u] = __ldg(fT + ((nt * (nt + 1)) / 2 + m) * 32);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int nt = n0 + u;
+                    if (nt < NT && nt >= m) dmma8x8x4(dl[nt][0], dl[nt][1], un[m][0], b[u].x);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int nt = n0 + u;
+                    if (nt < NT && nt >= m) dmma8x8x4(dl[nt][0], dl[nt][1], un[m][1], b[u].y);
+                }
+            }
+        }
+        if (kvalid) od[4 * m] = make_double2(dl[m][0], dl[m][1]);
+        if (m >= m_lo) {  // delta vanishes above the block
+#pragma unroll
+            for (int n0 = (m & ~3); n0 < NT; n0 += 4) {
+                double2 b[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int nt = n0 + u;
+                    if (nt < NT && nt >= m) b[u] = __ldg(fA + ((nt * (nt + 1)) / 2 + m) * 32);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int nt = n0 + u;
+                    if (nt < NT && nt >= m) dmma8x8x4(wv[nt][0], wv[nt][1], dl[m][0], b[u].x);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int nt = n0 + u;
+                    if (nt < NT && nt >= m) dmma8x8x4(wv[nt][0], wv[nt][1], dl[m][1], b[u].y);
+                }
+            }
+        }
+        if (kvalid) ow[4 * m] = make_double2(wv[m][0], wv[m][1]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // k_stream_whiten: y_m = L_m^-1 P (x - mu_m) of every chain at window start, 8 chains per warp
 // on the tensor pipe.  ys : [chain][modes][DP]
 // ---------------------------------------------------------------------------------------
@@ -646,10 +746,16 @@ static int launch_stream_products(cudaStream_t st, const double *pack, const Str
                                   double *delta, double *wout) {
     const int64_t wts = n_tasks * ((n_b + 7) / 8);
     const unsigned grid = (unsigned)((wts + 7) / 8);
+    const bool one = P.n_modes == 1 && P.tri_like;  // interleaved sweeps, 12 warps/SM
+    const unsigned grid1 = (unsigned)((wts + 3) / 4);
 #define CB2_SP(N)                                                                            \
     case N:                                                                                  \
-        k_stream_products<N><<<grid, 256, 0, st>>>(pack, P, basis, n_b, j0, n_tasks, delta,  \
-                                                   wout);                                    \
+        if (one)                                                                             \
+            k_stream_products1<N><<<grid1, 128, 0, st>>>(pack, P, basis, n_b, j0, n_tasks,   \
+                                                         delta, wout);                       \
+        else                                                                                 \
+            k_stream_products<N><<<grid, 256, 0, st>>>(pack, P, basis, n_b, j0, n_tasks,     \
+                                                       delta, wout);                         \
         break;
     switch (P.NT) {
         CB2_SP(9) CB2_SP(10) CB2_SP(11) CB2_SP(12) CB2_SP(13) CB2_SP(14) CB2_SP(15) CB2_SP(16)
