@@ -515,32 +515,32 @@ k_basis_wy(uint32_t key0, uint32_t key1, uint64_t chain_id0, int block, int n,
 // -------------------------------------------------------------------------------------
 // k_basis_wy_big: the same compact-WY backward accumulation for 128 < n <= 512 (n % 8 == 0).
 // N = H^T (n x n) no longer fits the registers of a CTA: it lives in the basis store itself
-// (global memory, L2 where it fits) and every group of 8 reflectors streams the rows/columns
-// >= 8g of it twice (Y = N V_g; N -= (Y T_g^T) V_g^T) as m8n8k4 A/C fragments.  One CTA of 8
-// warps per basis; the 8 Householder vectors of the current group sit in shared memory.
-// 4/3 n^3 FLOP and ~n^3 B of N traffic per basis (n = 512: 134 MB): bandwidth-bound.
+// (global memory, L2 where it fits) and every panel of 16 reflectors streams the rows/columns
+// >= 16g of it twice (Y = N V_g; N -= (Y T_g^T) V_g^T) as m8n8k4 A/C fragments.  One CTA of 8
+// warps per basis; the 16 Householder vectors of the current panel sit in shared memory.
+// 4/3 n^3 FLOP and ~n^3/2 B of N traffic per basis (n = 512: 67 MB): bandwidth-bound.
 // Normals from k_normals.  Output as everywhere: store[c*n + i] = D[i] N[c][i] = R[i][c].
 // -------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 2)
 k_basis_wy_big(int n, const double *__restrict__ normals, int nn_pad, double *__restrict__ store,
                int64_t n_tasks) {
+    // panels of 16 reflectors (two 8-wide halves a, b): half as many passes over N as with 8
     extern __shared__ __align__(16) double bsm[];
     const int LDX = n + 1;
-    double *X = bsm;               // [8][LDX]: X[j][c] = x_{8g+j}[c - (8g+j)]
-    double *Dv = X + 8 * LDX;      // [n] signs D (functions.py:51,59)
-    double *Sg = Dv + n;           // [64] Gram of the group
-    double *Tg = Sg + 64;          // [64] T of the group
-    double *tau = Tg + 64;         // [8]
+    double *X = bsm;               // [16][LDX]: X[j][c] = x_{16g+j}[c - (16g+j)]
+    double *Dv = X + 16 * LDX;     // [n] signs D (functions.py:51,59)
+    double *Sg = Dv + n;           // [256] Gram of the panel
+    double *Tg = Sg + 256;         // [256] T of the panel (upper triangular, row-major)
+    double *tau = Tg + 256;        // [16]
     __shared__ int n_negative;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, q = lane >> 2, r = lane & 3;
     const int64_t task = blockIdx.x;
     if (task >= n_tasks) return;
     double *N = store + (size_t)task * (size_t)n * n;
     const double *src = normals + (size_t)task * (size_t)nn_pad;
-    const int NT = n >> 3;                 // tiles per side
-    const int NGr = (n - 1 + 7) >> 3;      // groups that hold reflectors (m < n-1)
-    // N = I
-    for (int e = tid; e < n * (n >> 1); e += 256) {
+    const int NT = n >> 3;                 // 8-wide tiles per side
+    const int NGr = (n - 1 + 15) >> 4;     // panels that hold reflectors (m < n-1)
+    for (int e = tid; e < n * (n >> 1); e += 256) {  // N = I
         const int row = e / (n >> 1), c2 = (e % (n >> 1)) * 2;
         reinterpret_cast<double2 *>(N + (size_t)row * n)[c2 >> 1] =
             make_double2(row == c2 ? 1.0 : 0.0, row == c2 + 1 ? 1.0 : 0.0);
@@ -549,34 +549,37 @@ k_basis_wy_big(int n, const double *__restrict__ normals, int nn_pad, double *__
     for (int e = tid; e < n; e += 256) Dv[e] = 1.0;
     __syncthreads();
     for (int g = NGr - 1; g >= 0; --g) {
-        const int c_lo = 8 * g;
-        // ---- the 8 vectors of the group (zero where a vector has not started / m >= n-1)
-        for (int e = tid; e < 8 * LDX; e += 256) {
+        const int c_lo = 16 * g;
+        // ---- the 16 vectors of the panel (zero where a vector has not started / m >= n-1)
+        for (int e = tid; e < 16 * LDX; e += 256) {
             const int j = e / LDX, c = e % LDX, m = c_lo + j;
             double v = 0.0;
             if (m < n - 1 && c >= m && c < n) v = __ldg(src + ((m * (2 * n - m + 1)) >> 1) + (c - m));
             X[e] = v;
         }
         __syncthreads();
-        // ---- Gram over the normals as drawn: 4 threads per entry
+        // ---- Gram over the normals as drawn: one entry per thread
         {
-            const int ent = tid >> 2, part = tid & 3, i = ent >> 3, j = ent & 7;
+            const int i = tid >> 4, j = tid & 15;
             const double *xi = X + i * LDX, *xj = X + j * LDX;
-            double acc = 0.0;
-            for (int c = c_lo + part; c < n; c += 4) acc = fma(xi[c], xj[c], acc);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-            if (part == 0) Sg[ent] = acc;
+            double a0 = 0.0, a1 = 0.0;
+            int c = c_lo;
+            for (; c + 1 < n; c += 2) {
+                a0 = fma(xi[c], xj[c], a0);
+                a1 = fma(xi[c + 1], xj[c + 1], a1);
+            }
+            if (c < n) a0 = fma(xi[c], xj[c], a0);
+            Sg[tid] = a0 + a1;
         }
         __syncthreads();
-        // ---- norms, signs, x0 += D |x|, tau (functions.py:50-55); T by 8 lanes (dlarft)
+        // ---- norms, signs, x0 += D |x|, tau (functions.py:50-55); T by 16 lanes (dlarft)
         if (w == 0) {
             double ca = 0.0;
             int neg = 0;
-            if (lane < 8) {
+            if (lane < 16) {
                 const int m = c_lo + lane;
                 const bool valid = m < n - 1;
-                const double nu = Sg[lane * 9], x0 = X[lane * LDX + m];
+                const double nu = Sg[lane * 17], x0 = X[lane * LDX + m];
                 const double d = (x0 != 0.0) ? (x0 > 0 ? 1.0 : -1.0) : 1.0;
                 ca = valid ? d * sqrt(nu) : 0.0;
                 const double x0n = x0 + ca;
@@ -586,57 +589,71 @@ k_basis_wy_big(int n, const double *__restrict__ normals, int nn_pad, double *__
             neg = __popc(__ballot_sync(0xffffffffu, neg != 0));
             if (lane == 0) n_negative += neg;
             // modified leading elements: S_ij += (x_j[0]' - x_j[0]) x_i[j - i] for i < j
-            double cj[8];
+            double cj[16];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) cj[j] = __shfl_sync(0xffffffffu, ca, j);
+            for (int j = 0; j < 16; ++j) cj[j] = __shfl_sync(0xffffffffu, ca, j);
             __syncwarp();
-            if (lane < 8) {
+            if (lane < 16) {
                 const int i = lane;
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (i < j) Sg[i * 8 + j] = fma(cj[j], X[i * LDX + c_lo + j], Sg[i * 8 + j]);
+                for (int j = 0; j < 16; ++j)
+                    if (i < j) Sg[i * 16 + j] = fma(cj[j], X[i * LDX + c_lo + j], Sg[i * 16 + j]);
             }
             __syncwarp();
-            if (lane < 8) X[lane * LDX + c_lo + lane] += ca;
+            if (lane < 16) X[lane * LDX + c_lo + lane] += ca;
             __syncwarp();
-            if (lane < 8) {
+            if (lane < 16) {
                 const int i = lane;
-                double trow[8];
+                double trow[16];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) trow[j] = (j == i) ? tau[i] : 0.0;
+                for (int j = 0; j < 16; ++j) trow[j] = (j == i) ? tau[i] : 0.0;
 #pragma unroll
-                for (int j = 1; j < 8; ++j) {
+                for (int j = 1; j < 16; ++j) {
                     double acc = 0.0;
 #pragma unroll
-                    for (int l = 0; l < 8; ++l)
-                        if (l >= i && l < j) acc = fma(trow[l], Sg[l * 8 + j], acc);
+                    for (int l = 0; l < 16; ++l)
+                        if (l >= i && l < j) acc = fma(trow[l], Sg[l * 16 + j], acc);
                     if (i < j) trow[j] = -tau[j] * acc;
                 }
 #pragma unroll
-                for (int j = 0; j < 8; ++j) Tg[i * 8 + j] = trow[j];
+                for (int j = 0; j < 16; ++j) Tg[i * 16 + j] = trow[j];
             }
         }
         __syncthreads();
-        // ---- N[8g:, 8g:] <- N - ((N V) T^T) V^T, one row tile per warp at a time
-        const double tb0 = Tg[q * 8 + 2 * r], tb1 = Tg[q * 8 + 2 * r + 1];
-        for (int rt = g + w; rt < NT; rt += 8) {
+        // ---- N[16g:, 16g:] <- N - ((N V) T^T) V^T, one 8-row tile per warp at a time.
+        // B fragments of T^T blocks: lane (q,r) supplies T[row q'][col l] as B[k = l][n = q'].
+        const double t11a = Tg[q * 16 + 2 * r], t11b = Tg[q * 16 + 2 * r + 1];
+        const double t12a = Tg[q * 16 + 8 + 2 * r], t12b = Tg[q * 16 + 8 + 2 * r + 1];
+        const double t22a = Tg[(8 + q) * 16 + 8 + 2 * r], t22b = Tg[(8 + q) * 16 + 8 + 2 * r + 1];
+        const double *Xa = X, *Xb = X + 8 * LDX;
+        for (int rt = 2 * g + w; rt < NT; rt += 8) {
             double2 *Nrow = reinterpret_cast<double2 *>(N + (size_t)(8 * rt + q) * n) + r;
-            double y00 = 0.0, y01 = 0.0, y10 = 0.0, y11 = 0.0;
-            for (int ct = g; ct < NT; ++ct) {
+            double ya0 = 0.0, ya1 = 0.0, ya2 = 0.0, ya3 = 0.0;  // Ya: two partial accumulators
+            double yb0 = 0.0, yb1 = 0.0, yb2 = 0.0, yb3 = 0.0;  // Yb
+            for (int ct = 2 * g; ct < NT; ++ct) {
                 const double2 a = Nrow[4 * ct];
-                const double b0 = X[q * LDX + 8 * ct + 2 * r], b1 = X[q * LDX + 8 * ct + 2 * r + 1];
-                dmma8x8x4(y00, y01, a.x, b0);
-                dmma8x8x4(y10, y11, a.y, b1);
+                const int c0 = 8 * ct + 2 * r;
+                dmma8x8x4(ya0, ya1, a.x, Xa[q * LDX + c0]);
+                dmma8x8x4(yb0, yb1, a.x, Xb[q * LDX + c0]);
+                dmma8x8x4(ya2, ya3, a.y, Xa[q * LDX + c0 + 1]);
+                dmma8x8x4(yb2, yb3, a.y, Xb[q * LDX + c0 + 1]);
             }
-            double z0 = 0.0, z1 = 0.0;
-            dmma8x8x4(z0, z1, y00 + y10, tb0);
-            dmma8x8x4(z0, z1, y01 + y11, tb1);
-            // y00/y01 = Y[q][2r], Y[q][2r+1] halves from the even-k MMAs, y10/y11 from the odd-k ones
-            for (int ct = g; ct < NT; ++ct) {
+            const double Ya0 = ya0 + ya2, Ya1 = ya1 + ya3, Yb0 = yb0 + yb2, Yb1 = yb1 + yb3;
+            // Z = Y T^T with T = [[T11, T12], [0, T22]]:  Za = Ya T11^T + Yb T12^T, Zb = Yb T22^T
+            double za0 = 0.0, za1 = 0.0, zb0 = 0.0, zb1 = 0.0;
+            dmma8x8x4(za0, za1, Ya0, t11a);
+            dmma8x8x4(zb0, zb1, Yb0, t22a);
+            dmma8x8x4(za0, za1, Ya1, t11b);
+            dmma8x8x4(zb0, zb1, Yb1, t22b);
+            dmma8x8x4(za0, za1, Yb0, t12a);
+            dmma8x8x4(za0, za1, Yb1, t12b);
+            for (int ct = 2 * g; ct < NT; ++ct) {
                 double2 c2 = Nrow[4 * ct];
-                const double v0 = X[(2 * r) * LDX + 8 * ct + q], v1 = X[(2 * r + 1) * LDX + 8 * ct + q];
-                dmma8x8x4(c2.x, c2.y, -z0, v0);
-                dmma8x8x4(c2.x, c2.y, -z1, v1);
+                const int cc = 8 * ct + q;
+                dmma8x8x4(c2.x, c2.y, -za0, Xa[(2 * r) * LDX + cc]);
+                dmma8x8x4(c2.x, c2.y, -za1, Xa[(2 * r + 1) * LDX + cc]);
+                dmma8x8x4(c2.x, c2.y, -zb0, Xb[(2 * r) * LDX + cc]);
+                dmma8x8x4(c2.x, c2.y, -zb1, Xb[(2 * r + 1) * LDX + cc]);
                 Nrow[4 * ct] = c2;
             }
         }
@@ -658,7 +675,7 @@ k_basis_wy_big(int n, const double *__restrict__ normals, int nn_pad, double *__
 static inline bool wy_big_supported(int n) { return n > 128 && n <= 512 && (n % 8) == 0; }
 static inline int launch_basis_wy_big(cudaStream_t st, int n, const double *normals,
                                       double *store, int64_t tasks) {
-    const size_t smem = (size_t)(8 * (n + 1) + n + 64 + 64 + 8) * sizeof(double);
+    const size_t smem = (size_t)(16 * (n + 1) + n + 256 + 256 + 16) * sizeof(double);
     if (cudaFuncSetAttribute(k_basis_wy_big, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)smem) != cudaSuccess)
         return -1;
