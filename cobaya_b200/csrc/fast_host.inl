@@ -119,7 +119,9 @@ static int pack_fast(cb2_engine *h) {
 // ---------------------------------------------------------------------------------------
 static int pack_stream(cb2_engine *h) {
     h->stream_ready = false;
-    if (h->D <= 64 || !stream_step_supported(h->M, h->likes.size())) return 0;
+    // D <= 64 is the territory of the register-resident kernels; the streamed path takes what
+    // they refuse (several components over disjoint parameters)
+    if ((h->D <= 64 && h->fast_ready) || !stream_step_supported(h->M, h->likes.size())) return 0;
     const int D = h->D, NT = (D + 7) / 8, DP = 8 * NT;
     const int NL = (int)h->likes.size();
     // whitened coordinate a = aoff[l] + a' for component l; every sampled parameter must be

@@ -1,4 +1,5 @@
-// kernels_stream.cuh -- the "streamed" Metropolis path for 64 < D <= 128 (sm_100a).
+// kernels_stream.cuh -- the "streamed" Metropolis path: 64 < D <= 512, and D <= 64 for models
+// the register-resident kernels do not take (several gaussian_mixture components) (sm_100a).
 //
 // By linearity of the proposal map and of the Gaussian's whitening map, everything on the
 // proposal side of a Metropolis step (mcmc.py:545-562) is independent of the chain state:
@@ -758,6 +759,7 @@ static int launch_stream_products(cudaStream_t st, const double *pack, const Str
                                                        delta, wout);                         \
         break;
     switch (P.NT) {
+        CB2_SP(1) CB2_SP(2) CB2_SP(3) CB2_SP(4) CB2_SP(5) CB2_SP(6) CB2_SP(7) CB2_SP(8)
         CB2_SP(9) CB2_SP(10) CB2_SP(11) CB2_SP(12) CB2_SP(13) CB2_SP(14) CB2_SP(15) CB2_SP(16)
         default: return -1;
     }
@@ -774,6 +776,7 @@ static int launch_stream_whiten(cudaStream_t st, const double *pack, const Strea
         k_stream_whiten<N><<<grid, 256, 0, st>>>(pack, P, x, D, n_chains, ys);           \
         break;
     switch (P.NT) {
+        CB2_SW(1) CB2_SW(2) CB2_SW(3) CB2_SW(4) CB2_SW(5) CB2_SW(6) CB2_SW(7) CB2_SW(8)
         CB2_SW(9) CB2_SW(10) CB2_SW(11) CB2_SW(12) CB2_SW(13) CB2_SW(14) CB2_SW(15) CB2_SW(16)
         default: return -1;
     }
@@ -796,6 +799,7 @@ static int launch_stream_accept(cudaStream_t st, const ModelDev &M, const ChainS
         return cudaGetLastError() == cudaSuccess ? 0 : -2;                                  \
     }
 #define CB2_SA_L(C_, M_) CB2_SA(C_, M_, 1) CB2_SA(C_, M_, 2) CB2_SA(C_, M_, 3)
+    CB2_SA_L(1, 1) CB2_SA_L(1, 2) CB2_SA_L(1, 4) CB2_SA_L(2, 1) CB2_SA_L(2, 2) CB2_SA_L(2, 4)
     CB2_SA_L(3, 1) CB2_SA_L(3, 2) CB2_SA_L(3, 4) CB2_SA_L(4, 1) CB2_SA_L(4, 2) CB2_SA_L(4, 4)
 #undef CB2_SA_L
 #undef CB2_SA

@@ -433,6 +433,44 @@ def test_streamed_kernels_blocks_modes_priors(cuda_lib):
         assert st["weight"][c] == s_ref["weight"]
 
 
+def test_streamed_path_takes_two_components_at_small_d(cuda_lib):
+    """Two gaussian_mixture components of different speed over disjoint parameters at D = 12
+    (the shape of the reference's own speed-blocking tests, common_sampler.py:264-372): the
+    register-resident kernels take one component only, so this runs on the streamed kernels."""
+    from cobaya_b200.flatmodel import FlatModel, LikeSpec
+
+    rng = np.random.default_rng(23)
+    D, ns = 12, 4
+    a = LikeSpec.gaussian_mixture(np.arange(ns), [rng.uniform(-0.05, 0.05, ns)],
+                                  [_mixture_cov(ns, rng, scale=0.05)], name="slow")
+    b = LikeSpec.gaussian_mixture(np.arange(ns, D),
+                                  [rng.uniform(-0.05, 0.05, D - ns) for _ in range(2)],
+                                  [_mixture_cov(D - ns, rng, scale=0.05) for _ in range(2)],
+                                  name="fast")
+    fm = FlatModel(names=[f"p{i}" for i in range(D)], prior_kind=np.zeros(D, np.int32),
+                   lower=np.full(D, -1.0), upper=np.full(D, 1.0), loc=np.zeros(D),
+                   pscale=np.ones(D), periodic=np.zeros(D, np.int32), likes=[a, b],
+                   blocks=[list(range(ns)), list(range(ns, D))], oversampling=[1, 3],
+                   proposal_cov=np.diag(np.full(D, 0.04**2)), output_thin=2)
+    C, n = 9, 400
+    x0 = rng.uniform(-0.03, 0.03, (C, D))
+    eng = _engine(fm, C, seed=41, chain_id0=5, rows_cap=n)
+    eng.set_state(x0)
+    for k in (3, 150, 247):
+        eng.advance(k)
+    assert eng.last_step_kernel() == 3
+    st = eng.get_state()
+    assert not st["flags"].any()
+    ref = _oracle_rows(fm, 41, range(5, 5 + C), x0, n, 0)
+    for c in range(C):
+        rc, rows_ref, s_ref = ref[c]
+        rows = eng.rows(c)
+        assert rows.shape == rows_ref.shape, f"chain {c}"
+        np.testing.assert_array_equal(rows[:, 0], rows_ref[:, 0])
+        np.testing.assert_allclose(rows, rows_ref, rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(st["x"][c], s_ref["x"], rtol=RTOL, atol=ATOL)
+
+
 def test_producer_consumer_kernel_blocks_normal_prior_thinning(cuda_lib):
     """The producer/consumer DMMA kernel with two blocks + oversampling + thinning, a normal
     prior, burn-in and temperature (one mode, no periodic parameter), against the oracle;
