@@ -279,3 +279,20 @@ def test_products_and_output_files_roundtrip(tmp_path):
                                rtol=1e-7)
     np.testing.assert_allclose(half[["p0", "p1"]].to_numpy(),
                                s._ens.samples(skip_samples=0.5)[:, 2:4], rtol=0)
+    # .progress: the reference's format (mcmc.py:163-181,1067-1077), read by its own loader
+    import datetime
+
+    from cobaya.tools import load_DataFrame
+
+    for i, (N, acc, r1, rcl) in enumerate([(1200, 0.31, 0.8, None), (2400, 0.29, 0.05, 0.4)], 1):
+        s.progress.loc[i] = [N, datetime.datetime.now().isoformat(), acc, r1, rcl]
+    s.write_checkpoint()
+    assert "run.progress" in os.listdir(tmp_path)
+    with open(s.progress_filename()) as f:
+        lines = f.readlines()
+    assert lines[0].startswith("#") and len(lines) == 3
+    prog = load_DataFrame(s.progress_filename())
+    assert list(prog.columns) == ["N", "timestamp", "acceptance_rate", "Rminus1", "Rminus1_cl"]
+    np.testing.assert_allclose(prog["N"], [1200, 2400])
+    np.testing.assert_allclose(prog["Rminus1"], [0.8, 0.05])
+    assert np.isnan(prog["Rminus1_cl"][0]) and prog["Rminus1_cl"][1] == 0.4
