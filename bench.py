@@ -388,8 +388,9 @@ def run_gpu_arm(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "D": D, "chains_per_gpu": C,
                    "locksteps_per_step": locksteps, "checkpoints_in_timed_region": n_ckpt - ck0,
-                   "l2": "working set per step (268 MB of Haar bases + sample rows) exceeds "
-                         "the 126 MB L2; no explicit flush",
+                   "l2": "inputs larger than L2: every 256-proposal window streams 1.07 GB of "
+                         "Haar bases + 0.55 GB of normals + new sample rows through the 126 MB "
+                         "L2; no explicit flush",
                    "step_kernel": {0: "general", 1: "dmma", 2: "dmma-producer-consumer", 3: "dmma-streamed"}.get(
                        eng.last_step_kernel(), "?"),
                    "parallelism": f"chains sharded over {world} GPU(s), no data-path "
