@@ -166,8 +166,8 @@ k_stream_products(const double *__restrict__ pack, StreamPackDesc P, const doubl
 }
 
 // ---------------------------------------------------------------------------------------
-// k_stream_products1: the single-mode, triangular-L^-1 case with the two column sweeps
-// interleaved.  After column m of T the tile delta[m] is final: it is stored and immediately
+// k_stream_products1: the triangular-L^-1 case with the column sweeps of T and of the first
+// mode's L^-1 P interleaved (further modes are swept from the delta kept in registers).  After column m of T the tile delta[m] is final: it is stored and immediately
 // feeds column m of L^-1 P, after which w[m] is final too.  Direction tiles are loaded two
 // columns ahead instead of all at once, so a warp keeps 2 (not 3) D-vectors of accumulators
 // live and 12 instead of 8 warps fit an SM.
@@ -208,8 +208,9 @@ k_stream_products1(const double *__restrict__ pack, StreamPackDesc P,
     const double2 *fT = reinterpret_cast<const double2 *>(pack + P.off_T) + lane;
     const double2 *fA = reinterpret_cast<const double2 *>(pack + P.off_A) + lane;
     const size_t row = (size_t)task * n_b + (kvalid ? k : 0);
+    const int nmod = P.n_modes;
     double2 *od = reinterpret_cast<double2 *>(delta + row * DP) + r;
-    double2 *ow = reinterpret_cast<double2 *>(wout + row * DP) + r;
+    double2 *ow = reinterpret_cast<double2 *>(wout + row * nmod * DP) + r;
     double dl[NT][2], wv[NT][2], un[NT][2];
 #pragma unroll
     for (int n = 0; n < NT; ++n) { dl[n][0] = dl[n][1] = wv[n][0] = wv[n][1] = 0.0; }
@@ -262,6 +263,38 @@ k_stream_products1(const double *__restrict__ pack, StreamPackDesc P,
             }
         }
         if (kvalid) ow[4 * m] = make_double2(wv[m][0], wv[m][1]);
+    }
+    // further mixture modes: column sweeps of L_m^-1 P over the delta kept in registers
+    for (int km = 1; km < nmod; ++km) {
+        const double2 *fAk = fA + (size_t)km * P.blocks_A * 32;
+        double2 *owk = ow + (size_t)km * (DP / 2);
+#pragma unroll
+        for (int n = 0; n < NT; ++n) { wv[n][0] = 0.0; wv[n][1] = 0.0; }
+#pragma unroll
+        for (int m = 0; m < NT; ++m) {
+            if (m >= m_lo) {
+#pragma unroll
+                for (int n0 = (m & ~3); n0 < NT; n0 += 4) {
+                    double2 b[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int nt = n0 + u;
+                        if (nt < NT && nt >= m) b[u] = __ldg(fAk + ((nt * (nt + 1)) / 2 + m) * 32);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int nt = n0 + u;
+                        if (nt < NT && nt >= m) dmma8x8x4(wv[nt][0], wv[nt][1], dl[m][0], b[u].x);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int nt = n0 + u;
+                        if (nt < NT && nt >= m) dmma8x8x4(wv[nt][0], wv[nt][1], dl[m][1], b[u].y);
+                    }
+                }
+            }
+            if (kvalid) owk[4 * m] = make_double2(wv[m][0], wv[m][1]);
+        }
     }
 }
 
@@ -328,7 +361,7 @@ __device__ __forceinline__ double warp_sum_all(double v) {
 
 // (capping the registers for 5 CTAs/SM was measured: the spills cost what the occupancy gains)
 template <int NC, int NM, int NL>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, (NM >= 3) ? 3 : 1)
 k_stream_accept(ModelDev M, ChainState S, StreamWindow SW, const double *__restrict__ pack,
                 StreamPackDesc P, const double2 *__restrict__ draws,
                 const int2 *__restrict__ plan, const double *__restrict__ ys_in,
@@ -747,7 +780,7 @@ static int launch_stream_products(cudaStream_t st, const double *pack, const Str
                                   double *delta, double *wout) {
     const int64_t wts = n_tasks * ((n_b + 7) / 8);
     const unsigned grid = (unsigned)((wts + 7) / 8);
-    const bool one = P.n_modes == 1 && P.tri_like;  // interleaved sweeps, 12 warps/SM
+    const bool one = P.tri_like != 0;  // interleaved sweeps (triangular L^-1 P), 12 warps/SM
     const unsigned grid1 = (unsigned)((wts + 3) / 4);
 #define CB2_SP(N)                                                                            \
     case N:                                                                                  \
@@ -790,7 +823,7 @@ static int launch_stream_accept(cudaStream_t st, const ModelDev &M, const ChainS
                                 const double *ys, int64_t n_chains, int n_steps) {
     const unsigned grid = (unsigned)((n_chains + 3) / 4);
     const int NC = (P.DP + 31) / 32;
-    const int NM = P.n_modes == 1 ? 1 : (P.n_modes == 2 ? 2 : 4);
+    const int NM = P.n_modes;  // 1..4
     const int NL = P.n_like;
 #define CB2_SA(C_, M_, L_)                                                                  \
     if (NC == C_ && NM == M_ && NL == L_) {                                                 \
@@ -799,8 +832,10 @@ static int launch_stream_accept(cudaStream_t st, const ModelDev &M, const ChainS
         return cudaGetLastError() == cudaSuccess ? 0 : -2;                                  \
     }
 #define CB2_SA_L(C_, M_) CB2_SA(C_, M_, 1) CB2_SA(C_, M_, 2) CB2_SA(C_, M_, 3)
-    CB2_SA_L(1, 1) CB2_SA_L(1, 2) CB2_SA_L(1, 4) CB2_SA_L(2, 1) CB2_SA_L(2, 2) CB2_SA_L(2, 4)
-    CB2_SA_L(3, 1) CB2_SA_L(3, 2) CB2_SA_L(3, 4) CB2_SA_L(4, 1) CB2_SA_L(4, 2) CB2_SA_L(4, 4)
+    CB2_SA_L(1, 1) CB2_SA_L(1, 2) CB2_SA_L(1, 3) CB2_SA_L(1, 4)
+    CB2_SA_L(2, 1) CB2_SA_L(2, 2) CB2_SA_L(2, 3) CB2_SA_L(2, 4)
+    CB2_SA_L(3, 1) CB2_SA_L(3, 2) CB2_SA_L(3, 3) CB2_SA_L(3, 4)
+    CB2_SA_L(4, 1) CB2_SA_L(4, 2) CB2_SA_L(4, 3) CB2_SA_L(4, 4)
 #undef CB2_SA_L
 #undef CB2_SA
     return -1;
