@@ -24,6 +24,9 @@
 #define CB2_STREAM_MAX_D 512   /* 64 < D <= 128: DMMA products; above: plain GEMMs (cuBLAS) */
 #define CB2_STREAM_FRAG_MAX_D 128
 #define CB2_STREAM_MAX_MODES 4
+#ifndef CB2_STREAM_STAGE
+#define CB2_STREAM_STAGE 4   /* look-ahead (steps) of the accept kernel's cp.async staging; 0: registers */
+#endif
 #define CB2_STREAM_MAX_LIKES 3
 
 struct StreamPackDesc {
@@ -401,6 +404,70 @@ k_stream_accept(ModelDev M, ChainState S, StreamWindow SW, const double *__restr
     const int2 *my_plan = plan + chain * (int64_t)n_steps;
     const bool temp_one = M.temperature == 1.0;
 
+#if CB2_STREAM_STAGE
+    // The proposal-side vectors are staged through shared memory with cp.async, CB2_STREAM_STAGE
+    // steps ahead of their use: every lane copies exactly the elements it will read itself, so
+    // no cross-lane synchronisation is needed, only cp.async.wait_group.  HBM latency (the
+    // chain is serial) is hidden by the look-ahead instead of by occupancy.
+    constexpr int KS = CB2_STREAM_STAGE;
+    constexpr int VS = (1 + NM) * NC;                     // doubles per lane and step
+    extern __shared__ __align__(16) double stage_sm[];
+    double *my_stage = stage_sm + (size_t)(threadIdx.x >> 5) * KS * VS * 32 + lane;
+    int2 pl_q = __ldg(my_plan);                           // plan entry of the next step to issue
+    auto issue = [&](int t) {
+        if (t < n_steps) {
+            const int2 pl = pl_q;
+            if (t + 1 < n_steps) pl_q = __ldg(my_plan + t + 1);
+            const int b = pl.y;
+            const double *dp, *wp;
+            if (M.bsize[b] >= 2) {
+                dp = SW.delta[b] + (size_t)pl.x * DP;
+                wp = SW.wv[b] + (size_t)pl.x * P.n_modes * DP;
+            } else {
+                dp = pack + P.off_d1 + (size_t)b * DP;
+                wp = pack + P.off_w1 + (size_t)b * P.n_modes * DP;
+            }
+            double *slot = my_stage + (size_t)(t % KS) * VS * 32;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const int j = lane + 32 * c;
+                if (j < DP) {
+                    const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(slot + (size_t)c * 32);
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d0), "l"(dp + j));
+#pragma unroll
+                    for (int m = 0; m < NM; ++m)
+                        if (m < P.n_modes) {
+                            const uint32_t d1 = (uint32_t)__cvta_generic_to_shared(
+                                slot + (size_t)((1 + m) * NC + c) * 32);
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d1),
+                                         "l"(wp + (size_t)m * DP + j));
+                        }
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");  // one group per step, even if empty
+    };
+#pragma unroll
+    for (int t = 0; t < KS; ++t) issue(t);
+    double2 dr = __ldg(my_draws);
+    for (int s = 0; s < n_steps; ++s) {
+        const double rs = dr.x * M.proposal_scale, e_acc = dr.y;
+        if (s + 1 < n_steps) dr = __ldg(my_draws + s + 1);
+        asm volatile("cp.async.wait_group %0;" ::"n"(KS - 1) : "memory");
+        double dl[NC], wl[NM][NC];
+        {
+            const double *slot = my_stage + (size_t)(s % KS) * VS * 32;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const int j = lane + 32 * c;
+                dl[c] = (j < DP) ? slot[(size_t)c * 32] : 0.0;
+#pragma unroll
+                for (int m = 0; m < NM; ++m)
+                    wl[m][c] = (j < DP && m < P.n_modes) ? slot[(size_t)((1 + m) * NC + c) * 32] : 0.0;
+            }
+        }
+        issue(s + KS);  // refills the slot just read
+#else
     // the proposal-side vectors of step s + 1 are loaded during step s
     double dn[NC], wn[NM][NC];
     double2 dr;
@@ -436,6 +503,7 @@ k_stream_accept(ModelDev M, ChainState S, StreamWindow SW, const double *__restr
             for (int m = 0; m < NM; ++m) wl[m][c] = wn[m][c];
         }
         if (s + 1 < n_steps) fetch(s + 1);
+#endif
         // ---- trial point, bounds and priors (prior.py:733-763)
         bool bad = false;
         double ps = 0.0, qs[NL][NM];
@@ -470,34 +538,53 @@ k_stream_accept(ModelDev M, ChainState S, StreamWindow SW, const double *__restr
         bad = __any_sync(0xffffffffu, bad);
         if (M.any_normal) ps = warp_sum_all(ps);
         const double t_prior = bad ? -CUDART_INF : (M.uniform_logp + ps);
-        // ---- GaussianMixture.logp (gaussian_mixture.py:138-163), one term per component
+        // ---- GaussianMixture.logp (gaussian_mixture.py:138-163), one term per component.
+        // The log-sum-exp terms are spread over the lanes (lane 4 l + m owns mode m of
+        // component l): one exp and one log per step instead of one per mode and component.
         double t_ll[NL], t_like = 0.0;
+        {
+            double lp[NL][NM], mx[NL];
 #pragma unroll
-        for (int l = 0; l < NL; ++l) {
-            const int nm = P.like_modes[l];
-            double lp[NM];
+            for (int l = 0; l < NL; ++l) {
+                const int nm = P.like_modes[l];
+                mx[l] = -CUDART_INF;
 #pragma unroll
-            for (int m = 0; m < NM; ++m)
-                lp[m] = (m < nm) ? -0.5 * (__ldg(pack + P.off_c0 + l * CB2_STREAM_MAX_MODES + m) +
-                                           warp_sum_all(qs[l][m]))
-                                 : -CUDART_INF;
-            if (NM == 1 || nm == 1) t_ll[l] = lp[0];
-            else {
-                double mx = lp[0];
-#pragma unroll
-                for (int m = 1; m < NM; ++m) mx = fmax(mx, lp[m]);
-                if (mx == -CUDART_INF) t_ll[l] = -CUDART_INF;
-                else {
-                    double acc = 0.0;
-#pragma unroll
-                    for (int m = 0; m < NM; ++m)
-                        if (m < nm)
-                            acc += __ldg(pack + P.off_w + l * CB2_STREAM_MAX_MODES + m) *
-                                   exp(lp[m] - mx);
-                    t_ll[l] = log(acc) + mx;
+                for (int m = 0; m < NM; ++m) {
+                    lp[l][m] = (m < nm)
+                                   ? -0.5 * (__ldg(pack + P.off_c0 + l * CB2_STREAM_MAX_MODES + m) +
+                                             warp_sum_all(qs[l][m]))
+                                   : -CUDART_INF;
+                    mx[l] = fmax(mx[l], lp[l][m]);
                 }
             }
-            t_like += t_ll[l];
+            if (NM == 1) {
+#pragma unroll
+                for (int l = 0; l < NL; ++l) t_ll[l] = lp[l][0];
+            } else {
+                const int l_me = lane >> 2, m_me = lane & 3;
+                double my_lp = -CUDART_INF, my_mx = 0.0;
+#pragma unroll
+                for (int l = 0; l < NL; ++l)
+#pragma unroll
+                    for (int m = 0; m < NM; ++m)
+                        if (l_me == l && m_me == m) { my_lp = lp[l][m]; my_mx = mx[l]; }
+                double e = 0.0;
+                if (l_me < NL && m_me < NM && my_lp != -CUDART_INF)
+                    e = __ldg(pack + P.off_w + l_me * CB2_STREAM_MAX_MODES + m_me) *
+                        exp(my_lp - my_mx);
+                e += __shfl_xor_sync(0xffffffffu, e, 1);
+                e += __shfl_xor_sync(0xffffffffu, e, 2);
+                const double ll_me = log(e) + my_mx;
+#pragma unroll
+                for (int l = 0; l < NL; ++l) {
+                    const double v = __shfl_sync(0xffffffffu, ll_me, 4 * l);
+                    // a single-mode component keeps its exact value (no exp/log round trip)
+                    t_ll[l] = (P.like_modes[l] == 1) ? lp[l][0]
+                                                     : (mx[l] == -CUDART_INF ? -CUDART_INF : v);
+                }
+            }
+#pragma unroll
+            for (int l = 0; l < NL; ++l) t_like += t_ll[l];
         }
         const double t_post = bad ? -CUDART_INF : (t_prior + t_like);
         // ---- metropolis_accept (mcmc.py:670-683)
@@ -827,8 +914,14 @@ static int launch_stream_accept(cudaStream_t st, const ModelDev &M, const ChainS
     const int NL = P.n_like;
 #define CB2_SA(C_, M_, L_)                                                                  \
     if (NC == C_ && NM == M_ && NL == L_) {                                                 \
-        k_stream_accept<C_, M_, L_><<<grid, 128, 0, st>>>(M, S, SW, pack, P, draws, plan,   \
-                                                          ys, n_chains, n_steps);           \
+        const size_t sm = (size_t)CB2_STREAM_STAGE * (1 + M_) * C_ * 32 * 8 * 4;            \
+        if (sm > 48 * 1024 &&                                                               \
+            cudaFuncSetAttribute(k_stream_accept<C_, M_, L_>,                               \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) !=   \
+                cudaSuccess)                                                                \
+            return -3;                                                                      \
+        k_stream_accept<C_, M_, L_><<<grid, 128, sm, st>>>(M, S, SW, pack, P, draws, plan,  \
+                                                           ys, n_chains, n_steps);          \
         return cudaGetLastError() == cudaSuccess ? 0 : -2;                                  \
     }
 #define CB2_SA_L(C_, M_) CB2_SA(C_, M_, 1) CB2_SA(C_, M_, 2) CB2_SA(C_, M_, 3)
