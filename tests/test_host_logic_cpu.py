@@ -124,12 +124,15 @@ WORKER = textwrap.dedent("""
     mn, mx, sm = td.all_reduce_min_max_sum([min(len(r) for r in mine)],
                                            [max(len(r) for r in mine)],
                                            [sum(len(r) for r in mine)])
+    # samples(combined=True) / to_getdist: per-rank row arrays gathered on every rank
+    gathered = td.all_gather_object([np.asarray(r) for r in mine])
+    n_gathered = [sum(len(r) for r in part) for part in gathered]
     # one file per rank: the two ranks' stdout lines can interleave
     with open(os.path.join(os.path.dirname(os.path.abspath(__file__)),
                            f"rank{{td.rank}}.json"), "w") as f:
         json.dump(dict(rank=td.rank, R=res["Rminus1"], N=res["N"],
                        W00=float(res["W"][0, 0]), mn=int(mn[0]),
-                       mx=int(mx[0]), sm=int(sm[0])), f)
+                       mx=int(mx[0]), sm=int(sm[0]), n_gathered=n_gathered), f)
     dist.destroy_process_group()
 """)
 
@@ -155,6 +158,9 @@ def test_world_size_2_gloo_allreduce_gives_identical_verdict_on_every_rank(tmp_p
     np.testing.assert_allclose(res[0]["R"], single["Rminus1"], rtol=1e-10)
     assert res[0]["N"] == single["N"] == sum(len(r) for r in rows)
     assert res[0]["mn"] == min(len(r) for r in rows) and res[0]["mx"] == max(len(r) for r in rows)
+    # every rank holds every rank's chains after the gather, in rank order
+    expect = [sum(len(r) for r in rows[:3]), sum(len(r) for r in rows[3:])]
+    assert res[0]["n_gathered"] == expect and res[1]["n_gathered"] == expect
 
 
 def test_cabi_exports_every_declared_symbol():
