@@ -302,6 +302,37 @@ def info_g5():
     return info, mean, cov, cov * 0.5
 
 
+def info_g7():
+    """72-D (the streamed kernels' territory, D > 64): 2-mode mixture with weights, two blocks of
+    36 parameters with oversampling + thinning, one normal prior, burn-in."""
+    rng = np.random.default_rng(17)
+    D = 72
+    means = np.stack([rng.uniform(-0.05, 0.05, D), rng.uniform(-0.05, 0.05, D)])
+    covs = []
+    for k in range(2):
+        A = rng.standard_normal((D, 2 * D))
+        C = A @ A.T / (2 * D)
+        s = 0.04 * (1 + rng.uniform(0, 1, D))
+        d = np.sqrt(np.diag(C))
+        covs.append((C / d[:, None] / d[None, :]) * s[:, None] * s[None, :])
+    names = [f"p{i}" for i in range(D)]
+    params = {n: {"prior": {"min": -1, "max": 1}, "ref": 0.0} for n in names}
+    params["p5"] = {"prior": {"dist": "norm", "loc": 0.0, "scale": 0.4}, "ref": 0.0}
+    S0 = np.diag(np.full(D, 0.03**2))
+    perm = [int(i) for i in rng.permutation(D)]
+    slow, fast = [names[i] for i in perm[:36]], [names[i] for i in perm[36:]]
+    return {
+        "likelihood": {"gaussian_mixture": {
+            "means": means.tolist(), "covs": [c.tolist() for c in covs],
+            "weights": [0.6, 0.4], "input_params": names, "derived": False}},
+        "params": params,
+        "sampler": {"mcmc": {"covmat": S0, "covmat_params": names,
+                             "blocking": [[1, slow], [2, fast]],
+                             "oversample_thin": True, "learn_proposal": False,
+                             "measure_speeds": False, "burn_in": 3, "seed": 6}},
+    }, means, np.array(covs), S0
+
+
 def _prior_shapes(model):
     a, b, loc, scale = [], [], [], []
     for pdf in model.prior.pdf:
@@ -514,6 +545,7 @@ if __name__ == "__main__":
         ("g3_dragging", info_g3, 400, 103, [1]),
         ("g4_block1d", info_g4, 1200, 104, [5]),
         ("g5_scipy_priors", info_g5, 1500, 105, [2]),
+        ("g7_stream72", info_g7, 450, 107, [2, 9]),
     ]:
         if want(name):
             dump_case(name, fn, n, seed=seed, chain_ids=cids)
