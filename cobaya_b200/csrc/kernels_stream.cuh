@@ -170,8 +170,9 @@ k_stream_products(const double *__restrict__ pack, StreamPackDesc P, const doubl
 
 // ---------------------------------------------------------------------------------------
 // k_stream_products1: the triangular-L^-1 case with the column sweeps of T and of the first
-// mode's L^-1 P interleaved (further modes are swept from the delta kept in registers).  After column m of T the tile delta[m] is final: it is stored and immediately
-// feeds column m of L^-1 P, after which w[m] is final too.  Direction tiles are loaded two
+// mode's L^-1 P interleaved (further modes are swept from the delta kept in registers).
+// After column m of T the tile delta[m] is final: it is stored and immediately feeds column m
+// of L^-1 P, after which w[m] is final too.  Direction tiles are loaded two
 // columns ahead instead of all at once, so a warp keeps 2 (not 3) D-vectors of accumulators
 // live and 12 instead of 8 warps fit an SM.
 // ---------------------------------------------------------------------------------------
