@@ -190,10 +190,12 @@ int cb2_timer_stop(cb2_engine *h, float *ms);
 int cb2_set_profiling(cb2_engine *h, int32_t on);
 int cb2_kernel_times(cb2_engine *h, double ms[5], int64_t n[5], int32_t reset);
 /* which step kernel the last cb2_advance used: 0 = general warp-per-chain,
- * 1 = DMMA (mma.sync.m8n8k4.f64) register-resident, 2 = DMMA producer/consumer */
+ * 1 = DMMA (mma.sync.m8n8k4.f64) register-resident, 2 = DMMA producer/consumer,
+ * 3 = streamed (batched DMMA / cuBLAS products of every proposal direction + accept chain) */
 int cb2_last_step_kernel(const cb2_engine *h);
 const char *cb2_debug_message(const cb2_engine *h); /* why a faster kernel was not used */
-/* 0 auto, 1 force the general kernels, 2 fast kernels without the producer/consumer one */
+/* 0 auto, 1 force the general kernels, 2 fast kernels without the producer/consumer one;
+ * +4: Householder sweep of the Haar bases with DFMA instead of the tensor pipe (n <= 64) */
 int cb2_set_kernel_policy(cb2_engine *h, int32_t policy);
 
 #ifdef __cplusplus
