@@ -10,6 +10,17 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "timeout: per-test time limit (pytest-timeout)")
+
+
+def pytest_collection_modifyitems(config, items):
+    """A hung kernel must end as a failed test, not as a stalled box: every GPU test gets a
+    generous time limit when pytest-timeout is installed (the whole GPU suite runs in < 1 min)."""
+    if not config.pluginmanager.hasplugin("timeout"):
+        return
+    for item in items:
+        if item.get_closest_marker("gpu") and not item.get_closest_marker("timeout"):
+            item.add_marker(pytest.mark.timeout(600))
 
 
 @pytest.fixture(scope="session")
