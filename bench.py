@@ -417,9 +417,12 @@ def run_gpu_arm(args):
         "wall_s_timed_region": t_wall,
     }
     try:  # R-1 of means at the convergence checks of this run (warm-up + timed region)
+        def _fin(v):
+            return float(v) if v is not None and np.isfinite(v) else None
+
         line["convergence"] = [
-            {"accepted_steps": int(c.N), "Rminus1": None if c.Rminus1 is None else float(c.Rminus1),
-             "acceptance_rate": float(c.acceptance_rate), "covmat_learned": bool(c.learned)}
+            {"accepted_steps": int(c.N), "Rminus1": _fin(c.Rminus1),
+             "acceptance_rate": _fin(c.acceptance_rate), "covmat_learned": bool(c.learned)}
             for c in smp.progress]
     except Exception:  # never lose the benchmark line over the extra report
         pass
