@@ -61,22 +61,6 @@ def fp64_peak():
         return FP64_NOMINAL_TFLOPS, "nominal"
 
 
-def build_problem(seed=1):
-    from cobaya_b200.flatmodel import FlatModel, synthetic_gaussian_cov
-
-    cov = synthetic_gaussian_cov(D)
-    # start from a deliberately imperfect proposal (diagonal of the truth) so that
-    # learning has something to do, as SURVEY.md section 8d suggests
-    prop0 = np.diag(np.diag(cov))
-    fm = FlatModel.gaussian(np.zeros(D), cov, bounds=(-1.0, 1.0), proposal_cov=prop0)
-    return fm, cov
-
-
-def start_points(fm, cov, n, rank, seed=1):
-    rng = np.random.default_rng([seed, rank])
-    return rng.multivariate_normal(np.zeros(D), cov, size=n)  # ref: N(0, Sigma)
-
-
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons DURING the timed region."""
 
@@ -122,26 +106,27 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------ CPU legs
-def cpu_oracle_baseline(fm, cov, target_seconds=12.0):
+def cpu_oracle_baseline(fm, prob, target_seconds=12.0):
     """The C oracle (a scalar port of the reference algorithm) on the host cores, on a
     bounded sample of the same workload."""
     from oracle import oracle as orc
 
     cores = os.cpu_count() or 1
     om = orc.OracleModel(fm)
-    x0 = start_points(fm, cov, 4 * cores, rank=999)
+    x0 = prob.start(4 * cores, 999)
     chains = [orc.OracleChain(om, 1, 10**6 + c, x0[c]) for c in range(len(x0))]
+    cyc = max(1, fm.cycle_length)
     t = time.perf_counter()
-    orc.ensemble_advance(chains, 64, store=False, n_threads=cores)
+    orc.ensemble_advance(chains, cyc, store=False, n_threads=cores)
     dt = time.perf_counter() - t
-    rate = len(chains) * 64 / dt
-    n = int(max(64, min(20000, target_seconds * rate / len(chains))) // 64 * 64)
+    rate = len(chains) * cyc / dt
+    n = int(max(cyc, min(20000, target_seconds * rate / len(chains))) // cyc * cyc)
     t = time.perf_counter()
     orc.ensemble_advance(chains, n, store=False, n_threads=cores)
     dt = time.perf_counter() - t
     return {"value": len(chains) * n / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{len(chains)} chains x {n} proposals of the same 64-D target "
-                      f"(oracle/mcmc_oracle.c, OpenMP over chains), {dt:.1f} s"}
+            "sample": f"{len(chains)} chains x {n} proposals of the same target ({prob.key}; "
+                      f"oracle/mcmc_oracle.c, OpenMP over chains), {dt:.1f} s"}
 
 
 _REF_WORKER = r"""
@@ -192,15 +177,18 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    fm, cov = build_problem()
+    from cobaya_b200 import problems
+
+    prob = problems.get(args.config)
+    fm = prob.fm
     cores = os.cpu_count() or 1
     steps, warm = args.steps, args.warmup
     peak, _ = peaks()
     base = {"metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warm, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "impl": "reference", "gpu_launches": 0,
-            "config": {"workload": WORKLOAD, "D": D}}
-    if reference_available():
+            "config": {"workload": prob.workload, "D": fm.D}}
+    if reference_available() and prob.key == "c1":
         n_samples = 250  # accepted rows per chain per step (about 0.15 s of run())
         procs = []
         t0 = time.perf_counter()
@@ -237,7 +225,8 @@ def run_reference_arm(args):
                              "d2h_bytes_per_step": 0})
             emit(base)
             return
-    cb = cpu_oracle_baseline(fm, cov, target_seconds=max(5.0, 2.0 * steps))
+    # configs[2]/[3] (and a box without the reference package): the oracle port
+    cb = cpu_oracle_baseline(fm, prob, target_seconds=max(5.0, 2.0 * steps))
     base.update(value=cb["value"], ms_per_step=None, cpu_baseline=cb,
                 e2e={"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
                      "d2h_bytes_per_step": 0})
@@ -245,6 +234,60 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------ GPU arm
+KERNEL_NAMES = {0: "general", 1: "dmma", 2: "dmma-producer-consumer", 3: "dmma-streamed"}
+
+
+def e2e_through_cobaya_run(chains, max_samples=200):
+    """The README quick start, timed: ``cobaya.run.run(info)`` with ``sampler: mcmc`` resolved
+    to the engine (install_as_mcmc), 64-D target, ``chains_per_gpu`` chains, no output
+    prefix; wall clock around run(): model construction, 8192 start points drawn through the
+    reference's own ``Model.get_valid_point``, sampling, bulk hand-over of every stored row
+    into a real SampleCollection.  Needs the reference package (baseline/_ref)."""
+    if not reference_available():
+        return {"unavailable": "reference package not installed under baseline/_ref"}
+    for p_ in (os.path.join(ROOT, "oracle", "shims"), os.path.join(ROOT, "baseline", "_ref")):
+        if p_ not in sys.path:
+            sys.path.insert(0, p_)
+    import logging
+
+    logging.disable(logging.CRITICAL)
+    try:
+        from cobaya.run import run
+
+        import cobaya_b200.plugin as plugin
+        from cobaya_b200.flatmodel import synthetic_gaussian_cov
+
+        cov = synthetic_gaussian_cov(D)
+        names = [f"x{i}" for i in range(D)]
+        info = {"likelihood": {"gaussian_mixture": {"means": [np.zeros(D)], "covs": [cov],
+                                                    "input_params": names, "derived": False}},
+                "params": {n: {"prior": {"min": -1, "max": 1},
+                               "ref": {"dist": "norm", "loc": 0, "scale": 0.001}} for n in names},
+                "sampler": {"mcmc": {"covmat": np.diag(np.diag(cov)), "covmat_params": names,
+                                     "measure_speeds": False, "learn_proposal": True,
+                                     "burn_in": 0, "seed": 1, "max_samples": max_samples,
+                                     "Rminus1_stop": 1e-9, "chains_per_gpu": chains}}}
+        saved = sys.modules.get("cobaya.samplers.mcmc")
+        plugin.install_as_mcmc()
+        try:
+            t0 = time.perf_counter()
+            _, smp = run(info)
+            wall = time.perf_counter() - t0
+        finally:
+            if saved is not None:
+                sys.modules["cobaya.samplers.mcmc"] = saved
+        props = int(smp.n_steps_raw) * chains
+        rows = len(smp.collection)
+        return {"value": props / wall, "unit": UNIT, "wall_s": wall, "proposals": props,
+                "rows_in_collection": rows, "d2h_bytes": int(rows * smp._fm.row_width * 8),
+                "what": f"cobaya.run.run(info), sampler: mcmc, chains_per_gpu={chains}, "
+                        f"max_samples={max_samples}, no output prefix (wall clock of run())"}
+    except Exception as e:  # never lose the benchmark line over the extra report
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+    finally:
+        logging.disable(logging.NOTSET)
+
+
 def run_gpu_arm(args):
     import torch
 
@@ -261,19 +304,28 @@ def run_gpu_arm(args):
         import torch.distributed as tdist
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line
+        # NCCL's log goes to a file per rank (rank count, transports, NVLS are observable
+        # there); stdout stays the single JSON line
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_FILE",
+                              os.path.join(ROOT, "gpurun_out", f"nccl_n{world}_%h_%p.log"))
         tdist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from cobaya_b200 import problems
     from cobaya_b200.mcmc import EnsembleMCMC, TorchDist
 
     if world > 1:
         dist = TorchDist()
-    fm, cov = build_problem()
+    prob = problems.get(args.config)
+    fm, Dp = prob.fm, prob.fm.D
     C = args.chains
-    x0 = start_points(fm, cov, C, rank)
+    x0 = prob.start(C, rank)
     locksteps = args.locksteps
+    if locksteps is None:
+        # about 10 ms of device work per step for every configuration
+        locksteps = {"c1": 1024, "c2": 2 * fm.cycle_length, "c3": 20 * fm.cycle_length}[prob.key]
     K, W = args.steps, args.warmup
-    total_steps = (K + W) * 2 + 4
-    # stored rows per chain: acceptance stays below ~0.35
+    # stored rows per chain: acceptance stays below ~0.35 (and thinning only lowers it)
     rows_cap = int(0.45 * locksteps * (K + W + 2)) + 4096
     opts = {"seed": 1, "chains_per_gpu": C, "device": local, "rows_per_chain": rows_cap,
             "Rminus1_stop": 0.0, "learn_proposal_Rminus1_max": 1e9, "burn_in": 0}
@@ -289,6 +341,7 @@ def run_gpu_arm(args):
 
     def one_step():
         nonlocal n_ckpt
+        smp._ensure_row_capacity()
         eng.advance(locksteps)
         smp.n_steps_raw += locksteps
         g = smp._global_summary()
@@ -298,6 +351,7 @@ def run_gpu_arm(args):
             smp.i_learn += 1
             n_ckpt += 1
 
+    smp.launch_steps = locksteps
     for _ in range(W):
         one_step()
     # the checkpoint kernels are part of the warm-up too (CUDA loads a kernel lazily on its
@@ -310,6 +364,7 @@ def run_gpu_arm(args):
         clocks.start()
     eng.set_profiling(True)
     eng.kernel_times(reset=True)
+    eng.window_counts(reset=True)
     l0 = eng.launch_count()
     rows0 = eng.summary()["sum_rows"]
     ck0 = n_ckpt
@@ -321,6 +376,7 @@ def run_gpu_arm(args):
     barrier()
     t_wall = time.perf_counter() - t_wall
     kt = eng.kernel_times(reset=True)
+    windows = eng.window_counts(reset=True)
     eng.set_profiling(False)
     launches = eng.launch_count() - l0
     rows1 = eng.summary()["sum_rows"]
@@ -333,26 +389,50 @@ def run_gpu_arm(args):
     proposals = world * C * locksteps * K
     value = proposals / (ms_total * 1e-3)
 
-    # ---- e2e: same pass through the host API with pinned-host inputs + read-back
-    pin = torch.from_numpy(np.ascontiguousarray(x0)).pin_memory()
-    x0_pinned = pin.numpy()
-    Ke = max(2, min(K, 5))
-    barrier()
-    te = time.perf_counter()
-    for _ in range(Ke):
-        eng.set_state(x0_pinned)                         # H2D: start points
-        eng.advance(locksteps)
-        sums = smp._moments(0, 0)                        # moments (+ all-reduce) -> host
-        st = eng.get_state()                             # D2H: current points + counters
-    barrier()
-    te = time.perf_counter() - te
+    # ---- e2e: the same pass through the host API, HOST buffers on both sides.  Every step:
+    # start points uploaded from page-locked host memory (set_state), `locksteps`
+    # proposals per chain, then EVERY ROW the step stored is handed to the host -- device-side
+    # compaction + one asynchronous D2H into a page-locked double buffer, running under the
+    # next step's kernels (cb2_drain_start) -- plus the moments and the current points.
+    # This is what the reference holds on the host after the same work (its
+    # SampleCollection, collection.py:402-427), so nothing is left on the device.
+    Wd = fm.row_width
+    max_rows = int(0.5 * C * locksteps) + 1024
+    bufs = [eng.host_buffer(max_rows * Wd) for _ in range(2)]
+    cnts = [eng.host_buffer(C).view(np.int64) for _ in range(2)]
+    x0_pinned = eng.host_buffer(C * Dp).reshape(C, Dp)
+    x0_pinned[:] = x0
+    Ke = max(3, min(K, 6))
+    rows_out, sums, st = [], None, None
+    for warm in (True, False):  # one untimed pass: staging buffers are sized, pages touched
+        barrier()
+        te = time.perf_counter()
+        for k in range(1 if warm else Ke):
+            eng.set_state(x0_pinned)                         # H2D: start points
+            eng.advance(locksteps)
+            if k >= 2:
+                eng.drain_wait()                             # buffer k % 2 is free again
+            n_out = eng.drain_start(bufs[k % 2], cnts[k % 2])   # D2H (async): the step's rows
+            sums = smp._moments(0, 0)                        # moments (+ all-reduce) -> host
+            st = eng.get_state()                             # D2H: current points + counters
+            if not warm:
+                rows_out.append(n_out)
+        eng.drain_wait()
+        barrier()
+        te = time.perf_counter() - te
     tt = torch.tensor([te], dtype=torch.float64, device="cuda")
     if world > 1:
         tdist.all_reduce(tt, op=tdist.ReduceOp.MAX)
     e2e_value = world * C * locksteps * Ke / float(tt.item())
-    h2d = x0_pinned.nbytes + D * 8
-    d2h = (sums.nbytes + st["x"].nbytes + st["logpost"].nbytes + st["weight"].nbytes
-           + st["n_rows"].nbytes + st["n_accepted"].nbytes + st["flags"].nbytes + 64)
+    row_bytes = float(np.mean(rows_out)) * Wd * 8
+    # the rows really are on the host: weights are positive integers, chain counts add up
+    last = bufs[(Ke - 1) % 2][: rows_out[-1] * Wd].reshape(-1, Wd)
+    e2e_ok = bool(rows_out[-1] == int(cnts[(Ke - 1) % 2].sum()) and np.all(last[:, 0] >= 1)
+                  and np.all(last[:, 0] == np.round(last[:, 0])))
+    h2d = x0_pinned.nbytes + Dp * 8
+    d2h = (row_bytes + C * 8 + sums.nbytes + st["x"].nbytes + st["logpost"].nbytes
+           + st["weight"].nbytes + st["n_rows"].nbytes + st["n_accepted"].nbytes
+           + st["flags"].nbytes + 64)
 
     if rank != 0:
         return
@@ -361,47 +441,59 @@ def run_gpu_arm(args):
     peak, peak_src = peaks()
     dom = max(("step", "basis"), key=lambda k: kt[k]["ms"])
     acc_rate = (rows1 - rows0) / (C * locksteps * K)     # stored-row rate a
-    bytes_per_prop = 16 * D + 8 * acc_rate * (D + 6)
+    Wrow = fm.row_width
+    bytes_per_prop = 16 * Dp + 8 * acc_rate * Wrow
+    # the dominant kernel with ITS OWN bytes: the step kernel reads one basis column per
+    # proposal and writes the stored rows; the basis kernel writes the bases (8 D B per
+    # proposal, amortised) and reads the normals it is made from (about as much again)
+    own_bytes = {"step": 8 * Dp + 8 * acc_rate * Wrow, "basis": 8 * Dp + 4 * (Dp + 2)}
     hot_ms = kt["step"]["ms"] + kt["basis"]["ms"]
     n_l = max(kt[dom]["launches"], 1)
-    props_per_launch = C * locksteps * K / max(kt["step"]["launches"], 1)
-    # the step and basis kernels together implement one proposal; the roofline is quoted
-    # for the pair (achieved = algorithmic bytes / their summed device time) and the
-    # dominant one is named
-    achieved = bytes_per_prop * C * locksteps * K / (hot_ms * 1e-3) / 1e9
+    props_timed = C * locksteps * K
+    props_per_launch = props_timed / max(kt["step"]["launches"], 1)
+    achieved = bytes_per_prop * props_timed / (hot_ms * 1e-3) / 1e9
+    dom_achieved = own_bytes[dom] * props_timed / (max(kt[dom]["ms"], 1e-9) * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and prob.key == "c1":
         try:
             tj = json.load(open(tp))
-            # ncu figure of a 64-proposal window, scaled to the proposals of one launch now
+            # ncu figure of one window, scaled to the proposals of one launch now
             traffic = int(tj["dram_bytes_per_launch"] * props_per_launch /
                           float(tj.get("proposals_per_profiled_launch", props_per_launch)))
         except Exception:
             traffic = None
-    flops = 4 * D * D * C * locksteps * K / (hot_ms * 1e-3) / 1e12
+    flops = prob.flops_per_proposal * props_timed / (hot_ms * 1e-3) / 1e12
     fp64_pk, fp64_src = fp64_peak()
-    cb = cpu_oracle_baseline(fm, cov) if not args.no_cpu_baseline else None
+    cb = cpu_oracle_baseline(fm, prob) if not args.no_cpu_baseline else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
         "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "D": D, "chains_per_gpu": C,
+        "config": {"workload": prob.workload, "D": Dp, "chains_per_gpu": C,
                    "locksteps_per_step": locksteps, "checkpoints_in_timed_region": n_ckpt - ck0,
-                   "l2": "inputs larger than L2: every 256-proposal window streams 1.07 GB of "
-                         "Haar bases + 0.55 GB of normals + new sample rows through the 126 MB "
-                         "L2; no explicit flush",
-                   "step_kernel": {0: "general", 1: "dmma", 2: "dmma-producer-consumer", 3: "dmma-streamed"}.get(
-                       eng.last_step_kernel(), "?"),
+                   "posterior_evaluations_per_proposal": prob.evals_per_proposal,
+                   "l2": "inputs larger than L2: every window streams its Haar bases, their "
+                         "normals and the new sample rows (> 1 GB at 8192 chains) through "
+                         "the 126 MB L2; no explicit flush",
+                   "step_kernel": KERNEL_NAMES.get(eng.last_step_kernel(), "?"),
+                   "windows_by_step_kernel": windows,
                    "parallelism": f"chains sharded over {world} GPU(s), no data-path "
                                   "collective; NCCL all-reduce of moments per checkpoint"},
         "clocks": clk, "gpu_launches": int(launches), "engine_note": eng.debug_message(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "steps": Ke,
-                "what": "set_state(pinned host) + advance + moments->host + get_state"},
+                "rows_per_step": float(np.mean(rows_out)), "rows_checked_on_host": e2e_ok,
+                "d2h_gbs": d2h * Ke / float(tt.item()) / 1e9,
+                "what": "set_state(page-locked host) + advance + EVERY stored row drained to "
+                        "page-locked host memory (async, under the next step) + "
+                        "moments->host + get_state; bound by the host link, not the kernels"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "dominant_kernel": dom,
+                     "dominant_kernel_own": {"bytes_per_proposal": own_bytes[dom],
+                                             "achieved": dom_achieved,
+                                             "frac": dom_achieved / peak},
                      "algorithmic_bytes_per_proposal": bytes_per_prop,
                      "stored_row_rate": acc_rate,
                      "avg_launch_ms": {k: kt[k]["ms"] / max(kt[k]["launches"], 1)
@@ -410,12 +502,14 @@ def run_gpu_arm(args):
                      "proposals_per_step_launch": props_per_launch, "launches": n_l,
                      "fp64": {"tflops": flops, "peak_tflops": fp64_pk,
                               "peak_source": fp64_src, "frac": flops / fp64_pk,
-                              "flops_per_proposal": 4 * D * D,
+                              "flops_per_proposal": prob.flops_per_proposal,
                               "note": "binding roof above D~23 (SURVEY.md 8d); DMMA and "
                                       "vector FP64 share one datapath"}},
         "cpu_baseline": cb,
         "wall_s_timed_region": t_wall,
     }
+    if prob.evals_per_proposal > 1:
+        line["posterior_evaluations_per_s"] = value * prob.evals_per_proposal
     try:  # R-1 of means at the convergence checks of this run (warm-up + timed region)
         def _fin(v):
             return float(v) if v is not None and np.isfinite(v) else None
@@ -426,6 +520,9 @@ def run_gpu_arm(args):
             for c in smp.progress]
     except Exception:  # never lose the benchmark line over the extra report
         pass
+    if world == 1 and prob.key == "c1" and not args.no_cobaya_run:
+        eng.close()
+        line["e2e_cobaya_run"] = e2e_through_cobaya_run(C)
     emit(line)
 
 
@@ -457,8 +554,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU)
-    ap.add_argument("--locksteps", type=int, default=1024)
+    ap.add_argument("--locksteps", type=int, default=None)
+    ap.add_argument("--config", default="c1", choices=["c1", "c2", "c3"],
+                    help="c1 = BASELINE configs[1] (headline), c2 = configs[2] (128-D, 3 modes, "
+                         "speed blocks), c3 = configs[3] (30-D Rosenbrock, dragging)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cobaya-run", action="store_true",
+                    help="skip the second end-to-end figure through cobaya.run.run")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

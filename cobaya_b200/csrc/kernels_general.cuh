@@ -4,7 +4,7 @@
 #pragma once
 #include "common.cuh"
 
-#define CB2_FLAG_INTERNAL 4u
+// CB2_FLAG_INTERNAL: include/cobaya_b200.h
 #define FULLMASK 0xffffffffu
 
 // ------------------------------------------------------------------ cycler tapes

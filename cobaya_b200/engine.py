@@ -37,7 +37,11 @@ def _i32(a):
 
 class Engine:
     def __init__(self, fm: FlatModel, n_chains: int, seed: int, device: int = 0,
-                 chain_id0: int = 0, rows_cap: int = 1024, burn_in: int = 0):
+                 chain_id0: int = 0, rows_cap: int | None = 1024, burn_in: int = 0,
+                 rows_want: int = 4096, mem_fraction: float = 0.4):
+        """``rows_cap``: stored rows per chain the engine can hold before ``grow_rows``;
+        ``None`` sizes it to ``rows_want``, limited to ``mem_fraction`` of the free device
+        memory (the store can grow later, up to what the device holds)."""
         self.lib = _cabi.load()
         self.fm = fm
         self.n_chains = int(n_chains)
@@ -51,6 +55,11 @@ class Engine:
         if rc != 0:
             raise EngineError(self.lib.cb2_last_error(None).decode())
         self.h = h
+        self._pinned = []
+        if rows_cap is None:
+            free, _, _ = self.mem_info()
+            fit = int(mem_fraction * free / (self.n_chains * fm.row_width * 8))
+            rows_cap = max(16, min(int(rows_want), fit))
         self.rows_cap = int(rows_cap)
         self.burn_in = int(burn_in)
         self._upload_model()
@@ -64,6 +73,9 @@ class Engine:
         if getattr(self, "h", None):
             self.lib.cb2_destroy(self.h)
             self.h = None
+        for p in getattr(self, "_pinned", []):
+            self.lib.cb2_host_free(p)
+        self._pinned = []
 
     def __del__(self):
         try:
@@ -172,13 +184,101 @@ class Engine:
         return out
 
     def rows(self, chain: int, first: int = 0, n: int | None = None):
+        """Rows [first, first + n) of one chain (all stored rows by default)."""
         W = self.lib.cb2_row_width(self.h)
-        n = self.rows_cap if n is None else int(n)
-        out = np.empty((max(n, 1), W))
-        got = self.lib.cb2_copy_rows(self.h, int(chain), int(first), n, _cabi.ptr(out))
+        if n is None:
+            one = np.zeros(1, np.int64)
+            f = np.array([int(first)], np.int64)
+            n = self.lib.cb2_copy_rows_bulk(self.h, int(chain), int(chain) + 1, _cabi.ptr(f),
+                                            _cabi.ptr(one), None, 0)
+            if n < 0:
+                raise EngineError(self.lib.cb2_last_error(self.h).decode())
+        out = np.empty((max(int(n), 1), W))
+        got = self.lib.cb2_copy_rows(self.h, int(chain), int(first), int(n), _cabi.ptr(out))
         if got < 0:
             raise EngineError(self.lib.cb2_last_error(self.h).decode())
-        return out[:got].copy()
+        return out[:got]
+
+    # budget of one bulk transfer (rows are staged once on the device before they leave it)
+    BULK_BYTES = 2 << 30
+
+    def rows_bulk(self, first=None, chains=None):
+        """Rows ``[first[c], n_rows[c])`` of the chains ``chains = (begin, end)`` (default:
+        all), chain-major in one array, and the per-chain counts.  One device-side
+        compaction and one D2H copy per ~2 GB (cb2_copy_rows_bulk), instead of one copy per
+        chain -- the bulk counterpart of SampleCollection's per-row append
+        (collection.py:402-427)."""
+        W = self.lib.cb2_row_width(self.h)
+        c0, c1 = (0, self.n_chains) if chains is None else (int(chains[0]), int(chains[1]))
+        n = c1 - c0
+        counts = np.zeros(n, np.int64)
+        f = None if first is None else np.ascontiguousarray(first, dtype=np.int64)
+        if f is not None and f.shape != (n,):
+            raise EngineError("rows_bulk: `first` needs one entry per selected chain")
+        total = self.lib.cb2_copy_rows_bulk(self.h, c0, c1, _cabi.ptr(f), _cabi.ptr(counts),
+                                            None, 0)
+        if total < 0:
+            raise EngineError(self.lib.cb2_last_error(self.h).decode())
+        out = np.empty((int(total), W))
+        budget = max(1, self.BULK_BYTES // (8 * W))
+        ends = np.cumsum(counts)
+        a = 0
+        while a < n:  # chain ranges of at most `budget` rows (at least one chain)
+            base = ends[a - 1] if a else 0
+            b = int(np.searchsorted(ends, base + budget, side="right"))
+            b = min(max(b, a + 1), n)
+            r0, r1 = int(base), int(ends[b - 1])
+            if r1 > r0:
+                fa = None if f is None else np.ascontiguousarray(f[a:b])
+                got = self.lib.cb2_copy_rows_bulk(self.h, c0 + a, c0 + b, _cabi.ptr(fa), None,
+                                                  _cabi.ptr(out[r0:r1]), r1 - r0)
+                if got != r1 - r0:
+                    raise EngineError(self.lib.cb2_last_error(self.h).decode()
+                                      or "rows changed during the bulk copy")
+            a = b
+        return out, counts
+
+    def mem_info(self):
+        """(free, total, held by the row store) bytes of the engine's GPU."""
+        v = np.zeros(3, np.int64)
+        self._ck(self.lib.cb2_mem_info(self.h, _cabi.ptr(v[0:1]), _cabi.ptr(v[1:2]),
+                                       _cabi.ptr(v[2:3])))
+        return int(v[0]), int(v[1]), int(v[2])
+
+    def grow_rows(self, new_cap: int):
+        """Larger per-chain sample capacity; stored rows are kept (cb2_grow_rows)."""
+        self._ck(self.lib.cb2_grow_rows(self.h, int(new_cap)))
+        self.rows_cap = max(self.rows_cap, int(new_cap))
+
+    # ---- asynchronous drain (run loop) ---------------------------------------------------
+    def host_buffer(self, n_doubles: int):
+        """Page-locked float64 buffer (cb2_host_alloc) as a numpy array; freed with the
+        engine (or explicitly by ``free_host_buffer``)."""
+        n_doubles = max(int(n_doubles), 1)
+        p = self.lib.cb2_host_alloc(n_doubles * 8)
+        if not p:
+            raise EngineError(f"cannot page-lock {n_doubles * 8 / 1e9:.2f} GB of host memory")
+        arr = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(n_doubles,))
+        self._pinned.append(p)
+        return arr
+
+    def drain_start(self, out: np.ndarray, counts: np.ndarray | None = None) -> int:
+        """Start handing the rows added since the previous drain to ``out`` (flat or
+        [rows, W], ideally from ``host_buffer``); returns the number of rows on their way.
+        The copy runs on its own stream under the next ``advance``; read ``out`` only after
+        ``drain_wait``."""
+        W = self.lib.cb2_row_width(self.h)
+        got = self.lib.cb2_drain_start(self.h, _cabi.ptr(out), out.size // W, _cabi.ptr(counts))
+        if got < 0:
+            raise EngineError(self.lib.cb2_last_error(self.h).decode())
+        return int(got)
+
+    def drain_wait(self):
+        self._ck(self.lib.cb2_drain_wait(self.h))
+
+    def drain_reset(self, first=None):
+        f = None if first is None else np.ascontiguousarray(first, dtype=np.int64)
+        self._ck(self.lib.cb2_drain_reset(self.h, _cabi.ptr(f)))
 
     # ---- resuming ---------------------------------------------------------------------
     def export_state(self) -> np.ndarray:
@@ -190,12 +290,36 @@ class Engine:
         self._ck(self.lib.cb2_export_state(self.h, _cabi.ptr(buf), n))
         return buf
 
-    def import_state(self, blob, rows=None):
+    def import_state(self, blob, rows=None, counts=None):
         """Restore a snapshot taken from an identically configured engine; ``rows`` is the
-        list of per-chain row arrays (``self.rows(c)`` of the exporting engine)."""
+        list of per-chain row arrays (``self.rows(c)`` of the exporting engine), or, with
+        ``counts``, all rows chain-major in one array (``rows_bulk()`` of the exporter)."""
         blob = np.ascontiguousarray(blob, dtype=np.uint8)
         self._ck(self.lib.cb2_import_state(self.h, _cabi.ptr(blob), blob.size))
-        if rows is not None:
+        if rows is not None and counts is not None:
+            counts = np.ascontiguousarray(counts, dtype=np.int64)
+            if counts.shape != (self.n_chains,):
+                raise EngineError("import_state: one count per chain is required")
+            W = self.lib.cb2_row_width(self.h)
+            rows = _f64(rows).reshape(-1, W)
+            if rows.shape[0] != counts.sum():
+                raise EngineError("import_state: rows do not match the counts")
+            if counts.size and counts.max() > self.rows_cap:
+                raise EngineError("import_state: more rows per chain than rows_cap")
+            ends = np.cumsum(counts)
+            budget = max(1, self.BULK_BYTES // (8 * W))
+            a = 0
+            while a < self.n_chains:
+                base = ends[a - 1] if a else 0
+                b = int(np.searchsorted(ends, base + budget, side="right"))
+                b = min(max(b, a + 1), self.n_chains)
+                r0, r1 = int(base), int(ends[b - 1])
+                if r1 > r0:
+                    self._ck(self.lib.cb2_load_rows_bulk(
+                        self.h, a, b, _cabi.ptr(np.ascontiguousarray(counts[a:b])),
+                        _cabi.ptr(rows[r0:r1])))
+                a = b
+        elif rows is not None:
             if len(rows) != self.n_chains:
                 raise EngineError("import_state: one row array per chain is required")
             keep = []
@@ -226,6 +350,14 @@ class Engine:
 
     def last_step_kernel(self):
         return int(self.lib.cb2_last_step_kernel(self.h))
+
+    def window_counts(self, reset: bool = False):
+        """Windows run by each step kernel, and windows that left their preferred kernel."""
+        v = np.zeros(6, np.int64)
+        self._ck(self.lib.cb2_window_counts(self.h, _cabi.ptr(v), int(reset)))
+        names = ["general", "dmma", "dmma-producer-consumer", "dmma-streamed",
+                 "pc_launch_refused", "streamed_did_not_fit"]
+        return {k: int(x) for k, x in zip(names, v)}
 
     def debug_message(self):
         return self.lib.cb2_debug_message(self.h).decode()

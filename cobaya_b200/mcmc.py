@@ -42,6 +42,10 @@ class SamplerError(RuntimeError):
     """Mirror of cobaya.log.LoggedError for the standalone driver."""
 
 
+class OtherRankError(SamplerError):
+    """Another process of the run failed (mirror of cobaya.mpi.OtherProcessError)."""
+
+
 # defaults of cobaya/samplers/mcmc/mcmc.yaml (every key, verbatim) + the engine's keys
 MCMC_DEFAULTS = {
     "burn_in": 0, "max_tries": "40d", "covmat": None, "covmat_params": None,
@@ -111,8 +115,8 @@ class _NoDist:
     def all_reduce_sum(self, arr):
         return arr
 
-    def all_reduce_min_max_sum(self, mins, maxs, sums):
-        return mins, maxs, sums
+    def all_gather_i64(self, vec):
+        return [list(vec)]
 
     def all_gather_object(self, obj):
         return [obj]
@@ -130,6 +134,7 @@ class TorchDist:
         self.torch, self.dist, self.group = torch, dist, group
         self.rank, self.size = dist.get_rank(group), dist.get_world_size(group)
         self.backend = dist.get_backend(group)
+        self._gather_buf = self._gather_in = None
         self.device = device if device is not None else (
             torch.device("cuda", torch.cuda.current_device()) if self.backend == "nccl"
             else torch.device("cpu"))
@@ -151,15 +156,18 @@ class TorchDist:
         self.dist.all_gather_object(out, obj, group=self.group)
         return out
 
-    def all_reduce_min_max_sum(self, mins, maxs, sums):
+    def all_gather_i64(self, vec):
+        """One small all-gather (the per-launch summary): a single collective and a single
+        device->host read instead of three all-reduces with their own copies."""
         tt = self.torch
-        a = tt.as_tensor(np.asarray(mins, dtype=np.int64)).to(self.device)
-        b = tt.as_tensor(np.asarray(maxs, dtype=np.int64)).to(self.device)
-        c = tt.as_tensor(np.asarray(sums, dtype=np.int64)).to(self.device)
-        self.dist.all_reduce(a, op=self.dist.ReduceOp.MIN, group=self.group)
-        self.dist.all_reduce(b, op=self.dist.ReduceOp.MAX, group=self.group)
-        self.dist.all_reduce(c, op=self.dist.ReduceOp.SUM, group=self.group)
-        return a.cpu().numpy(), b.cpu().numpy(), c.cpu().numpy()
+        n = len(vec)
+        if self._gather_buf is None or self._gather_buf.numel() != self.size * n:
+            self._gather_buf = tt.zeros(self.size * n, dtype=tt.int64, device=self.device)
+            self._gather_in = tt.zeros(n, dtype=tt.int64, device=self.device)
+        self._gather_in.copy_(tt.as_tensor(np.asarray(vec, dtype=np.int64)),
+                              non_blocking=False)
+        self.dist.all_gather_into_tensor(self._gather_buf, self._gather_in, group=self.group)
+        return self._gather_buf.cpu().numpy().reshape(self.size, n)
 
 
 def decide_learning(opts, Rminus1, converged):
@@ -216,12 +224,19 @@ class EnsembleMCMC:
         self.max_samples = opts["max_samples"]
         if covmat_incomplete and opts["learn_proposal"]:  # mcmc.py:419-429
             opts["learn_proposal_Rminus1_max"] = opts["learn_proposal_Rminus1_max_early"]
-        # sample capacity per chain
+        lc = opts["launch_cycles"]
+        if lc is None:
+            lc = max(1, (self.learn_every.value // 2) // max(self.cycle_length, 1))
+        self.launch_steps = int(lc) * self.cycle_length
+        # Sample capacity per chain: the INITIAL size of the device row store.  The store
+        # grows on demand (_ensure_row_capacity), so neither a finite `max_samples` (the
+        # run stops when the SLOWEST chain has that many rows; faster chains hold more) nor
+        # `max_samples: inf` needs a worst-case allocation up front.  Without
+        # `rows_per_chain` the engine fits the wanted size into 40 % of the free memory.
         rows = opts["rows_per_chain"]
-        if rows is None:
-            rows = (int(self.max_samples) + 2 * self.learn_every.value
-                    if np.isfinite(self.max_samples) else 64 * self.learn_every.value)
-        self.rows_per_chain = int(rows)
+        rows_want = (int(self.max_samples) + self.launch_steps + 2 * self.learn_every.value
+                     if np.isfinite(self.max_samples) else 16 * self.learn_every.value)
+        self.rows_per_chain = None if rows is None else int(rows)
         seed = opts["seed"]
         self.seed = int(seed) if seed is not None else int(
             np.random.SeedSequence().generate_state(2, np.uint32).view(np.uint64)[0] >> 1)
@@ -235,15 +250,24 @@ class EnsembleMCMC:
             self._check_snapshot(snap)
             self.seed = int(snap["seed"])
             fm.set_covariance(np.asarray(snap["proposal_cov"]))  # the learned proposal
-            need = int(np.max(snap["n_rows"])) + 2 * self.learn_every.value
-            if self.rows_per_chain < need and opts["rows_per_chain"] is None:
-                self.rows_per_chain = need + (int(self.max_samples)
-                                              if np.isfinite(self.max_samples) else
-                                              64 * self.learn_every.value)
-        self.engine = engine or Engine(
-            fm, n_chains=self.n_chains_local, seed=self.seed, device=int(device),
-            chain_id0=self.dist.rank * self.n_chains_local, rows_cap=self.rows_per_chain,
-            burn_in=int(self.burn_in.value))
+            need = int(np.max(snap["n_rows"])) + self.launch_steps
+            rows_want = max(rows_want, need + 2 * self.learn_every.value)
+            if self.rows_per_chain is not None:
+                self.rows_per_chain = max(self.rows_per_chain, need)
+        # `engine`: an engine object, or a factory with Engine's signature (dependency
+        # injection for the CPU tests of this host logic; the default is the CUDA engine and
+        # nothing else is ever chosen here)
+        if engine is None or callable(engine):
+            engine = (engine or Engine)(
+                fm, n_chains=self.n_chains_local, seed=self.seed, device=int(device),
+                chain_id0=self.dist.rank * self.n_chains_local, rows_cap=self.rows_per_chain,
+                burn_in=int(self.burn_in.value), rows_want=rows_want)
+        self.engine = engine
+        self.rows_per_chain = self.engine.rows_cap
+        if snap is not None and self.rows_per_chain < int(np.max(snap["n_rows"])):
+            raise SamplerError(
+                "Cannot resume: the device cannot hold the %d rows per chain of the "
+                "snapshot (room for %d)." % (int(np.max(snap["n_rows"])), self.rows_per_chain))
         self.converged = False
         self.Rminus1_last = np.inf
         self.i_learn = 1
@@ -252,9 +276,9 @@ class EnsembleMCMC:
         if snap is None:
             self.engine.set_state(x0)
         else:
-            ends = np.cumsum(snap["n_rows"])
-            rows = np.split(np.asarray(snap["rows"]).reshape(-1, fm.row_width), ends[:-1])
-            self.engine.import_state(snap["blob"], rows)
+            self.engine.import_state(
+                snap["blob"], np.asarray(snap["rows"]).reshape(-1, fm.row_width),
+                np.asarray(snap["n_rows"], np.int64))
             self.Rminus1_last = float(snap["Rminus1_last"])
             self.i_learn = int(snap["i_learn"])
             self.n_steps_raw = int(snap["n_steps_raw"])
@@ -265,33 +289,33 @@ class EnsembleMCMC:
                            learned=bool(r[4]))
                 for r, t in zip(np.asarray(snap["progress"]).reshape(-1, 5),
                                 snap["progress_timestamps"])]
-        lc = opts["launch_cycles"]
-        if lc is None:
-            lc = max(1, (self.learn_every.value // 2) // max(self.cycle_length, 1))
-        self.launch_steps = int(lc) * self.cycle_length
         self._shift = np.asarray(self.dist.all_reduce_sum(x0.sum(axis=0))) / self.n_chains
         if snap is not None:
             self._shift = np.asarray(snap["shift"], dtype=np.float64)
         self._mom_buf = None
         self.last_summary = None
+        self.local_summary = None
 
     # ------------------------------------------------------------------ resuming
     SNAPSHOT_VERSION = 1
 
-    def snapshot(self) -> dict:
+    def snapshot(self, with_rows: bool = True) -> dict:
         """Everything needed to continue this rank's chains in a new process: the engine's
         per-chain state and stored rows plus the driver's checkpoint bookkeeping
         (the ensemble counterpart of mcmc.py:187-214,1045-1078)."""
         eng = self.engine
-        rows = [eng.rows(c) for c in range(self.n_chains_local)]
+        if with_rows:
+            rows_all, n_rows = eng.rows_bulk()
+        else:
+            rows_all = np.zeros((0, self.fm.row_width))
+            n_rows = eng.get_state()["n_rows"]
         prog = np.array([[c.N, c.acceptance_rate,
                           np.nan if c.Rminus1 is None else c.Rminus1,
                           np.nan if c.Rminus1_cl is None else c.Rminus1_cl,
                           float(c.learned)] for c in self.progress], dtype=np.float64)
         return dict(
             version=self.SNAPSHOT_VERSION, blob=eng.export_state(),
-            n_rows=np.array([len(r) for r in rows], np.int64),
-            rows=np.concatenate(rows) if rows else np.zeros((0, self.fm.row_width)),
+            n_rows=np.asarray(n_rows, np.int64), rows=rows_all,
             proposal_cov=self.fm.get_covariance(), seed=np.uint64(self.seed),
             rank=self.dist.rank, world=self.dist.size, n_chains_local=self.n_chains_local,
             D=self.fm.D, row_width=self.fm.row_width,
@@ -330,17 +354,56 @@ class EnsembleMCMC:
                     self.n_chains_local, self.fm.D, self.fm.row_width))
 
     # ------------------------------------------------------------------ helpers
-    def _global_summary(self):
-        s = self.engine.summary()
-        mins, maxs, sums = self.dist.all_reduce_min_max_sum(
-            [s["min_rows"]], [s["max_rows"]],
-            [s["sum_rows"], s["n_stuck"], s["n_rows_full"], s["n_internal"],
-             s["sum_accepted"], s["sum_weight"]])
-        g = dict(min_rows=int(mins[0]), max_rows=int(maxs[0]), sum_rows=int(sums[0]),
-                 n_stuck=int(sums[1]), n_rows_full=int(sums[2]), n_internal=int(sums[3]),
-                 sum_accepted=int(sums[4]), sum_weight=int(sums[5]))
+    def _global_summary(self, local_error: str | None = None):
+        """The 8-word engine summary of every rank in ONE collective (an all-gather of 9
+        int64 per rank; min, max and sums are then taken on the host).  The ninth word
+        carries "this rank failed", so that a rank-local error (CUDA error, device memory)
+        is raised on every rank in the same iteration instead of leaving the others blocked
+        in the next collective (the role of ProcessState, mpi.py:350-467)."""
+        if local_error is None:
+            s = self.engine.summary()
+        else:
+            s = dict(min_rows=0, max_rows=0, sum_rows=0, n_stuck=0, n_rows_full=0,
+                     n_internal=0, sum_accepted=0, sum_weight=0)
+        self.local_summary = s
+        vec = [s["min_rows"], s["max_rows"], s["sum_rows"], s["n_stuck"], s["n_rows_full"],
+               s["n_internal"], s["sum_accepted"], s["sum_weight"], int(local_error is not None)]
+        allv = np.asarray(self.dist.all_gather_i64(vec), dtype=np.int64).reshape(-1, 9)
+        if allv[:, 8].any():
+            bad = [int(r) for r in np.nonzero(allv[:, 8])[0]]
+            if local_error is not None:
+                raise SamplerError(local_error)
+            raise OtherRankError(f"Another process failed (rank {bad}) - exiting.")
+        g = dict(min_rows=int(allv[:, 0].min()), max_rows=int(allv[:, 1].max()),
+                 sum_rows=int(allv[:, 2].sum()), n_stuck=int(allv[:, 3].sum()),
+                 n_rows_full=int(allv[:, 4].sum()), n_internal=int(allv[:, 5].sum()),
+                 sum_accepted=int(allv[:, 6].sum()), sum_weight=int(allv[:, 7].sum()))
         self.last_summary = g
         return g
+
+    def _ensure_row_capacity(self):
+        """Grow the device row store before a chain can run out of room: one launch adds at
+        most ``launch_steps`` rows per chain (the reference's collection grows without
+        limit, collection.py:765-778)."""
+        eng = self.engine
+        have = (self.local_summary or eng.summary())["max_rows"]
+        if have + self.launch_steps <= eng.rows_cap:
+            return
+        need = have + self.launch_steps
+        want = max(need, int(1.5 * eng.rows_cap) + self.launch_steps)
+        free, _, held = eng.mem_info()
+        per_row = self.n_chains_local * self.fm.row_width * 8
+        fit = int(0.9 * free) // per_row  # old and new store coexist during the re-layout
+        new_cap = min(want, fit)
+        if new_cap < need:
+            raise SamplerError(
+                "Device memory exhausted by the stored samples: %d chains x %d rows hold "
+                "%.1f GB and %.1f GB are free; lower chains_per_gpu or use output_thin / "
+                "max_samples." % (self.n_chains_local, eng.rows_cap, held / 1e9, free / 1e9))
+        eng.grow_rows(new_cap)
+        self.rows_per_chain = eng.rows_cap
+        log.info("Sample store grown to %d rows per chain (%.1f GB).", eng.rows_cap,
+                 eng.rows_cap * per_row / 1e9)
 
     def n(self):
         """Stored rows of the shortest chain (the ensemble analogue of MCMC.n())."""
@@ -367,9 +430,14 @@ class EnsembleMCMC:
         log.info("Sampling! (%d chains on %d GPU(s))", self.n_chains, self.dist.size)
         g = self._global_summary()
         while g["min_rows"] < self.max_samples and not self.converged:
-            self.engine.advance(self.launch_steps)
+            err = None
+            try:
+                self._ensure_row_capacity()
+                self.engine.advance(self.launch_steps)
+            except Exception as e:  # rank-local: every rank must leave the loop together
+                err = f"{type(e).__name__}: {e}"
             self.n_steps_raw += self.launch_steps
-            g = self._global_summary()
+            g = self._global_summary(local_error=err)
             self._check_health(g)
             if callback is not None:
                 callback(self)
@@ -481,11 +549,26 @@ class EnsembleMCMC:
         k = int(skip * len(rows)) if 0 < skip < 1 else int(skip)
         return rows[k:]
 
-    def samples(self, chains=None, skip_samples: float = 0.0):
+    def samples(self, chains=None, skip_samples: float = 0.0, return_counts: bool = False):
         """Concatenated rows of the selected local chains (default: all), each with its
-        first ``skip_samples`` fraction/number of rows removed (mcmc.py:1127-1143)."""
-        chains = range(self.n_chains_local) if chains is None else chains
-        return np.concatenate([self.chain_rows(c, skip_samples) for c in chains])
+        first ``skip_samples`` fraction/number of rows removed (mcmc.py:1127-1143).  All
+        chains / a contiguous range leave the device in bulk (cb2_copy_rows_bulk)."""
+        eng = self.engine
+        if chains is None:
+            chains = range(self.n_chains_local)
+        chains = list(chains)
+        contiguous = chains == list(range(chains[0], chains[0] + len(chains))) if chains else False
+        if not contiguous:
+            per = [self.chain_rows(c, skip_samples) for c in chains]
+            out = np.concatenate(per) if per else np.zeros((0, self.fm.row_width))
+            return (out, np.array([len(r) for r in per], np.int64)) if return_counts else out
+        n_rows = eng.get_state()["n_rows"][chains[0]: chains[-1] + 1]
+        if 0 < skip_samples < 1:
+            first = (skip_samples * n_rows).astype(np.int64)
+        else:
+            first = np.minimum(np.full_like(n_rows, int(skip_samples)), n_rows)
+        rows, counts = eng.rows_bulk(first=first, chains=(chains[0], chains[-1] + 1))
+        return (rows, counts) if return_counts else rows
 
     def products(self, skip_samples: float = 0.0, chains=None):
         import pandas as pd

@@ -114,7 +114,7 @@ class MCMC(CovmatSampler):
 
     sampler_type: str = "mcmc"
     supports_periodic_params = True
-    file_base_name = "mcmc_b200"
+    file_base_name = "mcmc"
     _at_resume_prefer_new = CovmatSampler._at_resume_prefer_new + [
         "burn_in", "callback_function", "callback_every", "max_tries", "output_every",
         "learn_every", "learn_proposal_Rminus1_max", "learn_proposal_Rminus1_max_early",
@@ -158,6 +158,10 @@ class MCMC(CovmatSampler):
     rows_per_chain: int | None = None
     launch_cycles: int | None = None
 
+    # dependency injection for the CPU tests of the host logic (tests/oracle_engine.py);
+    # None = the CUDA engine.  Never set by the product.
+    _engine_factory = None
+
     def set_instance_defaults(self):
         super().set_instance_defaults()
         self.converged = False
@@ -169,6 +173,14 @@ class MCMC(CovmatSampler):
         """mcmc.py:111-271, for ``chains_per_gpu`` chains per process."""
         if not self.model.prior.d():
             raise LoggedError(self.log, "No parameters being varied for sampler")
+        from . import distributed as cbd
+
+        if not cbd.world_consistent():
+            raise LoggedError(
+                self.log, "torch.distributed runs %d processes but cobaya.mpi knows of %d: "
+                          "call cobaya_b200.distributed.init() on every rank before "
+                          "cobaya.run.run(), so that rank-dependent output (chain files, "
+                          "root-only checkpoint) is right.", self._torch_world(), mpi.size())
         if self.temperature is None:
             self.temperature = 1
         self._ens = None
@@ -182,12 +194,12 @@ class MCMC(CovmatSampler):
         # Resuming (mcmc.py:131-139,187-214): the ensemble continues from the engine
         # snapshot written next to the chain file at the end of the previous run
         self._resume_snapshot = None
-        if self.output and self.output.is_resuming():
-            world = self._world_size()
-            if max(self.mpi_size or 0, 1) != world:
+        resuming = bool(self.output and self.output.is_resuming())
+        if resuming:
+            if max(self.mpi_size or 0, 1) != mpi.size():  # mcmc.py:131-139
                 raise LoggedError(
                     self.log, "Cannot resume a run with a different number of chains: "
-                              "was %d and now is %d.", max(self.mpi_size or 0, 1), world)
+                              "was %d and now is %d.", max(self.mpi_size or 0, 1), mpi.size())
             try:
                 self._resume_snapshot = EnsembleMCMC.load_snapshot(self.snapshot_filename())
             except OSError as e:
@@ -215,14 +227,17 @@ class MCMC(CovmatSampler):
         self.current_point = _CurrentPointView(self)
         self.set_proposer_blocking()
         self.set_proposer_initial_covmat(load=True)
+        # one chain file per process, prefix.<rank+1>.txt (mcmc.py:142-151)
         self.collection = SampleCollection(
             self.model, self.output, name=str(1 + mpi.rank()), temperature=self.temperature,
-            sample_type="mcmc", is_batch=True)
-        if not (self.output and self.output.is_resuming()):
+            sample_type="mcmc", is_batch=True, resuming=resuming)
+        self._row_cursor = None   # per-chain rows already handed to the collection
+        self._segments = []       # per-drain row counts of every chain (file layout)
+        if not resuming:
             self.write_checkpoint()
 
     @staticmethod
-    def _world_size():
+    def _torch_world():
         try:
             import torch.distributed as tdist
 
@@ -236,20 +251,18 @@ class MCMC(CovmatSampler):
         """Engine snapshot of this process (next to ``prefix.<rank+1>.txt``)."""
         import os
 
-        rank = self._rank() if rank is None else rank
+        rank = mpi.rank() if rank is None else rank
         return os.path.join(self.output.folder,
                             f"{self.output.prefix}.b200_state.{rank + 1}.npz")
 
-    @staticmethod
-    def _rank():
-        try:
-            import torch.distributed as tdist
+    def rows_filename(self, rank=None):
+        """Binary copy of this process' chain file (raw float64 rows, same order): what a
+        resumed run reloads into the engine -- the text file keeps ~8 digits."""
+        import os
 
-            if tdist.is_available() and tdist.is_initialized():
-                return tdist.get_rank()
-        except ImportError:
-            pass
-        return 0
+        rank = mpi.rank() if rank is None else rank
+        return os.path.join(self.output.folder,
+                            f"{self.output.prefix}.b200_rows.{rank + 1}.bin")
 
     def set_proposer_blocking(self):
         """mcmc.py:320-410: blocks/oversampling from the model, dragging gates, thinning."""
@@ -323,30 +336,34 @@ class MCMC(CovmatSampler):
                 "rows_per_chain", "launch_cycles"]
         o = {k: getattr(self, k) for k in keys}
         seed = self.seed
-        o["seed"] = int(self._rng.integers(2**62)) if seed is None else int(
+        # one Philox key for the whole run (chains are told apart by their global id); an
+        # unseeded run takes it from the root process' generator
+        o["seed"] = mpi.share_mpi(int(self._rng.integers(2**62))) if seed is None else int(
             np.random.SeedSequence(seed).generate_state(1, np.uint64)[0] >> 2)
         return o
 
     def run(self):
         """mcmc.py:451-528 -- the loop body runs on the GPU."""
+        with mpi.ProcessState(self):  # a failing rank ends the others too (mcmc.py:469)
+            self._run()
+
+    def _run(self):
         dist = None
-        try:
-            import torch.distributed as tdist
+        if self._torch_world() > 1:
+            from .mcmc import TorchDist
 
-            if tdist.is_available() and tdist.is_initialized() and tdist.get_world_size() > 1:
-                from .mcmc import TorchDist
-
-                dist = TorchDist()
-        except ImportError:
-            pass
+            dist = TorchDist()
         try:
             self._ens = EnsembleMCMC(self._fm, self._x0, self._options(), dist=dist,
+                                     engine=self._engine_factory,
                                      covmat_incomplete=self._covmat_incomplete,
-                                     resume_from=self._resume_snapshot)
-            self._resume_snapshot = None  # rows of the previous run: free the host copy
+                                     resume_from=self._restore_rows(self._resume_snapshot))
         except Exception as e:
             raise LoggedError(self.log, "Could not start the B200 engine: %s", e) from e
         ens = self._ens
+        if self._resume_snapshot is None:
+            self._row_cursor = np.zeros(ens.n_chains_local, np.int64)
+        self._resume_snapshot = None  # rows of the previous run: free the host copy
         self.mpi_info("Sampling! (%d lock-step chains)", ens.n_chains)
 
         def _cb(_):
@@ -356,10 +373,11 @@ class MCMC(CovmatSampler):
                 self.callback_function_callable(self)
                 self.last_point_callback = ens.n()
 
-        # Timed output (mcmc.py:473-481): at a convergence check, if `output_every` seconds
-        # have passed, the engine snapshot, .progress/.checkpoint/.covmat are rewritten, so
-        # a killed run resumes from there instead of from scratch.  `output_every` without
-        # a unit counts accepted steps per chain (mcmc.py:696-698).
+        # Timed output (mcmc.py:473-481,696-699): at a convergence check, if `output_every`
+        # seconds have passed, the rows stored since the last output leave the device in
+        # bulk and are appended to the chain file, and the engine snapshot and
+        # .progress/.checkpoint/.covmat are rewritten, so a killed run keeps its chain and
+        # resumes from there.  `output_every` without a unit counts accepted steps per chain.
         out_every = NumberWithUnits(self.output_every, "s", dtype=int)
         last_out = {"t": time.time(), "n": 0}
 
@@ -370,13 +388,10 @@ class MCMC(CovmatSampler):
                 due = time.time() >= last_out["t"] + out_every.value
             else:
                 due = ens.last_summary["min_rows"] >= last_out["n"] + max(1, out_every.value)
-            if not due:
+            # every process must take the same decision (the snapshots of a run belong together)
+            if not mpi.share_mpi(bool(due)):
                 return
-            self.converged = ens.converged
-            self.Rminus1_last = ens.Rminus1_last
-            self._sync_progress(ens)
-            self.write_checkpoint()
-            ens.save_snapshot(self.snapshot_filename())
+            self._timed_output(ens)
             last_out["t"] = time.time()
             last_out["n"] = ens.last_summary["min_rows"]
 
@@ -385,17 +400,25 @@ class MCMC(CovmatSampler):
         except LoggedError:
             raise
         except Exception as e:
+            # keep what was sampled (a rows-full or device error used to lose it)
+            try:
+                self._drain_rows()
+            except Exception:  # the device may be gone
+                pass
             raise LoggedError(self.log, "%s", e) from e
         self.n_steps_raw = ens.n_steps_raw
+        self._timed_output(ens)
+        self.mpi_info("Sampling complete after %d accepted steps.",
+                      ens.last_summary["sum_rows"])
+
+    def _timed_output(self, ens):
         self.converged = ens.converged
         self.Rminus1_last = ens.Rminus1_last
         self._sync_progress(ens)
-        self._fill_collection()
+        self._drain_rows()
         self.write_checkpoint()
         if self.output:
-            ens.save_snapshot(self.snapshot_filename())
-        self.mpi_info("Sampling complete after %d accepted steps.",
-                      ens.last_summary["sum_rows"])
+            self._save_state(ens)
 
     def _sync_progress(self, ens):
         for i, c in enumerate(ens.progress, start=1):
@@ -414,17 +437,104 @@ class MCMC(CovmatSampler):
         target._cache_reset()
         return target
 
-    def _fill_collection(self):
-        """Materialise the (concatenated) chains as a real SampleCollection: a DataFrame
-        with exactly ``collection.columns`` assigned to ``_data`` (SURVEY.md section 8b);
-        with an ``output`` the chain file ``prefix.<rank+1>.txt`` is written."""
-        self._collection_from_rows(self._ens.samples(), self.collection)
+    # ---- rows: device -> collection -> files ---------------------------------------------
+    def _drain_rows(self):
+        """Hand the rows stored since the previous drain to ``self.collection`` (a real
+        SampleCollection, filled in bulk: SURVEY.md section 8b) and append them to the
+        chain file ``prefix.<rank+1>.txt`` through the reference's own writer
+        (collection.py:1287-1315) and to its binary twin.
+
+        File layout: every drain appends one *segment* = the new rows of chain 0, of chain
+        1, ... of this process.  The file is therefore chronological to within one output
+        interval, so that the ``skip``/``thin`` that ``load_samples``/GetDist apply per
+        FILE (output.py:324-424) act on every chain's early part, as they do for the
+        reference's one-chain-per-file layout."""
+        ens = self._ens
+        if ens is None or self._row_cursor is None:
+            return
+        rows, counts = ens.engine.rows_bulk(first=self._row_cursor)
+        if not len(rows):
+            return
+        self._row_cursor = self._row_cursor + counts
+        self._segments.append(counts)
+        df = pd.DataFrame(rows, columns=list(self.collection.columns))
+        self.collection._cache_reset()
+        self.collection._data = df if not len(self.collection._data) else pd.concat(
+            [self.collection._data, df], ignore_index=True)
         if self.output:
-            # the file is the concatenation of this process' chains, so more rows per chain
-            # (a resumed run, or products() after more sampling) is not an append: rewrite
+            with open(self.rows_filename(), "ab") as f:
+                rows.tofile(f)
+            self.collection.out_update()
+
+    def _save_state(self, ens):
+        """Engine snapshot without rows (they are in the binary rows file, appended to at
+        every drain): a few MB however long the run."""
+        import os
+
+        snap = ens.snapshot(with_rows=False)
+        snap["segments"] = (np.array(self._segments, np.int64).reshape(-1, ens.n_chains_local))
+        snap["file_rows"] = np.int64(len(self.collection))
+        tmp = self.snapshot_filename() + ".tmp"
+        with open(tmp, "wb") as f:
+            np.savez(f, **snap)
+        os.replace(tmp, self.snapshot_filename())
+
+    def _restore_rows(self, snap):
+        """Resuming: rebuild every chain's rows (chain-major, for the engine) from the
+        binary rows file and the segment table of the snapshot, and the collection from
+        the same rows (bit-exact; the text file is only checked for length)."""
+        if snap is None:
+            return None
+        import os
+
+        W = int(snap["row_width"])
+        seg = np.asarray(snap["segments"], np.int64).reshape(-1, int(snap["n_chains_local"]))
+        file_rows = int(snap["file_rows"])
+        if seg.sum() != file_rows or not np.array_equal(seg.sum(axis=0), snap["n_rows"]):
+            raise LoggedError(self.log, "Cannot resume: the snapshot's segment table does not "
+                                        "match its row counts.")
+        try:
+            flat = np.fromfile(self.rows_filename(), dtype=np.float64, count=file_rows * W)
+        except OSError as e:
+            raise LoggedError(self.log, "Cannot resume: rows file '%s' not readable (%s)",
+                              self.rows_filename(), e)
+        if flat.size != file_rows * W:
+            raise LoggedError(self.log, "Cannot resume: rows file '%s' holds %d rows, the "
+                                        "snapshot expects %d.", self.rows_filename(),
+                              flat.size // W, file_rows)
+        if os.path.getsize(self.rows_filename()) != file_rows * W * 8:
+            with open(self.rows_filename(), "r+b") as f:  # an output the snapshot never saw
+                f.truncate(file_rows * W * 8)
+        rows = flat.reshape(file_rows, W)
+        # segment order -> chain-major order
+        n_rows = seg.sum(axis=0)
+        chain_off = np.concatenate([[0], np.cumsum(n_rows)[:-1]])
+        before = np.zeros_like(n_rows)
+        dest = np.empty(file_rows, np.int64)
+        pos = 0
+        for counts in seg:
+            tot = int(counts.sum())
+            ids = np.repeat(np.arange(len(counts)), counts)
+            starts = np.concatenate([[0], np.cumsum(counts)[:-1]])
+            within = np.arange(tot) - np.repeat(starts, counts)
+            dest[pos: pos + tot] = chain_off[ids] + before[ids] + within
+            before = before + counts
+            pos += tot
+        chain_major = np.empty_like(rows)
+        chain_major[dest] = rows
+        # the collection continues the file: same rows, exact values
+        n_txt = len(self.collection)
+        self._collection_from_rows(rows, self.collection)
+        self.collection._n_last_out = file_rows
+        if n_txt != file_rows:  # text file ahead of / behind the snapshot: rewrite it
             self.collection._out_delete()
             self.collection._n_last_out = 0
             self.collection.out_update()
+        self._segments = [c for c in seg]
+        self._row_cursor = n_rows.copy()
+        snap = dict(snap)
+        snap["rows"] = chain_major
+        return snap
 
     # ------------------------------------------------------------------ products
     def samples(self, combined: bool = False, skip_samples: float = 0,

@@ -32,6 +32,8 @@ typedef struct cb2_engine cb2_engine;
 /* flags returned per chain by cb2_get_flags */
 #define CB2_FLAG_STUCK 1u        /* mcmc.py:717-743 "chain has been stuck" */
 #define CB2_FLAG_ROWS_FULL 2u    /* per-chain sample capacity exhausted */
+#define CB2_FLAG_INTERNAL 4u     /* engine invariant violated (basis/tape window, or a
+                                    non-finite start point in cb2_set_state) */
 
 /* moment modes of cb2_moments */
 #define CB2_MOMENTS_HALVES 0     /* multi-chain rule, mcmc.py:785-793 */
@@ -132,6 +134,9 @@ int64_t cb2_snapshot_size(cb2_engine *h);
 int cb2_export_state(cb2_engine *h, void *buf, int64_t nbytes);
 int cb2_import_state(cb2_engine *h, const void *buf, int64_t nbytes);
 int cb2_load_rows(cb2_engine *h, int64_t chain, int64_t n, const double *rows);
+/* the same for chains [chain_begin, chain_end) at once: rows chain-major, counts[c] each */
+int cb2_load_rows_bulk(cb2_engine *h, int64_t chain_begin, int64_t chain_end,
+                       const int64_t *counts, const double *rows);
 
 /* Model.logposterior (cobaya/model.py:579-678) for n points X[n*D]:
  * logpost[n], logprior[n], loglikes[n*n_like], derived[n*n_derived] (NULL ok). */
@@ -144,7 +149,7 @@ int cb2_advance(cb2_engine *h, int64_t n_proposals);
 int cb2_sync(cb2_engine *h);
 
 /* out[0..7] = min rows, max rows, sum rows, #stuck chains, #rows-full chains,
- * proposals per chain so far, sum accepted, sum of current weights */
+ * #chains with CB2_FLAG_INTERNAL, sum accepted, sum of current weights */
 int cb2_summary(cb2_engine *h, int64_t out[8]);
 
 /* Per-GPU sufficient statistics of check_convergence_and_learn_proposal
@@ -170,6 +175,36 @@ int cb2_bounds(cb2_engine *h, int32_t mode, int32_t split, double limfrac,
  * out[n*width], width = cb2_row_width. Returns number of rows copied (>=0). */
 int64_t cb2_copy_rows(cb2_engine *h, int64_t chain, int64_t row_begin, int64_t n,
                       double *out);
+/* Bulk transfer of sample rows.  The reference appends every accepted point to a host-side
+ * SampleCollection (cobaya/collection.py:402-427,519-571, dumped by out_update :1287-1315);
+ * the engine stores rows in HBM and hands them over in bulk: the rows
+ * [first[c], n_rows[c]) of chains chain_begin <= c < chain_end (first == NULL: from row 0;
+ * first is indexed from chain_begin) are compacted chain-major on the device and copied
+ * with one transfer.  counts[c - chain_begin] (NULL ok) = rows of chain c.  out == NULL:
+ * size query.  Returns the total number of rows (>= 0) or a negative error; fails if the
+ * total exceeds max_rows. */
+int64_t cb2_copy_rows_bulk(cb2_engine *h, int64_t chain_begin, int64_t chain_end,
+                           const int64_t *first, int64_t *counts, double *out,
+                           int64_t max_rows);
+/* Asynchronous drain inside the run loop (the engine keeps a per-chain cursor: rows
+ * before it have been handed over).  cb2_drain_start compacts the rows added since the
+ * previous drain and enqueues ONE device-to-host copy of them (then of counts[n_chains],
+ * NULL ok) on a copy stream, so that the following cb2_advance runs under the transfer;
+ * it returns the number of rows being copied.  `out` and `counts` should be page-locked
+ * (cb2_host_alloc) and must not be read before cb2_drain_wait returns; two drains may be
+ * in flight (staging double buffer).  cb2_drain_reset sets the cursor (NULL: row 0). */
+int64_t cb2_drain_start(cb2_engine *h, double *out, int64_t max_rows, int64_t *counts);
+int cb2_drain_wait(cb2_engine *h);
+int cb2_drain_reset(cb2_engine *h, const int64_t *first);
+/* page-locked host memory for the transfers above (plain pointers; NULL on failure) */
+void *cb2_host_alloc(int64_t bytes);
+int cb2_host_free(void *p);
+/* Re-layout of the row store for a larger per-chain capacity; stored rows are kept.  Call
+ * it before a chain can run out of room: cb2_advance(n) adds at most n rows per chain. */
+int cb2_grow_rows(cb2_engine *h, int64_t new_rows_cap);
+/* device memory: free and total bytes of the engine's GPU, bytes held by the row store */
+int cb2_mem_info(cb2_engine *h, int64_t *free_bytes, int64_t *total_bytes,
+                 int64_t *rows_bytes);
 int32_t cb2_row_width(const cb2_engine *h);
 int32_t cb2_n_derived(const cb2_engine *h);
 
@@ -194,6 +229,11 @@ int cb2_kernel_times(cb2_engine *h, double ms[5], int64_t n[5], int32_t reset);
  * 3 = streamed (batched DMMA / cuBLAS products of every proposal direction + accept chain) */
 int cb2_last_step_kernel(const cb2_engine *h);
 const char *cb2_debug_message(const cb2_engine *h); /* why a faster kernel was not used */
+/* windows run by each step kernel since the last reset: out[0..3] indexed as
+ * cb2_last_step_kernel; out[4] = windows whose k_step_pc launch was refused (ran on the
+ * single-role DMMA kernel), out[5] = windows whose streamed buffers did not fit in device
+ * memory (ran on the general kernel).  Nothing changes kernels silently. */
+int cb2_window_counts(cb2_engine *h, int64_t out[6], int32_t reset);
 /* 0 auto, 1 force the general kernels, 2 fast kernels without the producer/consumer one;
  * +4: Householder sweep of the Haar bases with DFMA instead of the tensor pipe (n <= 64) */
 int cb2_set_kernel_policy(cb2_engine *h, int32_t policy);

@@ -78,10 +78,9 @@ def test_random_so_n_matches_reference_rvs(cuda_lib, n, policy):
 
 
 CASES = [("g1_gauss3d", 0), ("g1_gauss3d", 7), ("g2_blocks_mixture", 3),
-         ("g3_dragging", 1), ("g4_block1d", 5)]
-# g7_stream72 (72-D, streamed kernels) pins the ORACLE against the reference on the CPU
-# (tests/test_oracle_cpu.py); the engine-vs-oracle tests below cover the same kernels on the GPU.
-# Its direct engine-vs-golden comparison could not be run before the round's GPU budget ended.
+         ("g3_dragging", 1), ("g4_block1d", 5),
+         # 72-D, two blocks, two modes: the streamed kernels against the reference's own rows
+         ("g7_stream72", 2), ("g7_stream72", 9)]
 
 
 @pytest.mark.parametrize("name,cid", CASES)

@@ -189,17 +189,25 @@ def test_cobaya_run_resume_continues_bit_for_bit(cuda_lib, tmp_path):
     assert 400 <= first.n() < 900
     _, second = run(copy.deepcopy(info(pb, 900)), resume=True)
     assert second.n_steps_raw == full.n_steps_raw
+    # same rows, exact values; the ORDER in the collection / chain file is by output segment
+    # (one segment per drain: first run, then the resumed part), so compare as sorted sets
+    # and chain by chain through the engine
     a, b = full.collection.data.to_numpy(), second.collection.data.to_numpy()
     assert a.shape == b.shape
-    np.testing.assert_array_equal(a, b)
+    key = lambda m: m[np.lexsort(m.T[::-1])]
+    np.testing.assert_array_equal(key(a), key(b))
+    for c in (0, 7, 15):
+        np.testing.assert_array_equal(full._ens.chain_rows(c), second._ens.chain_rows(c))
+    assert len(second._segments) == 2 and len(full._segments) == 1
     np.testing.assert_array_equal(full.proposer.get_covariance(),
                                   second.proposer.get_covariance())
     assert len(second.progress) == len(full.progress)
-    # the chain file on disk was rewritten with the longer chains
+    # the chain file on disk was appended to, not rewritten
     from cobaya.output import load_samples
 
     back = load_samples(pb, skip=0, combined=True)
     assert len(back) == len(b)
+    np.testing.assert_allclose(back.data.to_numpy()[:, :5], b[:, :5], rtol=1e-7)
 
 
 @pytest.mark.gpu

@@ -121,9 +121,10 @@ WORKER = textwrap.dedent("""
     shift = np.full(D, 0.19)
     tot = td.all_reduce_sum(local_sums(mine, D, shift))
     res = rminus1_from_sums(tot, D, shift)
-    mn, mx, sm = td.all_reduce_min_max_sum([min(len(r) for r in mine)],
-                                           [max(len(r) for r in mine)],
-                                           [sum(len(r) for r in mine)])
+    # the per-launch summary: one all-gather of the ranks' int64 vectors
+    allv = td.all_gather_i64([min(len(r) for r in mine), max(len(r) for r in mine),
+                              sum(len(r) for r in mine)])
+    mn, mx, sm = [allv[:, 0].min()], [allv[:, 1].max()], [allv[:, 2].sum()]
     # samples(combined=True) / to_getdist: per-rank row arrays gathered on every rank
     gathered = td.all_gather_object([np.asarray(r) for r in mine])
     n_gathered = [sum(len(r) for r in part) for part in gathered]

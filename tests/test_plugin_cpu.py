@@ -252,17 +252,39 @@ def test_products_and_output_files_roundtrip(tmp_path):
             om = orc.OracleModel(fm)
             self.rows = [orc.OracleChain(om, 7, c, x0[c], burn_in=2).advance(600)[1]
                          for c in range(len(x0))]
+            self.n_chains_local = len(x0)
+            self.engine = self
+            self.visible = 0.4  # fraction of every chain "sampled so far"
+
+        def rows_bulk(self, first=None, chains=None):  # Engine.rows_bulk
+            first = np.zeros(len(self.rows), np.int64) if first is None else first
+            part = [r[f: int(self.visible * len(r))] for r, f in zip(self.rows, first)]
+            return np.concatenate(part), np.array([len(q) for q in part], np.int64)
 
         def samples(self, chains=None, skip_samples=0.0):
             k = lambda r: int(skip_samples * len(r)) if 0 < skip_samples < 1 else int(skip_samples)
             return np.concatenate([r[k(r):] for r in self.rows])
 
     s._ens = FakeEnsemble(s._fm, s._x0)
-    s._fill_collection()
+    s._row_cursor = np.zeros(3, np.int64)
+    s._drain_rows()                    # a timed output in the middle of the run ...
+    n_first = len(s.collection)
+    assert 0 < n_first == sum(int(0.4 * len(r)) for r in s._ens.rows)
+    assert len(load_samples(prefix, skip=0, combined=True)) == n_first  # ... is on disk
+    s._ens.visible = 1.0
+    s._drain_rows()                    # ... and the rest at the end: appended, not rewritten
     s.write_checkpoint()
     col = s.products()["sample"]
     n = sum(len(r) for r in s._ens.rows)
     assert len(col) == n and list(col.columns) == s._fm.columns()
+    # layout: one segment per output, chains in order inside a segment
+    assert [list(c) for c in s._segments] == [
+        [int(0.4 * len(r)) for r in s._ens.rows],
+        [len(r) - int(0.4 * len(r)) for r in s._ens.rows]]
+    np.testing.assert_array_equal(col.data.to_numpy()[: int(0.4 * len(s._ens.rows[0]))],
+                                  s._ens.rows[0][: int(0.4 * len(s._ens.rows[0]))])
+    raw = np.fromfile(s.rows_filename()).reshape(n, -1)   # binary twin of the chain file
+    np.testing.assert_array_equal(raw, col.data.to_numpy())
     # the g2 case samples at temperature 2: compare the statistics of the tempered sample
     np.testing.assert_allclose(col.mean(tempered=True), np.average(
         np.concatenate(s._ens.rows)[:, 2:7], axis=0, weights=np.concatenate(s._ens.rows)[:, 0]))
