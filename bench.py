@@ -71,12 +71,20 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self._stop = index, [], threading.Event()
+        self.mark0 = self.mark1 = None
+
+    def mark(self, which):
+        """Remember how many samples existed when the timed region started / ended."""
+        if which == 0:
+            self.mark0 = len(self.rows)
+        else:
+            self.mark1 = len(self.rows)
 
     def run(self):
         try:
             self.p = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                 "-lms", "25", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             for line in self.p.stdout:
                 self.rows.append([c.strip() for c in line.split(",")])
                 if self._stop.is_set():
@@ -90,8 +98,16 @@ class ClockSampler(threading.Thread):
             self.p.terminate()
         except Exception:
             pass
+        # samples taken inside the timed region; the region can be shorter than nvidia-smi's
+        # start-up, so the sampler runs from before the warm-up (the same kernels, the same
+        # load) and falls back to those samples when the region itself holds fewer than 3
+        rows, where = self.rows, "warm-up + timed region"
+        if self.mark0 is not None and self.mark1 is not None and self.mark1 - self.mark0 >= 3:
+            rows, where = self.rows[self.mark0:self.mark1], "timed region"
+        elif self.mark0 is not None and len(self.rows) - self.mark0 >= 3:
+            rows, where = self.rows[self.mark0:], "timed region + e2e leg"
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
                 for name, v in zip(["hw_slowdown", "hw_thermal_slowdown",
@@ -102,7 +118,7 @@ class ClockSampler(threading.Thread):
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": float(max(mx)) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "sampled_during": where}
 
 
 # ------------------------------------------------------------------ CPU legs
@@ -352,6 +368,9 @@ def run_gpu_arm(args):
             n_ckpt += 1
 
     smp.launch_steps = locksteps
+    clocks = ClockSampler(local) if rank == 0 else None
+    if clocks:
+        clocks.start()
     for _ in range(W):
         one_step()
     # the checkpoint kernels are part of the warm-up too (CUDA loads a kernel lazily on its
@@ -359,9 +378,8 @@ def run_gpu_arm(args):
     smp._moments(0, 0)
     smp._bounds(0, 0, 0.475)
     barrier()
-    clocks = ClockSampler(local) if rank == 0 else None
     if clocks:
-        clocks.start()
+        clocks.mark(0)
     eng.set_profiling(True)
     eng.kernel_times(reset=True)
     eng.window_counts(reset=True)
@@ -374,13 +392,14 @@ def run_gpu_arm(args):
         one_step()
     ms_dev = eng.timer_stop()
     barrier()
+    if clocks:
+        clocks.mark(1)
     t_wall = time.perf_counter() - t_wall
     kt = eng.kernel_times(reset=True)
     windows = eng.window_counts(reset=True)
     eng.set_profiling(False)
     launches = eng.launch_count() - l0
     rows1 = eng.summary()["sum_rows"]
-    clk = clocks.stop() if clocks else None
     # max over ranks of the device time
     t = torch.tensor([ms_dev], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -424,6 +443,7 @@ def run_gpu_arm(args):
     if world > 1:
         tdist.all_reduce(tt, op=tdist.ReduceOp.MAX)
     e2e_value = world * C * locksteps * Ke / float(tt.item())
+    clk = clocks.stop() if clocks else None
     row_bytes = float(np.mean(rows_out)) * Wd * 8
     # the rows really are on the host: weights are positive integers, chain counts add up
     last = bufs[(Ke - 1) % 2][: rows_out[-1] * Wd].reshape(-1, Wd)

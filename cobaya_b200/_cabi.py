@@ -28,7 +28,7 @@ EXPORTS = [
     "cb2_launch_count", "cb2_timer_start", "cb2_timer_stop", "cb2_last_step_kernel",
     "cb2_set_kernel_policy", "cb2_set_profiling", "cb2_kernel_times", "cb2_debug_message",
     "cb2_copy_rows_bulk", "cb2_drain_start", "cb2_drain_wait", "cb2_drain_reset",
-    "cb2_host_alloc", "cb2_host_free", "cb2_grow_rows", "cb2_mem_info", "cb2_load_rows_bulk", "cb2_window_counts",
+    "cb2_host_alloc", "cb2_host_free", "cb2_grow_rows", "cb2_mem_info", "cb2_load_rows_bulk", "cb2_window_counts", "cb2_debug_counters",
 ]
 
 
@@ -99,6 +99,7 @@ def load():
     L.cb2_grow_rows.argtypes = [vp, i64]
     L.cb2_mem_info.argtypes = [vp, vp, vp, vp]
     L.cb2_window_counts.argtypes = [vp, vp, i32]
+    L.cb2_debug_counters.argtypes = [vp, vp, i32]
     L.cb2_load_rows_bulk.argtypes = [vp, i64, i64, vp, vp]
     L.cb2_row_width.restype = i32
     L.cb2_row_width.argtypes = [vp]

@@ -49,6 +49,7 @@ static int pack_fast(cb2_engine *h) {
     P.off_lower = take(DP); P.off_upper = take(DP); P.off_loc = take(DP);
     P.off_mls = take(DP); P.off_isc = take(DP); P.off_pa = take(DP); P.off_pb = take(DP);
     P.off_flags = take(DP); P.off_iofj = take(DP);
+    P.off_klo = take(DP); P.off_kup = take(DP);
     P.total = o;
     {
         bool ident = (D == DP) && (row_width(h) % 2 == 0);
@@ -81,6 +82,15 @@ static int pack_fast(cb2_engine *h) {
         pk[P.off_w + km] = L.w[km];
     }
     // flags / i_of_j are stored as int32 inside the (double) pack
+    // order-preserving integer keys of the bounds (k_step_pc2 tests them on the integer pipe)
+    auto dkey = [](double d) {
+        int64_t b;
+        memcpy(&b, &d, 8);
+        b ^= (b >> 63) & 0x7fffffffffffffffLL;
+        double out;
+        memcpy(&out, &b, 8);
+        return out;
+    };
     int32_t *iflags = reinterpret_cast<int32_t *>(pk.data() + P.off_flags);
     int32_t *iiofj = reinterpret_cast<int32_t *>(pk.data() + P.off_iofj);
     for (int j = 0; j < DP; ++j) {
@@ -88,6 +98,8 @@ static int pack_fast(cb2_engine *h) {
             const int i = h->i_of_j[j];
             pk[P.off_lower + j] = h->lower[i];
             pk[P.off_upper + j] = h->upper[i];
+            pk[P.off_klo + j] = dkey(h->lower[i]);
+            pk[P.off_kup + j] = dkey(h->upper[i]);
             pk[P.off_loc + j] = h->loc[i];
             pk[P.off_isc + j] = h->pscale[i];
             const int kd = h->prior_kind[i];
@@ -100,6 +112,8 @@ static int pack_fast(cb2_engine *h) {
         } else {
             pk[P.off_lower + j] = -INFINITY;
             pk[P.off_upper + j] = INFINITY;
+            pk[P.off_klo + j] = dkey(-INFINITY);
+            pk[P.off_kup + j] = dkey(INFINITY);
             pk[P.off_isc + j] = 1.0;
             iflags[j] = 0;
             iiofj[j] = -1;
@@ -107,6 +121,30 @@ static int pack_fast(cb2_engine *h) {
     }
     int rc = upload(h, h->d_fastpack, pk);
     if (rc) return rc;
+    // G = (L^-1 P) T for k_step_pc2 (one mode, triangular likelihood matrix): the image of a
+    // direction in whitened coordinates without going through delta.  Lower triangular as
+    // the product of two lower-triangular matrices; accumulated in extended precision.
+    h->fastG_ready = false;
+    if (tri && nm == 1) {
+        std::vector<double> Am((size_t)DP * DP, 0.0), Tm((size_t)DP * DP, 0.0),
+            Gm((size_t)DP * DP, 0.0);
+        for (int a = 0; a < D; ++a)
+            for (int j = 0; j <= a; ++j)
+                Am[(size_t)a * DP + j] = L.linvT[(size_t)ilike_of_i[h->i_of_j[j]] * D + a];
+        for (int j = 0; j < D; ++j)
+            for (int k = 0; k <= j; ++k) Tm[(size_t)j * DP + k] = h->Trow[(size_t)j * D + k];
+        for (int a = 0; a < D; ++a)
+            for (int k = 0; k <= a; ++k) {
+                long double acc = 0.0L;
+                for (int j = k; j <= a; ++j)
+                    acc += (long double)Am[(size_t)a * DP + j] * (long double)Tm[(size_t)j * DP + k];
+                Gm[(size_t)a * DP + k] = (double)acc;
+            }
+        std::vector<double> gk((size_t)blocks_T * 64, 0.0);
+        pack_frag(gk, 0, Gm, DP, NT, true);
+        if ((rc = upload(h, h->d_fastG, gk))) return rc;
+        h->fastG_ready = true;
+    }
     h->fast_desc = P;
     h->fast_ready = true;
     return 0;

@@ -775,6 +775,7 @@ struct FastPackDesc {
     int off_pa, off_pb;  // [DP] shape parameters of the generic 1-D priors
     int off_flags; // [DP] as doubles: bit0 non-uniform prior, bit1 periodic, bits 8.. prior kind
     int off_iofj;  // [DP] as doubles: sampler index of sorted j (or -1 for padding)
+    int off_klo, off_kup;  // [DP] order-preserving int64 keys of lower / upper
     int iofj_identity;  // D == DP, i_of_j[j] == j and the row stride keeps 16-byte alignment
     int vec_ok;         // every block with n_b >= 2 has even start and even size
     int total;     // doubles

@@ -353,10 +353,10 @@ class Engine:
 
     def window_counts(self, reset: bool = False):
         """Windows run by each step kernel, and windows that left their preferred kernel."""
-        v = np.zeros(6, np.int64)
+        v = np.zeros(8, np.int64)
         self._ck(self.lib.cb2_window_counts(self.h, _cabi.ptr(v), int(reset)))
         names = ["general", "dmma", "dmma-producer-consumer", "dmma-streamed",
-                 "pc_launch_refused", "streamed_did_not_fit"]
+                 "pc_launch_refused", "streamed_did_not_fit", "of_pc_split_products"]
         return {k: int(x) for k, x in zip(names, v)}
 
     def debug_message(self):

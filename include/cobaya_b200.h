@@ -230,12 +230,19 @@ int cb2_kernel_times(cb2_engine *h, double ms[5], int64_t n[5], int32_t reset);
 int cb2_last_step_kernel(const cb2_engine *h);
 const char *cb2_debug_message(const cb2_engine *h); /* why a faster kernel was not used */
 /* windows run by each step kernel since the last reset: out[0..3] indexed as
- * cb2_last_step_kernel; out[4] = windows whose k_step_pc launch was refused (ran on the
- * single-role DMMA kernel), out[5] = windows whose streamed buffers did not fit in device
- * memory (ran on the general kernel).  Nothing changes kernels silently. */
-int cb2_window_counts(cb2_engine *h, int64_t out[6], int32_t reset);
+ * cb2_last_step_kernel; out[4] = windows whose producer/consumer launch was refused (ran on
+ * the next DMMA kernel), out[5] = windows whose streamed buffers did not fit in device
+ * memory (ran on the general kernel), out[6] = of out[2], the windows on the variant with
+ * the products split over the SM sub-partitions (k_step_pc2), out[7] reserved.  Nothing
+ * changes kernels silently. */
+int cb2_window_counts(cb2_engine *h, int64_t out[8], int32_t reset);
+/* kernel experiments: cycle counters of one producer and one consumer warp of k_step_pc2 in
+ * libraries built with -DCB2_PC2_TIMING (zeros otherwise) */
+int cb2_debug_counters(cb2_engine *h, int64_t out[16], int32_t reset);
 /* 0 auto, 1 force the general kernels, 2 fast kernels without the producer/consumer one;
- * +4: Householder sweep of the Haar bases with DFMA instead of the tensor pipe (n <= 64) */
+ * +4: Householder sweep of the Haar bases with DFMA instead of the tensor pipe (n <= 64);
+ * +8: producer/consumer kernel with one producer warp per tile (k_step_pc) where the
+ *     split-product variant (k_step_pc2) would be chosen */
 int cb2_set_kernel_policy(cb2_engine *h, int32_t policy);
 
 #ifdef __cplusplus

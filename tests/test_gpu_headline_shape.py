@@ -71,11 +71,14 @@ def _compare_with_oracle(eng, fm, seed, id0, x0, chains, n, burn_in=0, state=Non
     return worst
 
 
+@pytest.mark.parametrize("variant", ["split_products", "producer_per_tile"])
 @pytest.mark.parametrize("n_chains", [2048, 8192, 65536])
-def test_headline_shape_pc_kernel_matches_oracle(cuda_lib, n_chains):
+def test_headline_shape_pc_kernel_matches_oracle(cuda_lib, n_chains, variant):
     """BASELINE configs[1] exactly as bench.py runs it (64-D, one block, proposal = diag of
-    the target, bounds [-1, 1]): k_step_pc with 2 and 7 warp pairs per CTA and, at 65 536
-    chains, several waves of CTAs; two windows of 4 proposal cycles."""
+    the target, bounds [-1, 1]) on both producer/consumer kernels: k_step_pc2 (products
+    split over the SM sub-partitions, 2 and 7 tiles per CTA) and k_step_pc (one warp pair
+    per tile, 2 and 7 pairs per CTA; policy +8); at 65 536 chains several waves of CTAs; two
+    windows of 4 proposal cycles."""
     from cobaya_b200.flatmodel import FlatModel, synthetic_gaussian_cov
 
     D, n = 64, 512
@@ -86,16 +89,21 @@ def test_headline_shape_pc_kernel_matches_oracle(cuda_lib, n_chains):
     x0 = rng.multivariate_normal(np.zeros(D), cov, size=n_chains)
     id0 = 8192 * 3  # as on rank 3 of a multi-GPU run
     eng = _engine(fm, n_chains, seed=1, chain_id0=id0, rows_cap=n)
+    if variant == "producer_per_tile":
+        eng.set_kernel_policy(8)
     eng.set_state(x0)
     eng.advance(256)
     eng.advance(256)
     assert eng.last_step_kernel() == 2, eng.debug_message()
     assert eng.debug_message() == ""
+    wc = eng.window_counts()
+    assert wc["dmma-producer-consumer"] == 2 and wc["pc_launch_refused"] == 0
+    assert wc["of_pc_split_products"] == (2 if variant == "split_products" else 0)
     tiles = (n_chains + 7) // 8
     wpc = min(7, -(-tiles // SMS))
     assert wpc == {2048: 2, 8192: 7, 65536: 7}[n_chains]
     chains = _sample_chains(n_chains, wpc)
-    assert len(chains) >= 40
+    assert len(chains) >= 20
     _compare_with_oracle(eng, fm, 1, id0, x0, chains, n)
 
 
