@@ -320,12 +320,10 @@ def run_gpu_arm(args):
         import torch.distributed as tdist
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL's log goes to a file per rank (rank count, transports, NVLS are observable
-        # there); stdout stays the single JSON line
-        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_FILE",
-                              os.path.join(ROOT, "gpurun_out", f"nccl_n{world}_%h_%p.log"))
+        # NCCL_DEBUG / NCCL_DEBUG_FILE are left exactly as the launcher set them: whatever
+        # NCCL logs (rank count, transports, NVLS) goes to stderr or to the launcher's file;
+        # stdout stays the single JSON line (file descriptor 1 points at stderr, see
+        # _quiet_stdout)
         tdist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from cobaya_b200 import problems
     from cobaya_b200.mcmc import EnsembleMCMC, TorchDist

@@ -103,12 +103,42 @@ def _check_lowered_priors(prior, kind, lower, upper, loc, scale, pa, pb):
                     f"be lowered consistently (engine {got!r} vs scipy {want!r} at x={x!r}).")
 
 
+def _reference_class(module: str, name: str):
+    """The reference's own likelihood class, or None when that module is not importable."""
+    try:
+        import importlib
+
+        return getattr(importlib.import_module(module), name)
+    except Exception:
+        return None
+
+
+def _indices(like, name, sampled):
+    """Positions of a likelihood's input parameters in the sampled vector; an input that is
+    fixed or derived from others is outside what the device evaluates."""
+    missing = [p for p in like.input_params if p not in sampled]
+    if missing:
+        raise UnsupportedModelError(
+            f"Likelihood '{name}': input parameter(s) {missing} are not sampled (fixed or "
+            "dynamically defined inputs are not supported by the B200 ensemble engine).")
+    return [sampled.index(p) for p in like.input_params]
+
+
 def lower_likelihoods(model, sampled):
+    """Recognised by CLASS (isinstance against the reference's classes), never by name: a
+    user class that happens to be called ``GaussianMixture`` is not lowered as the built-in."""
+    gm_cls = _reference_class("cobaya.likelihoods.gaussian_mixture", "GaussianMixture")
+    g_cls = _reference_class("cobaya.likelihoods.gaussian", "Gaussian")
+    one_cls = _reference_class("cobaya.likelihoods.one", "one")
+    if len(getattr(model, "theory", {}) or {}):
+        raise UnsupportedModelError(
+            "Theory components are not supported by the B200 ensemble engine: "
+            f"{list(model.theory)}. No CPU fallback is provided.")
     likes = []
     for name, like in model.likelihood.items():
         cls = type(like).__name__
-        if cls == "GaussianMixture":
-            idx = [sampled.index(p) for p in like.input_params]
+        if gm_cls is not None and isinstance(like, gm_cls):
+            idx = _indices(like, name, sampled)
             weights = like.weights
             if np.isscalar(weights):
                 weights = None
@@ -119,15 +149,15 @@ def lower_likelihoods(model, sampled):
                     derived_names=list(like.output_params) if like.derived else [],
                 )
             )
-        elif cls == "Gaussian" and hasattr(like, "inv_cov"):
-            idx = [sampled.index(p) for p in like.input_params]
+        elif g_cls is not None and isinstance(like, g_cls):
+            idx = _indices(like, name, sampled)
             likes.append(LikeSpec.gaussian(idx, np.asarray(like.mean), np.asarray(like.cov),
                                            normalized=bool(getattr(like, "normalized", True)),
                                            name=name))
-        elif cls == "one" and not getattr(like, "noise", None):
+        elif one_cls is not None and isinstance(like, one_cls) and not getattr(like, "noise", None):
             likes.append(LikeSpec.constant(0.0, name=name))
-        elif cls == "Rosenbrock" and hasattr(like, "b200_scale"):
-            idx = [sampled.index(p) for p in like.input_params]
+        elif hasattr(like, "b200_scale") and cls == "Rosenbrock":  # the engine's own built-in
+            idx = _indices(like, name, sampled)
             likes.append(LikeSpec.rosenbrock(idx, scale=like.b200_scale, name=name))
         else:
             raise UnsupportedModelError(
