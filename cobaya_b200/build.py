@@ -38,8 +38,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not (force or is_stale()):
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
-    # cuBLAS: only for the plain D x D GEMMs of the 128 < D <= 512 streamed path
-    cmd = [nvcc_path()] + NVCC_FLAGS + ["-o", LIB, os.path.join(SRC, "engine.cu"), "-lcublas"]
+    # no library kernels: every kernel of the engine is in csrc/
+    cmd = [nvcc_path()] + NVCC_FLAGS + ["-o", LIB, os.path.join(SRC, "engine.cu")]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr
     with open(os.path.join(LIB_DIR, "build.log"), "w") as f:

@@ -197,7 +197,7 @@ static int pack_stream(cb2_engine *h) {
                 if (aoff[l] + a < j && v != 0.0) tri = false;
             }
         }
-    const bool frag = D <= CB2_STREAM_FRAG_MAX_D;  // above: plain matrices for cuBLAS
+    const bool frag = D <= CB2_STREAM_FRAG_MAX_D;  // above: plain matrices for k_rowgemm
     P.tri_like = tri ? 1 : 0;
     P.blocks_T = frag ? NT * (NT + 1) / 2 : 0;
     P.blocks_A = frag ? (tri ? P.blocks_T : NT * NT) : 0;
@@ -226,16 +226,10 @@ static int pack_stream(cb2_engine *h) {
         for (int k = 0; k <= j; ++k) Tm[(size_t)j * DP + k] = h->Trow[(size_t)j * D + k];
     if (frag) pack_frag(pk, P.off_T, Tm, DP, NT, true);
     else {
-        // column-major copies: Tcm[j + i DP] = T[j][i], Acm[a + j DP] = (L^-1 P)[a][j]
-        std::vector<double> Tcm((size_t)DP * DP), Acm((size_t)DP * DP);
-        for (int j = 0; j < DP; ++j)
-            for (int i = 0; i < DP; ++i) {
-                Tcm[(size_t)j + (size_t)i * DP] = Tm[(size_t)j * DP + i];
-                Acm[(size_t)j + (size_t)i * DP] = Am[0][(size_t)j * DP + i];
-            }
+        // row-major DP x DP copies for k_rowgemm: Trm[j][i] = T[j][i], Arm[a][j] = (L^-1 P)[a][j]
         int rcu;
-        if ((rcu = upload(h, h->d_Tcm, Tcm))) return rcu;
-        if ((rcu = upload(h, h->d_Acm, Acm))) return rcu;
+        if ((rcu = upload(h, h->d_Trm, Tm))) return rcu;
+        if ((rcu = upload(h, h->d_Arm, Am[0]))) return rcu;
     }
     for (int km = 0; km < nm; ++km) {
         if (frag) pack_frag(pk, P.off_A + (size_t)km * P.blocks_A * 64, Am[km], DP, NT, tri);

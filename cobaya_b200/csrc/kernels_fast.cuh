@@ -488,13 +488,25 @@ k_basis_wy(uint32_t key0, uint32_t key1, uint64_t chain_id0, int block, int n,
             const int c = 8 * (sl ? t1 : t0) + q;
             if (c < n) {
                 if ((n & 1) == 0) {  // 16-byte stores: i even, rows of n doubles stay aligned
+                    // D[i] = +-1: the product is a sign flip, done on the integer pipe (a
+                    // vector FP64 instruction issued among DMMAs of the co-resident CTAs costs
+                    // the FP64 pipe about as much as a DMMA; tools/fp64_mix.cu)
 #pragma unroll
                     for (int nt = 0; nt < NG; ++nt) {
                         const int i = 8 * nt + 2 * r;
-                        if (i < n)
+                        if (i < n) {
+                            const double2 d2 = *reinterpret_cast<const double2 *>(Dv + i);
+                            const double db = (i + 1 == n - 1) ? d_last : d2.y;
+                            const unsigned long long sa =
+                                (unsigned long long)__double_as_longlong(d2.x) & 0x8000000000000000ull;
+                            const unsigned long long sb =
+                                (unsigned long long)__double_as_longlong(db) & 0x8000000000000000ull;
                             *reinterpret_cast<double2 *>(out + (size_t)c * n + i) = make_double2(
-                                Dv[i] * nreg[sl][nt][0],
-                                (i + 1 == n - 1 ? d_last : Dv[i + 1]) * nreg[sl][nt][1]);
+                                __longlong_as_double((long long)((unsigned long long)
+                                    __double_as_longlong(nreg[sl][nt][0]) ^ sa)),
+                                __longlong_as_double((long long)((unsigned long long)
+                                    __double_as_longlong(nreg[sl][nt][1]) ^ sb)));
+                        }
                     }
                 } else {
 #pragma unroll

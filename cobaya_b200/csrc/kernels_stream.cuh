@@ -667,7 +667,7 @@ k_stream_accept(ModelDev M, ChainState S, StreamWindow SW, const double *__restr
 
 // ---------------------------------------------------------------------------------------
 // 128 < D <= 512: the proposal-side products are plain D x D x (directions) GEMMs with one
-// shared matrix and go to cuBLAS (cublasDgemm, FP64 tensor pipe); only the glue is here.
+// shared matrix and go to k_rowgemm (kernels_gemm.cuh, FP64 tensor pipe); only the glue is here.
 // k_stream_center: z[chain][j] = x_sorted[j] - mu[j] (input of the whitening GEMM).
 // k_stream_accept_big<NC>: k_stream_accept for one single-mode component with the per-coordinate
 // constants read from the constant block instead of registers (NC up to 16 coordinates per lane).
