@@ -318,3 +318,70 @@ def test_products_and_output_files_roundtrip(tmp_path):
     np.testing.assert_allclose(prog["N"], [1200, 2400])
     np.testing.assert_allclose(prog["Rminus1"], [0.8, 0.05])
     assert np.isnan(prog["Rminus1_cl"][0]) and prog["Rminus1_cl"][1] == 0.4
+
+
+def test_reference_minimize_and_post_consume_the_engine_output(tmp_path):
+    """SURVEY 8f row 4 (consumers): the files the plugin writes -- per-process chain file,
+    ``.covmat``, ``updated.yaml`` -- are what the reference's own ``minimize`` sampler
+    (start from the best sample, step sizes from the learned covmat:
+    samplers/minimize/minimize.py:170-250,435) and ``post`` (importance re-weighting over
+    the stored rows: post.py:279-600) read.  Chains come from the oracle-backed test
+    engine (no GPU here); everything downstream is the unmodified reference."""
+    enable_reference()
+    from cobaya.post import post
+    from cobaya.run import run
+
+    import cobaya_b200.plugin as plugin
+    from tests.oracle_engine import OracleEngine
+
+    g = __import__("tests.util", fromlist=["load_golden"]).load_golden("g1_gauss3d")
+    mean, cov = g["means"][0], np.asarray(g["covs"]).reshape(3, 3)
+    prefix = str(tmp_path / "run")
+    info = {
+        "likelihood": {"gaussian_mixture": {"means": [mean], "covs": [cov],
+                                            "input_params_prefix": "a_",
+                                            "output_params_prefix": "", "derived": False}},
+        "params": {f"a__{i}": {"prior": {"min": -1, "max": 1}} for i in range(3)},
+        "sampler": {"cobaya_b200.plugin.MCMC": {
+            "covmat": np.asarray(g["S0"]), "covmat_params": ["a__0", "a__1", "a__2"],
+            "burn_in": 5, "max_tries": 3000, "learn_proposal_Rminus1_max": 30,
+            "Rminus1_stop": 1e-9, "measure_speeds": False, "seed": 3, "chains_per_gpu": 6,
+            "max_samples": 700, "learn_every": "20d"}},
+        "output": prefix,
+    }
+    plugin.MCMC._engine_factory = OracleEngine
+    try:
+        _, smp = run(copy.deepcopy(info), force=True)
+    finally:
+        plugin.MCMC._engine_factory = None
+    learned = smp.proposer.get_covariance()
+    # ---- minimize: step sizes from the covmat file the plugin wrote.  (Sharing the output
+    # prefix, so that it also starts from the chain's best point, runs into a bug of the
+    # reference itself: minimize.py:197 passes `concatenate=` to Output.load_collections,
+    # which output.py:374 does not accept.)
+    info_min = copy.deepcopy(info)
+    del info_min["output"]
+    info_min["sampler"] = {"minimize": {"method": "scipy", "best_of": 1, "ignore_prior": False,
+                                        "covmat": prefix + ".covmat", "seed": 1}}
+    _, mini = run(info_min)
+    x_min = np.array([mini.products()["minimum"][f"a__{i}"] for i in range(3)])
+    np.testing.assert_allclose(x_min, mean, atol=2e-4)
+    # the step scales of the minimizer come from the covmat the engine wrote
+    np.testing.assert_allclose(mini._scales, 1 / np.sqrt(np.diag(np.linalg.inv(learned))),
+                               rtol=1e-5)
+    # ---- post: re-weight the stored sample to a shifted target
+    shift = np.array([0.02, -0.01, 0.0])
+    info_post = {"output": prefix, "post": {
+        "suffix": "shifted", "skip": 0.3,
+        "remove": {"likelihood": {"gaussian_mixture": None}},
+        "add": {"likelihood": {"gaussian_mixture": {
+            "means": [mean + shift], "covs": [cov], "input_params_prefix": "a_",
+            "output_params_prefix": "", "derived": False}}}}}
+    _, res = post(info_post)
+    col = res["sample"]
+    col = col[0] if isinstance(col, list) else col
+    before = smp.products(skip_samples=0.3)["sample"]
+    assert len(col) > 100
+    moved = np.array(col.mean()[:3]) - np.array(before.mean()[:3])
+    # importance re-weighting moves the mean towards the new target
+    assert np.dot(moved, shift) > 0.5 * np.dot(shift, shift)
