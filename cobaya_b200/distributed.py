@@ -262,11 +262,11 @@ def init(backend: str | None = None, device: int | None = None):
 
 def world_consistent() -> bool:
     """True unless torch.distributed has several ranks that ``cobaya.mpi`` does not know of."""
-    try:
-        import torch.distributed as dist
-    except ImportError:
-        return True
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+    import sys
+
+    dist = sys.modules.get("torch.distributed")  # never import torch just to ask (seconds)
+    if dist is None or not (dist.is_available() and dist.is_initialized()) or \
+            dist.get_world_size() == 1:
         return True
     from cobaya import mpi
 

@@ -575,7 +575,7 @@ class EnsembleMCMC:
 
         data = self.samples(chains, skip_samples)
         return {
-            "sample": pd.DataFrame(data, columns=self.fm.columns()),
+            "sample": pd.DataFrame(data, columns=self.fm.columns(), copy=False),
             "progress": pd.DataFrame(
                 [dict(N=c.N, timestamp=c.timestamp, acceptance_rate=c.acceptance_rate,
                       Rminus1=c.Rminus1, Rminus1_cl=c.Rminus1_cl) for c in self.progress]),

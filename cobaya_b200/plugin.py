@@ -214,11 +214,16 @@ class MCMC(CovmatSampler):
         self._x0 = np.empty((n_local, D))
         self._logpost0 = np.empty(n_local)
         self.log.info("Getting %d initial points...", n_local)
-        for c in range(n_local if self._resume_snapshot is None else 0):
-            x, res = self.model.get_valid_point(max_tries=max_tries_init * 100,
-                                                random_state=self._rng)
-            self._x0[c] = x
-            self._logpost0[c] = res.logpost
+        if self._resume_snapshot is None:
+            if n_local <= self._START_POINTS_ONE_BY_ONE:
+                for c in range(n_local):  # exactly the reference's call (mcmc.py:215-222)
+                    x, res = self.model.get_valid_point(max_tries=max_tries_init * 100,
+                                                        random_state=self._rng)
+                    self._x0[c] = x
+                    self._logpost0[c] = res.logpost
+            else:
+                self._x0[:] = self._start_points_batch(n_local, max_tries_init * 100)
+                self._logpost0[:] = np.nan  # evaluated on the device by cb2_set_state
         if self._resume_snapshot is not None:
             self._x0[:] = np.nan  # replaced by the snapshot's current points in run()
         if self.measure_speeds and not self.blocking:
@@ -236,15 +241,62 @@ class MCMC(CovmatSampler):
         if not resuming:
             self.write_checkpoint()
 
+    # up to this many chains per process the start points come from the reference's own
+    # Model.get_valid_point, one call per chain; above, from the vectorised restatement
+    _START_POINTS_ONE_BY_ONE = 64
+
+    def _start_points_batch(self, n, max_tries):
+        """``n`` independent start points, each drawn like ``Prior.reference`` +
+        ``Model.get_valid_point`` draw one (prior.py:866-961, model.py:707-754) -- from the
+        ``ref`` pdf (or the fixed ``ref`` value, or the prior where no ``ref`` is given),
+        redrawn until the prior density is non-null -- but vectorised over the chains: one
+        ``rvs(size=n)`` per parameter instead of n x D scalar calls (the reference takes
+        ~2.5 ms per point at D = 64: 20 s for 8192 chains).  For the models the engine
+        accepts (lowering.py) the likelihood is finite wherever the prior is, so "valid
+        point" reduces to the prior's support; ``cb2_set_state`` then evaluates the
+        posterior of every point on the device and refuses non-finite ones."""
+        import numbers
+
+        prior, rng = self.model.prior, self._rng
+        D = prior.d()
+        lower = np.asarray(prior._lower_limits, dtype=np.float64)
+        upper = np.asarray(prior._upper_limits, dtype=np.float64)
+        from_prior = [i for i, r in enumerate(prior.ref_pdf)
+                      if isinstance(r, numbers.Real) and np.isnan(r)]
+        if from_prior:
+            self.log.info("Reference values or pdfs for some parameters were not provided. "
+                          "Sampling from the prior instead for those parameters.")
+        out = np.empty((n, D))
+        todo = np.arange(n)
+        for _ in range(int(max_tries)):
+            m = len(todo)
+            X = np.empty((m, D))
+            for i, ref in enumerate(prior.ref_pdf):
+                if hasattr(ref, "rvs"):
+                    X[:, i] = ref.rvs(size=m, random_state=rng)
+                elif i not in from_prior:
+                    X[:, i] = ref
+            if from_prior:
+                ps = prior.sample(n=m, ignore_external=True, random_state=rng)
+                X[:, from_prior] = ps[:, from_prior]
+            ok = np.all(np.isfinite(X), axis=1) & np.all(X >= lower, axis=1) & \
+                np.all(X <= upper, axis=1)
+            out[todo[ok]] = X[ok]
+            todo = todo[~ok]
+            if not len(todo):
+                return out
+        raise LoggedError(
+            self.log, "Could not sample from the reference pdf a point with non-null prior "
+                      "density after %d tries. Maybe your prior is improper of your reference "
+                      "pdf is null-defined in the domain of the prior.", max_tries)
+
     @staticmethod
     def _torch_world():
-        try:
-            import torch.distributed as tdist
-
-            if tdist.is_available() and tdist.is_initialized():
-                return tdist.get_world_size()
-        except ImportError:
-            pass
+        # a process group can only exist if torch.distributed has been imported already;
+        # importing torch here just to find out that there is none costs seconds
+        tdist = sys.modules.get("torch.distributed")
+        if tdist is not None and tdist.is_available() and tdist.is_initialized():
+            return tdist.get_world_size()
         return 1
 
     def snapshot_filename(self, rank=None):
@@ -433,7 +485,7 @@ class MCMC(CovmatSampler):
         if data.shape[1] != len(cols):
             raise LoggedError(self.log, "Engine row width %d does not match the collection's "
                                         "%d columns", data.shape[1], len(cols))
-        target._data = pd.DataFrame(data, columns=cols)
+        target._data = pd.DataFrame(data, columns=cols, copy=False)  # rows are ours: no copy
         target._cache_reset()
         return target
 
@@ -457,7 +509,7 @@ class MCMC(CovmatSampler):
             return
         self._row_cursor = self._row_cursor + counts
         self._segments.append(counts)
-        df = pd.DataFrame(rows, columns=list(self.collection.columns))
+        df = pd.DataFrame(rows, columns=list(self.collection.columns), copy=False)
         self.collection._cache_reset()
         self.collection._data = df if not len(self.collection._data) else pd.concat(
             [self.collection._data, df], ignore_index=True)

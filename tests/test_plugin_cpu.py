@@ -385,3 +385,38 @@ def test_reference_minimize_and_post_consume_the_engine_output(tmp_path):
     moved = np.array(col.mean()[:3]) - np.array(before.mean()[:3])
     # importance re-weighting moves the mean towards the new target
     assert np.dot(moved, shift) > 0.5 * np.dot(shift, shift)
+
+
+def test_vectorised_start_points_follow_ref_and_prior():
+    """More than 64 chains per process: the start points come from the vectorised
+    restatement of Prior.reference / Model.get_valid_point (prior.py:866-961,
+    model.py:707-754): ``ref`` pdf where given, fixed ``ref`` values kept, the prior where no
+    ``ref`` is given, every point inside the prior's support."""
+    enable_reference()
+    from cobaya.model import get_model
+    from cobaya.sampler import get_sampler
+
+    cov = np.diag([0.01, 0.04, 0.02, 0.01]) ** 2
+    info = {
+        "likelihood": {"gaussian_mixture": {"means": [np.zeros(4)], "covs": [cov],
+                                            "input_params": ["a", "b", "c", "d"],
+                                            "derived": False}},
+        "params": {
+            "a": {"prior": {"min": -1, "max": 1}, "ref": {"dist": "norm", "loc": 0.2, "scale": 0.01}},
+            "b": {"prior": {"min": 0, "max": 0.5}, "ref": 0.25},
+            "c": {"prior": {"min": -0.1, "max": 0.1}},                     # no ref: from the prior
+            "d": {"prior": {"dist": "norm", "loc": 0, "scale": 0.1},
+                  "ref": {"dist": "norm", "loc": 0, "scale": 3.0}}},
+        "sampler": {"cobaya_b200.plugin.MCMC": {"measure_speeds": False, "chains_per_gpu": 4000,
+                                                "seed": 2}},
+    }
+    model = get_model(info)
+    s = get_sampler(info["sampler"], model)
+    x = s._x0
+    assert x.shape == (4000, 4) and np.all(np.isfinite(x))
+    assert abs(x[:, 0].mean() - 0.2) < 1e-3 and abs(x[:, 0].std() - 0.01) < 1e-3
+    assert np.all(x[:, 1] == 0.25)
+    assert x[:, 2].min() >= -0.1 and x[:, 2].max() <= 0.1 and abs(x[:, 2].std() - 0.2 / 12 ** 0.5) < 4e-3
+    assert abs(x[:, 3].std() - 3.0) < 0.2
+    for row in x[:20]:
+        assert np.isfinite(model.logposterior(row).logpost)
