@@ -37,10 +37,11 @@ def run_cell(D, C, cycles, seed=1):
     x0 = rng.standard_normal((C, D)) @ L.T
     n = cycles * D
     warm = n  # same call shape as the timed one: every window buffer is sized before timing
-    cap = int(0.6 * (n + warm)) + 64
-    # keep the row store inside ~40 GB
-    if C * cap * (D + 6) * 8 > 40e9:
-        cap = int(40e9 / (C * (D + 6) * 8))
+    # every chain keeps every row it stores (the stored-row rate stays below 0.35): a cell
+    # whose chains ran out of room would have done less work than it claims
+    cap = int(0.45 * (n + warm)) + 64
+    if C * cap * (D + 6) * 8 > 120e9:
+        raise RuntimeError(f"row store of {C * cap * (D + 6) * 8 / 1e9:.0f} GB: lower --cycles")
     eng = Engine(fm, n_chains=C, seed=seed, rows_cap=cap)
     eng.set_state(x0)
     eng.advance(warm)
@@ -58,7 +59,8 @@ def run_cell(D, C, cycles, seed=1):
            "stored_row_rate": st_rate,
            "hbm_frac": bytes_pp * rate / (hbm * 1e9),
            "fp64_frac": 4.0 * D * D * rate / (fp64 * 1e12),
-           "n_stuck": s["n_stuck"], "n_rows_full": s["n_rows_full"]}
+           "n_stuck": s["n_stuck"], "n_rows_full": s["n_rows_full"],
+           "windows_by_step_kernel": eng.window_counts(), "engine_note": eng.debug_message()}
     eng.close()
     return out
 
@@ -74,6 +76,8 @@ def main():
         cells = [(D, C) for D in (8, 32, 64, 128, 512) for C in (1024, 8192, 65536)]
     for D, C in cells:
         cyc = a.cycles if D < 512 else max(1, a.cycles // 2)
+        if D >= 512 and C > 8192:
+            cyc = 1  # bases, delta^ and w^ of 64k chains at D = 512 do not fit: general kernel
         try:
             print(json.dumps(run_cell(D, C, cyc)), flush=True)
         except Exception as e:  # report the cell, go on with the grid
