@@ -356,7 +356,8 @@ class Engine:
         v = np.zeros(8, np.int64)
         self._ck(self.lib.cb2_window_counts(self.h, _cabi.ptr(v), int(reset)))
         names = ["general", "dmma", "dmma-producer-consumer", "dmma-streamed",
-                 "pc_launch_refused", "streamed_did_not_fit", "of_pc_split_products"]
+                 "pc_launch_refused", "streamed_did_not_fit", "of_pc_split_products",
+                 "chunked_over_chains"]
         return {k: int(x) for k, x in zip(names, v)}
 
     def debug_message(self):

@@ -233,8 +233,9 @@ const char *cb2_debug_message(const cb2_engine *h); /* why a faster kernel was n
  * cb2_last_step_kernel; out[4] = windows whose producer/consumer launch was refused (ran on
  * the next DMMA kernel), out[5] = windows whose streamed buffers did not fit in device
  * memory (ran on the general kernel), out[6] = of out[2], the windows on the variant with
- * the products split over the SM sub-partitions (k_step_pc2), out[7] reserved.  Nothing
- * changes kernels silently. */
+ * the products split over the SM sub-partitions (k_step_pc2), out[7] = windows that were run
+ * chunk by chunk over the chains because the per-window buffers of all chains did not fit in
+ * device memory (out[0..6] then count one per chunk).  Nothing changes kernels silently. */
 int cb2_window_counts(cb2_engine *h, int64_t out[8], int32_t reset);
 /* kernel experiments: cycle counters of one producer and one consumer warp of k_step_pc2 in
  * libraries built with -DCB2_PC2_TIMING (zeros otherwise) */

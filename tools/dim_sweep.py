@@ -37,6 +37,8 @@ def run_cell(D, C, cycles, seed=1):
     x0 = rng.standard_normal((C, D)) @ L.T
     n = cycles * D
     warm = n  # same call shape as the timed one: every window buffer is sized before timing
+    if D >= 512 and C > 8192:
+        warm = 64  # 64k chains at D = 512: windows are chunked over the chains; keep the rows small
     # every chain keeps every row it stores (the stored-row rate stays below 0.35): a cell
     # whose chains ran out of room would have done less work than it claims
     cap = int(0.45 * (n + warm)) + 64
@@ -77,7 +79,7 @@ def main():
     for D, C in cells:
         cyc = a.cycles if D < 512 else max(1, a.cycles // 2)
         if D >= 512 and C > 8192:
-            cyc = 1  # bases, delta^ and w^ of 64k chains at D = 512 do not fit: general kernel
+            cyc = 1  # 137 GB of bases for 64k chains: cb2_advance chunks the window over the chains
         try:
             print(json.dumps(run_cell(D, C, cyc)), flush=True)
         except Exception as e:  # report the cell, go on with the grid
