@@ -19,10 +19,18 @@ static void pack_frag(std::vector<double> &out, size_t off, const std::vector<do
 
 static int pack_fast(cb2_engine *h) {
     h->fast_ready = false;
-    if (!fast_step_supported(h->M, h->likes.size())) return 0;
+    h->drag_ready = false;
+    h->fastG_ready = false;
+    // one likelihood over all D <= 64 parameters: a Gaussian mixture (<= 4 modes, no derived
+    // parameters) for the Metropolis and dragging kernels, or the built-in Rosenbrock over
+    // the parameters in sampler order for the dragging kernel (kernels_drag.cuh)
+    if (h->D > 64 || h->likes.size() != 1) return 0;
+    const bool gauss = fast_step_supported_like(h->M);
+    const bool rosen = h->likes[0].d.kind == 1 && h->drag && h->likes[0].d.dim == h->D;
+    if (!gauss && !rosen) return 0;
     const int D = h->D, NT = (D + 7) / 8, DP = 8 * NT;
     const LikeHost &L = h->likes[0];
-    const int nm = L.d.n_modes;
+    const int nm = gauss ? L.d.n_modes : 0;
     std::vector<int> j_of_i(D), ilike_of_i(D, -1);
     for (int j = 0; j < D; ++j) j_of_i[h->i_of_j[j]] = j;
     for (int a = 0; a < D; ++a) {
@@ -32,6 +40,7 @@ static int pack_fast(cb2_engine *h) {
     bool tri = true;
     for (int j = 0; j < D; ++j)
         if (ilike_of_i[h->i_of_j[j]] != j) tri = false;
+    if (rosen && !tri) return 0;  // Rosenbrock couples neighbours: sorted order = input order
     FastPackDesc P;
     memset(&P, 0, sizeof(P));
     P.NT = NT;
@@ -121,11 +130,13 @@ static int pack_fast(cb2_engine *h) {
     }
     int rc = upload(h, h->d_fastpack, pk);
     if (rc) return rc;
+    h->drag_extra.like_kind = rosen ? 1 : 0;
+    h->drag_extra.like_dim = L.d.dim;
+    h->drag_extra.like_scale = L.d.scale;
     // G = (L^-1 P) T for k_step_pc2 (one mode, triangular likelihood matrix): the image of a
     // direction in whitened coordinates without going through delta.  Lower triangular as
     // the product of two lower-triangular matrices; accumulated in extended precision.
-    h->fastG_ready = false;
-    if (tri && nm == 1) {
+    if (tri && nm == 1 && !h->drag) {
         std::vector<double> Am((size_t)DP * DP, 0.0), Tm((size_t)DP * DP, 0.0),
             Gm((size_t)DP * DP, 0.0);
         for (int a = 0; a < D; ++a)
@@ -146,7 +157,8 @@ static int pack_fast(cb2_engine *h) {
         h->fastG_ready = true;
     }
     h->fast_desc = P;
-    h->fast_ready = true;
+    h->fast_ready = gauss && !h->drag;
+    h->drag_ready = drag_step_supported(h->M, NT);
     return 0;
 }
 

@@ -793,12 +793,16 @@ struct FastPackDesc {
     int total;     // doubles
 };
 
-static inline bool fast_step_supported(const ModelDev &M, size_t n_likes) {
-    if (M.drag || M.D > 64 || n_likes != 1) return false;
+// the one likelihood is a Gaussian mixture the register-resident kernels can evaluate
+static inline bool fast_step_supported_like(const ModelDev &M) {
     const LikeDev &L = M.likes[0];
     if (L.kind != 0 || L.dim != M.D || L.derived) return false;
     if (L.n_modes > 4) return false;
     return true;
+}
+static inline bool fast_step_supported(const ModelDev &M, size_t n_likes) {
+    if (M.drag || M.D > 64 || n_likes != 1) return false;
+    return fast_step_supported_like(M);
 }
 
 

@@ -100,6 +100,8 @@ def test_chain_matches_reference_golden(cuda_lib, name, cid):
             eng.advance(step)
             done += step
     st = eng.get_state()
+    if name == "g3_dragging":
+        assert eng.last_step_kernel() == 1  # k_step_drag, not the general kernel
     ref = g[f"rows_{cid}"]
     rows = eng.rows(0)
     assert st["flags"][0] == 0
@@ -355,6 +357,8 @@ def test_config4_30d_rosenbrock_dragging(cuda_lib):
     eng.set_state(x0)
     for k in (7, 13, 100):
         eng.advance(k)
+    # dragging with the chain state in registers (k_step_drag, Rosenbrock in fragment layout)
+    assert eng.last_step_kernel() == 1
     st = eng.get_state()
     assert not st["flags"].any()
     ref = _oracle_rows(fm, 12, range(40, 40 + C), x0, n, 0)
@@ -705,3 +709,49 @@ def test_windows_chunked_over_chains_are_bit_identical(cuda_lib, case, monkeypat
         np.testing.assert_array_equal(sa[k], sb[k], err_msg=k)
     np.testing.assert_array_equal(ca, cb)
     np.testing.assert_array_equal(ra, rb)
+
+
+@pytest.mark.parametrize("policy", [0, 1])
+def test_dragging_mixture_blocks_priors_match_oracle(cuda_lib, policy):
+    """get_new_sample_dragging (mcmc.py:564-668) on k_step_drag (policy 0) and on the general
+    kernel (policy 1) against the oracle: 2-mode mixture over permuted parameters, two slow and
+    two fast blocks (cycler tapes on both sides, a 1-parameter block), a normal and a
+    scipy-family prior, a bound that early-rejects some slow proposals, burn-in, thinning off,
+    temperature, advance calls that cut windows inside cycles."""
+    from cobaya_b200.flatmodel import FlatModel, LikeSpec
+
+    rng = np.random.default_rng(21)
+    D = 14
+    covs = [_mixture_cov(D, rng, scale=0.05) for _ in range(2)]
+    means = [rng.uniform(-0.05, 0.05, D), rng.uniform(-0.05, 0.05, D) + 0.08]
+    lk = LikeSpec.gaussian_mixture(rng.permutation(D), means, covs, weights=[0.7, 0.3])
+    kind = np.zeros(D, np.int32); kind[2] = 1
+    lower = np.full(D, -1.0); upper = np.full(D, 1.0)
+    lower[2], upper[2] = -np.inf, np.inf
+    lower[0], upper[0] = -0.12, 0.12          # tight: some slow proposals leave the prior
+    sc = np.ones(D); sc[2] = 0.3
+    blocks = [[0, 5, 9], [3], [1, 2, 4, 6], [7, 8, 10, 11, 12, 13]]
+    fm = FlatModel(names=[f"p{i}" for i in range(D)], prior_kind=kind, lower=lower, upper=upper,
+                   loc=np.zeros(D), pscale=sc, periodic=np.zeros(D, np.int32), likes=[lk],
+                   blocks=blocks, oversampling=[1, 1, 3, 3], drag=True, i_last_slow_block=1,
+                   drag_interp_steps=5, proposal_cov=np.diag(np.full(D, 0.05 ** 2)),
+                   temperature=1.5)
+    C, n = 19, 260
+    x0 = rng.uniform(-0.04, 0.04, (C, D))
+    eng = _engine(fm, C, seed=33, chain_id0=70, rows_cap=n, burn_in=2)
+    eng.set_kernel_policy(policy)
+    eng.set_state(x0)
+    for k in (3, 50, 207):
+        eng.advance(k)
+    assert eng.last_step_kernel() == (1 if policy == 0 else 0)
+    st = eng.get_state()
+    assert not st["flags"].any()
+    ref = _oracle_rows(fm, 33, range(70, 70 + C), x0, n, 2)
+    for c in range(C):
+        rc, rows_ref, s_ref = ref[c]
+        rows = eng.rows(c)
+        assert rows.shape == rows_ref.shape, f"chain {c}"
+        np.testing.assert_array_equal(rows[:, 0], rows_ref[:, 0])
+        np.testing.assert_allclose(rows, rows_ref, rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(st["x"][c], s_ref["x"], rtol=RTOL, atol=ATOL)
+        assert st["weight"][c] == s_ref["weight"]
