@@ -29,6 +29,7 @@ EXPORTS = [
     "cb2_set_kernel_policy", "cb2_set_profiling", "cb2_kernel_times", "cb2_debug_message",
     "cb2_copy_rows_bulk", "cb2_drain_start", "cb2_drain_wait", "cb2_drain_reset",
     "cb2_host_alloc", "cb2_host_free", "cb2_grow_rows", "cb2_mem_info", "cb2_load_rows_bulk", "cb2_window_counts", "cb2_debug_counters",
+    "cb2_checkpoint_device", "cb2_checkpoint_cov", "cb2_adopt_proposal", "cb2_get_proposal",
 ]
 
 
@@ -85,6 +86,10 @@ def load():
     L.cb2_summary.argtypes = [vp, vp]
     L.cb2_moments.argtypes = [vp, i32, i32, vp, vp, vp]
     L.cb2_bounds.argtypes = [vp, i32, i32, dbl, vp, vp, vp]
+    L.cb2_checkpoint_device.argtypes = [vp, vp, vp]
+    L.cb2_checkpoint_cov.argtypes = [vp, vp]
+    L.cb2_adopt_proposal.argtypes = [vp]
+    L.cb2_get_proposal.argtypes = [vp, vp]
     L.cb2_copy_rows.restype = i64
     L.cb2_copy_rows.argtypes = [vp, i64, i64, i64, vp]
     L.cb2_copy_rows_bulk.restype = i64

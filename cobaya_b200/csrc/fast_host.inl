@@ -135,7 +135,7 @@ static int pack_fast(cb2_engine *h) {
     h->drag_extra.like_scale = L.d.scale;
     // G = (L^-1 P) T for k_step_pc2 (one mode, triangular likelihood matrix): the image of a
     // direction in whitened coordinates without going through delta.  Lower triangular as
-    // the product of two lower-triangular matrices; accumulated in extended precision.
+    // the product of two lower-triangular matrices.
     if (tri && nm == 1 && !h->drag) {
         std::vector<double> Am((size_t)DP * DP, 0.0), Tm((size_t)DP * DP, 0.0),
             Gm((size_t)DP * DP, 0.0);
@@ -146,10 +146,12 @@ static int pack_fast(cb2_engine *h) {
             for (int k = 0; k <= j; ++k) Tm[(size_t)j * DP + k] = h->Trow[(size_t)j * D + k];
         for (int a = 0; a < D; ++a)
             for (int k = 0; k <= a; ++k) {
-                long double acc = 0.0L;
+                // one fused multiply-add chain in j order: k_ckpt_pack (kernels_ckpt.cuh)
+                // forms the same matrix on the device, bit for bit
+                double acc = 0.0;
                 for (int j = k; j <= a; ++j)
-                    acc += (long double)Am[(size_t)a * DP + j] * (long double)Tm[(size_t)j * DP + k];
-                Gm[(size_t)a * DP + k] = (double)acc;
+                    acc = std::fma(Am[(size_t)a * DP + j], Tm[(size_t)j * DP + k], acc);
+                Gm[(size_t)a * DP + k] = acc;
             }
         std::vector<double> gk((size_t)blocks_T * 64, 0.0);
         pack_frag(gk, 0, Gm, DP, NT, true);

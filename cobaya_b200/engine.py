@@ -173,6 +173,36 @@ class Engine:
                                       _cabi.ptr(out)))
         return out
 
+    # ---- device checkpoint (D <= 64): R-1, W and the new transform without host LAPACK
+    def checkpoint_device(self, dev_ptr=None):
+        """cb2_checkpoint_device on the sums of the last ``moments`` call (``dev_ptr``: the
+        all-reduced buffer).  Returns the dict of ``convergence.rminus1_from_sums`` without
+        W (``checkpoint_cov`` fetches it when somebody needs it on the host)."""
+        out = np.empty(8 + self.D)
+        self._ck(self.lib.cb2_checkpoint_device(
+            self.h, C.c_void_p(dev_ptr) if dev_ptr else None, _cabi.ptr(out)))
+        ok = bool(out[5] > 0.5) and bool(np.isfinite(out[3]))
+        return dict(M=int(round(out[0])), N=int(round(out[1])), acceptance=float(out[2]),
+                    Rminus1=float(out[3]) if ok else None, success=ok,
+                    proposal_ok=bool(out[4] > 0.5), sweeps=int(out[6]), mean=out[8:].copy())
+
+    def checkpoint_cov(self):
+        W = np.empty((self.D, self.D))
+        self._ck(self.lib.cb2_checkpoint_cov(self.h, _cabi.ptr(W)))
+        return W
+
+    def adopt_proposal(self, cov=None):
+        """The candidate transform of the last ``checkpoint_device`` becomes the proposal
+        (device-side repack); the host model follows with the transform read back."""
+        self._ck(self.lib.cb2_adopt_proposal(self.h))
+        self.fm.T = self.get_proposal()
+        self.fm.proposal_cov = self.checkpoint_cov() if cov is None else cov
+
+    def get_proposal(self):
+        T = np.empty((self.D, self.D))
+        self._ck(self.lib.cb2_get_proposal(self.h, _cabi.ptr(T)))
+        return T
+
     def bounds(self, limfrac, mode=MOMENTS_HALVES, split=4, shift=None, dev_ptr=None,
                host=True):
         """Sums of the per-chain confidence bounds (mcmc.py:918-1002): [1 + 4D]."""

@@ -32,7 +32,7 @@ import numpy as np
 
 from .convergence import rminus1_cl_from_sums, rminus1_from_sums
 from .engine import (FLAG_INTERNAL, FLAG_ROWS_FULL, FLAG_STUCK, MOMENTS_HALVES,
-                     MOMENTS_SINGLE_SPLIT, Engine)
+                     MOMENTS_SINGLE_SPLIT, Engine, EngineError)
 from .flatmodel import FlatModel
 
 log = logging.getLogger("mcmc")
@@ -63,6 +63,7 @@ ENGINE_DEFAULTS = {
     "device": None,               # CUDA device index (default: LOCAL_RANK or 0)
     "rows_per_chain": None,       # sample capacity per chain (default: from max_samples)
     "launch_cycles": None,        # proposal cycles per kernel launch group
+    "device_checkpoint": None,    # R-1 / covariance learning on the device (None: when D <= 64)
 }
 
 
@@ -470,6 +471,31 @@ class EnsembleMCMC:
         local = eng.moments(mode=mode, split=split, shift=self._shift)
         return np.asarray(d.all_reduce_sum(local))
 
+    def _use_device_checkpoint(self):
+        opt = self.opts.get("device_checkpoint")
+        able = (self.n_chains > 1 and self.fm.D <= 64 and
+                hasattr(self.engine, "checkpoint_device") and
+                (isinstance(self.dist, _NoDist) or getattr(self.dist, "backend", "") == "nccl"))
+        if opt and not able:
+            raise SamplerError("device_checkpoint needs D <= 64, more than one chain and the "
+                               "CUDA engine (single process or NCCL).")
+        return able if opt is None else bool(opt)
+
+    def _checkpoint_device(self):
+        """Sums -> (NCCL all-reduce) -> cb2_checkpoint_device; nothing D x D leaves the GPU."""
+        eng, d = self.engine, self.dist
+        if isinstance(d, TorchDist):
+            if self._mom_buf is None:
+                self._mom_buf = d.buffer(eng.moments_len)
+            eng.moments(mode=MOMENTS_HALVES, split=0, shift=self._shift,
+                        dev_ptr=self._mom_buf.data_ptr(), host=False)
+            eng.sync()
+            d.all_reduce_tensor_(self._mom_buf)
+            d.torch.cuda.current_stream().synchronize()
+            return eng.checkpoint_device(dev_ptr=self._mom_buf.data_ptr())
+        eng.moments(mode=MOMENTS_HALVES, split=0, shift=self._shift, host=False)
+        return eng.checkpoint_device()
+
     def _bounds(self, mode, split, limfrac):
         """Per-chain confidence bounds -> all-reduced sums (mcmc.py:918-939)."""
         eng, d = self.engine, self.dist
@@ -489,15 +515,20 @@ class EnsembleMCMC:
     def check_convergence_and_learn_proposal(self):
         """mcmc.py:773-1032 on all-reduced sums; identical result on every rank."""
         o = self.opts
-        if self.n_chains > 1:
-            sums = self._moments(MOMENTS_HALVES, 0)
+        on_device = self._use_device_checkpoint()
+        if on_device:
+            # D x D algebra and the new transform on the GPU (cb2_checkpoint_device)
+            res = self._checkpoint_device()
         else:
-            try:
-                sums = self._moments(MOMENTS_SINGLE_SPLIT, int(o["Rminus1_single_split"]))
-            except Exception as e:  # mcmc.py:816-821
-                log.info("Not enough points in chain to check convergence. (%s)", e)
-                return
-        res = rminus1_from_sums(sums, self.fm.D, self._shift)
+            if self.n_chains > 1:
+                sums = self._moments(MOMENTS_HALVES, 0)
+            else:
+                try:
+                    sums = self._moments(MOMENTS_SINGLE_SPLIT, int(o["Rminus1_single_split"]))
+                except Exception as e:  # mcmc.py:816-821
+                    log.info("Not enough points in chain to check convergence. (%s)", e)
+                    return
+            res = rminus1_from_sums(sums, self.fm.D, self._shift)
         cp = Checkpoint(N=res["N"], timestamp=datetime.datetime.now().isoformat(),
                         acceptance_rate=float(res["acceptance"]), Rminus1=res["Rminus1"])
         self.progress.append(cp)
@@ -517,6 +548,8 @@ class EnsembleMCMC:
                 mode = MOMENTS_HALVES if self.n_chains > 1 else MOMENTS_SINGLE_SPLIT
                 bsums = self._bounds(mode, int(o["Rminus1_single_split"]),
                                      float(o["Rminus1_cl_level"]) / 2.0)
+                if "W" not in res:
+                    res["W"] = self.engine.checkpoint_cov()
                 Rminus1_cl = rminus1_cl_from_sums(bsums, self.fm.D, res["W"])
             except Exception as e:  # mcmc.py:936-938,999-1002
                 log.info("Computation of the bounds was not possible (%s). "
@@ -536,7 +569,16 @@ class EnsembleMCMC:
             log.info(msg)
         if learn:
             try:
-                self.engine.set_covariance(res["W"])  # is already tempered (mcmc.py:1023)
+                if on_device and res["proposal_ok"]:
+                    try:
+                        self.engine.adopt_proposal(res.get("W"))  # repacked on the device
+                    except EngineError:
+                        # constant blocks that only the host packer builds
+                        self.engine.set_covariance(self.engine.checkpoint_cov())
+                else:
+                    if "W" not in res:
+                        res["W"] = self.engine.checkpoint_cov()
+                    self.engine.set_covariance(res["W"])  # is already tempered (mcmc.py:1023)
                 cp.learned = True
             except Exception as e:
                 log.debug("Updating covariance matrix failed unexpectedly (%s); "

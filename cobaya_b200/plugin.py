@@ -157,6 +157,7 @@ class MCMC(CovmatSampler):
     device: int | None = None
     rows_per_chain: int | None = None
     launch_cycles: int | None = None
+    device_checkpoint: bool | None = None
 
     # dependency injection for the CPU tests of the host logic (tests/oracle_engine.py);
     # None = the CUDA engine.  Never set by the product.
@@ -385,7 +386,7 @@ class MCMC(CovmatSampler):
                 "learn_proposal_Rminus1_max_early", "learn_proposal_Rminus1_min",
                 "max_samples", "Rminus1_stop", "Rminus1_cl_stop", "Rminus1_cl_level",
                 "Rminus1_single_split", "callback_every", "chains_per_gpu", "device",
-                "rows_per_chain", "launch_cycles"]
+                "rows_per_chain", "launch_cycles", "device_checkpoint"]
         o = {k: getattr(self, k) for k in keys}
         seed = self.seed
         # one Philox key for the whole run (chains are told apart by their global id); an

@@ -163,6 +163,28 @@ int cb2_summary(cb2_engine *h, int64_t out[8]);
 int cb2_moments(cb2_engine *h, int32_t mode, int32_t split, const double *shift,
                 double *dev_out, double *host_out);
 
+/* The D x D part of the checkpoint on the device (D <= 64), replacing the root-only block of
+ * check_convergence_and_learn_proposal (mcmc.py:856-889: numpy cholesky, scipy dtrtri, numpy
+ * eigvalsh) and BlockedProposer.set_covariance (proposal.py:226-260, tools.py:761-788):
+ * from the all-reduced sums of cb2_moments at DEVICE pointer `dev_sums` (NULL = the engine's
+ * own buffer of the last cb2_moments call; the shift is that call's) one kernel forms W, B,
+ * R-1 = max eig(L^-1 (B/dd^T) L^-T) (parallel-order Jacobi) and the candidate transform
+ * T = S chol(corr(W)) in block-sorted coordinates, all kept on the device.
+ * out_host[8 + D] = { M, sum N_c, acceptance, R-1 (NaN: Cholesky of W/dd^T failed,
+ * mcmc.py:872-887), candidate valid (1/0), chol ok (1/0), Jacobi sweeps, 0, mean[D] }.
+ * Returns -4 for D > 64 (use cb2_moments + host algebra + cb2_set_proposal). */
+int cb2_checkpoint_device(cb2_engine *h, const double *dev_sums, double *out_host);
+/* W (mean of the chains' covariances, sampler order, row-major D x D) of that call -> host */
+int cb2_checkpoint_cov(cb2_engine *h, double *W_out);
+/* mcmc.py:1023 `self.proposer.set_covariance(...)` without the host: the candidate transform
+ * of the last cb2_checkpoint_device becomes the proposal; the step kernels' constant blocks
+ * (fragment-ordered T, G = L^-1 P T, column-major T) are rewritten by a device kernel.
+ * -4 when the model's constant blocks need the host packer (streamed path, several
+ * components): fall back to cb2_set_proposal. */
+int cb2_adopt_proposal(cb2_engine *h);
+/* the proposal transform in use (row-major D x D, block-sorted coordinates) */
+int cb2_get_proposal(cb2_engine *h, double *T_out);
+
 /* R-1 of the confidence-interval bounds (mcmc.py:918-1002): per (virtual) chain the raw
  * weighted sample quantiles at limfrac and 1-limfrac of every sampled parameter (GetDist
  * `MCSamples.confidence`, mcmc.py:926-929 with limfrac = Rminus1_cl_level/2), summed into
