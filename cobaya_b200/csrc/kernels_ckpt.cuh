@@ -10,12 +10,21 @@
 // (fragment-ordered T and G, column-major T) -- no host LAPACK, no re-upload.
 // Everything lives in shared memory (five 64 x 64 matrices); the eigenvalues come from a
 // two-sided Jacobi iteration with the round-robin parallel ordering (32 disjoint rotations
-// per step).  The symmetric matrix is positive semi-definite, so max |eig| = max eig.
+// per step, applied as 32 x 32 independent 2 x 2 blocks, one per thread).  The symmetric matrix is positive semi-definite, so max |eig| = max eig.
 #pragma once
 #include "kernels_fast.cuh"
 
 #define CB2_CK_MAXD 64
 #define CB2_CK_LD 65
+#define CB2_CK_THREADS 1024
+
+// index at position i of the round-robin order after `step` rotations (n2 even)
+__device__ __forceinline__ int rr_index(int i, int step, int n2) {
+    if (i == 0) return 0;
+    int v = (i - 1 - step) % (n2 - 1);
+    if (v < 0) v += n2 - 1;
+    return v + 1;
+}
 
 struct CkptOut {          // device -> host, 8 + D doubles
     double M, N, acceptance, Rminus1, proposal_ok, chol_ok, sweeps, pad;
@@ -53,7 +62,7 @@ __device__ __forceinline__ int ck_cholesky(double *A, int n, int tid, int nt, in
 // sums: {M, S1 = sum N_c, S2 = sum N_c a_c, Sm[D], Smm[D*D], SC[D*D]} (cb2_moments)
 // shift: the vector the means were shifted by; i_of_j: sorted index -> sampler index.
 // Tnew[D*D]: row-major T in sorted coordinates; Wout[D*D]: W in sampler order.
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(CB2_CK_THREADS, 1)
 k_ckpt_device(const double *__restrict__ sums, const double *__restrict__ shift,
               const int32_t *__restrict__ i_of_j, int D, double *__restrict__ Tnew,
               double *__restrict__ Wout, double *__restrict__ out) {
@@ -64,7 +73,7 @@ k_ckpt_device(const double *__restrict__ sums, const double *__restrict__ shift,
     double *Li = L + CB2_CK_MAXD * CB2_CK_LD;    // L^-1, later scratch
     double *X = Li + CB2_CK_MAXD * CB2_CK_LD;    // products
     __shared__ double dvec[CB2_CK_MAXD], cvec[32], svec[32];
-    __shared__ int pp[32], qq[32], order[CB2_CK_MAXD], fail, fail2;
+    __shared__ int fail, fail2;
     __shared__ double offnorm, diagnorm;
     const int tid = threadIdx.x, nt = blockDim.x;
     const int DD = D * D;
@@ -130,9 +139,8 @@ k_ckpt_device(const double *__restrict__ sums, const double *__restrict__ shift,
         B[(n2 - 1) * CB2_CK_LD + tid] = 0.0;
         B[tid * CB2_CK_LD + n2 - 1] = 0.0;
     }
-    for (int i = tid; i < n2; i += nt) order[i] = i;
     __syncthreads();
-    int sweeps = 0;
+    int sweeps = 0, rr = 0;
     for (int sw = 0; sw < 30; ++sw) {
         // convergence: off-diagonal norm against the diagonal
         if (tid == 0) { offnorm = 0.0; diagnorm = 0.0; }
@@ -150,11 +158,12 @@ k_ckpt_device(const double *__restrict__ sums, const double *__restrict__ shift,
         __syncthreads();
         if (offnorm <= 1e-26 * diagnorm || !(diagnorm > 0.0)) break;
         sweeps = sw + 1;
-        for (int step = 0; step < n2 - 1; ++step) {
+        for (int step = 0; step < n2 - 1; ++step, ++rr) {
+            // pair k of this step: positions k and n2-1-k of the round-robin order
+            // order[0] = 0, order[i] = ((i - 1 - step) mod (n2 - 1)) + 1
             if (tid < half) {
-                int p = order[tid], q = order[n2 - 1 - tid];
+                int p = rr_index(tid, rr, n2), q = rr_index(n2 - 1 - tid, rr, n2);
                 if (p > q) { const int t_ = p; p = q; q = t_; }
-                pp[tid] = p; qq[tid] = q;
                 const double apq = B[p * CB2_CK_LD + q];
                 double c = 1.0, s = 0.0;
                 if (apq != 0.0) {
@@ -166,31 +175,24 @@ k_ckpt_device(const double *__restrict__ sums, const double *__restrict__ shift,
                 cvec[tid] = c; svec[tid] = s;
             }
             __syncthreads();
-            // columns: A <- A J
-            for (int e = tid; e < n2 * half; e += nt) {
-                const int i = e / half, k = e % half;
-                const int p = pp[k], q = qq[k];
-                const double c = cvec[k], s = svec[k];
-                const double aip = B[i * CB2_CK_LD + p], aiq = B[i * CB2_CK_LD + q];
-                B[i * CB2_CK_LD + p] = c * aip - s * aiq;
-                B[i * CB2_CK_LD + q] = s * aip + c * aiq;
-            }
-            __syncthreads();
-            // rows: A <- J^T A
-            for (int e = tid; e < n2 * half; e += nt) {
-                const int j = e / half, k = e % half;
-                const int p = pp[k], q = qq[k];
-                const double c = cvec[k], s = svec[k];
-                const double apj = B[p * CB2_CK_LD + j], aqj = B[q * CB2_CK_LD + j];
-                B[p * CB2_CK_LD + j] = c * apj - s * aqj;
-                B[q * CB2_CK_LD + j] = s * apj + c * aqj;
-            }
-            __syncthreads();
-            // next round: element 0 stays, the others rotate
-            if (tid == 0) {
-                const int last = order[n2 - 1];
-                for (int i = n2 - 1; i > 1; --i) order[i] = order[i - 1];
-                order[1] = last;
+            // A <- J^T A J one 2 x 2 block (pair k rows, pair l columns) per thread: every
+            // block is read and written by its own thread only
+            for (int e = tid; e < half * half; e += nt) {
+                const int k = e / half, l = e % half;
+                int pk = rr_index(k, rr, n2), qk = rr_index(n2 - 1 - k, rr, n2);
+                if (pk > qk) { const int t_ = pk; pk = qk; qk = t_; }
+                int pl = rr_index(l, rr, n2), ql = rr_index(n2 - 1 - l, rr, n2);
+                if (pl > ql) { const int t_ = pl; pl = ql; ql = t_; }
+                const double ck = cvec[k], sk = svec[k], cl = cvec[l], sl = svec[l];
+                const double a00 = B[pk * CB2_CK_LD + pl], a01 = B[pk * CB2_CK_LD + ql];
+                const double a10 = B[qk * CB2_CK_LD + pl], a11 = B[qk * CB2_CK_LD + ql];
+                // columns (pair l), then rows (pair k)
+                const double b00 = cl * a00 - sl * a01, b01 = sl * a00 + cl * a01;
+                const double b10 = cl * a10 - sl * a11, b11 = sl * a10 + cl * a11;
+                B[pk * CB2_CK_LD + pl] = ck * b00 - sk * b10;
+                B[pk * CB2_CK_LD + ql] = ck * b01 - sk * b11;
+                B[qk * CB2_CK_LD + pl] = sk * b00 + ck * b10;
+                B[qk * CB2_CK_LD + ql] = sk * b01 + ck * b11;
             }
             __syncthreads();
         }

@@ -151,6 +151,8 @@ def test_driver_takes_the_device_route_and_agrees_with_the_host_route():
         x0 = p.start(1024, 0)
         ens = EnsembleMCMC(p.fm, x0, {"seed": 5, "max_samples": 400, "learn_proposal": True,
                                       "Rminus1_stop": 0.0, "device_checkpoint": route,
+                                      "learn_proposal_Rminus1_max": 1e3,
+                                      "learn_proposal_Rminus1_min": 0.0,
                                       "learn_every": "4d"})
         assert ens._use_device_checkpoint() is route
         ens.run()

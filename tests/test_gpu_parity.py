@@ -101,7 +101,9 @@ def test_chain_matches_reference_golden(cuda_lib, name, cid):
             done += step
     st = eng.get_state()
     if name == "g3_dragging":
-        assert eng.last_step_kernel() == 1  # k_step_drag, not the general kernel
+        # one parameter of this case is periodic: k_step_drag refuses, the general kernel runs
+        # (k_step_drag is checked by the dragging tests against the oracle below)
+        assert eng.last_step_kernel() == 0
     ref = g[f"rows_{cid}"]
     rows = eng.rows(0)
     assert st["flags"][0] == 0
