@@ -494,7 +494,9 @@ def run_gpu_arm(args):
                    "l2": "inputs larger than L2: every window streams its Haar bases, their "
                          "normals and the new sample rows (> 1 GB at 8192 chains) through "
                          "the 126 MB L2; no explicit flush",
-                   "step_kernel": KERNEL_NAMES.get(eng.last_step_kernel(), "?"),
+                   "step_kernel": ("dmma-dragging (k_step_drag)"
+                                   if fm.drag and eng.last_step_kernel() == 1
+                                   else KERNEL_NAMES.get(eng.last_step_kernel(), "?")),
                    "windows_by_step_kernel": windows,
                    "parallelism": f"chains sharded over {world} GPU(s), no data-path "
                                   "collective; NCCL all-reduce of moments per checkpoint"},

@@ -19,9 +19,10 @@
 #define CB2_CK_THREADS 1024
 
 // index at position i of the round-robin order after `step` rotations (n2 even)
+// (step already reduced modulo n2 - 1: no integer division in the sweep)
 __device__ __forceinline__ int rr_index(int i, int step, int n2) {
     if (i == 0) return 0;
-    int v = (i - 1 - step) % (n2 - 1);
+    int v = i - 1 - step;
     if (v < 0) v += n2 - 1;
     return v + 1;
 }
@@ -141,6 +142,7 @@ k_ckpt_device(const double *__restrict__ sums, const double *__restrict__ shift,
     }
     __syncthreads();
     int sweeps = 0, rr = 0;
+    const int blk_k = tid / half, blk_l = tid % half;
     for (int sw = 0; sw < 30; ++sw) {
         // convergence: off-diagonal norm against the diagonal
         if (tid == 0) { offnorm = 0.0; diagnorm = 0.0; }
@@ -158,7 +160,7 @@ k_ckpt_device(const double *__restrict__ sums, const double *__restrict__ shift,
         __syncthreads();
         if (offnorm <= 1e-26 * diagnorm || !(diagnorm > 0.0)) break;
         sweeps = sw + 1;
-        for (int step = 0; step < n2 - 1; ++step, ++rr) {
+        for (int step = 0; step < n2 - 1; ++step, rr = (rr + 1 == n2 - 1) ? 0 : rr + 1) {
             // pair k of this step: positions k and n2-1-k of the round-robin order
             // order[0] = 0, order[i] = ((i - 1 - step) mod (n2 - 1)) + 1
             if (tid < half) {
@@ -177,8 +179,8 @@ k_ckpt_device(const double *__restrict__ sums, const double *__restrict__ shift,
             __syncthreads();
             // A <- J^T A J one 2 x 2 block (pair k rows, pair l columns) per thread: every
             // block is read and written by its own thread only
-            for (int e = tid; e < half * half; e += nt) {
-                const int k = e / half, l = e % half;
+            if (tid < half * half) {  // half <= 32: one block per thread (k, l fixed)
+                const int k = blk_k, l = blk_l;
                 int pk = rr_index(k, rr, n2), qk = rr_index(n2 - 1 - k, rr, n2);
                 if (pk > qk) { const int t_ = pk; pk = qk; qk = t_; }
                 int pl = rr_index(l, rr, n2), ql = rr_index(n2 - 1 - l, rr, n2);

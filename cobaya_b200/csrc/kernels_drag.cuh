@@ -139,6 +139,65 @@ __device__ __forceinline__ DragEval<NT> drag_logpost(const ModelDev &M, const Fa
     return out;
 }
 
+// Issued one fast step ahead in the dragging loop: the loads of the direction are in flight
+// while the two posterior evaluations of the current step run.  `v` comes back RAW (unit
+// direction, or nothing for a 1-parameter block); drag_block_finish applies the radius.
+struct DragPending {
+    double f;     // radius x proposal_scale (signed for a 1-parameter block)
+    int jsel;     // sorted index of a 1-parameter block's coordinate, -1 for n >= 2
+    bool ok;
+};
+
+template <int NT>
+__device__ __forceinline__ DragPending drag_block_issue(const ModelDev &M, const WindowDev &W,
+                                                        int64_t chain, uint64_t gid, uint64_t t,
+                                                        uint32_t sub, int b, long long *vis_q,
+                                                        const long long *e0_q, bool adv, int lane,
+                                                        bool vec, double (&v)[NT][2]) {
+    const int r = lane & 3;
+    const int n = M.bsize[b];
+    double rad, sign;
+    DragPending out;
+    out.ok = true;
+    out.jsel = -1;
+    if (n >= 2) {
+        const long long vb = vis_q[b];
+        const long long e = vb / n;
+        const int k = (int)(vb % n);
+        long long slot = e - e0_q[b];
+        if (slot < 0 || slot >= W.cnt[b]) { out.ok = false; slot = 0; }
+        int2 pl;
+        pl.x = (int)((chain * W.cnt[b] + slot) * n + k);
+        pl.y = b;
+        fetch_direction<NT>(M, W, pl, r, vec, v);
+        draw_radial(M, gid, t, sub, n, rad, sign);
+        out.f = rad * M.proposal_scale;
+    } else {
+        draw_radial(M, gid, t, sub, n, rad, sign);
+        out.f = (sign > 0) ? rad * M.proposal_scale : -(rad * M.proposal_scale);
+        out.jsel = M.jstart[b];
+    }
+    __syncwarp();
+    if (adv && r == 0) vis_q[b] += 1;
+    __syncwarp();
+    return out;
+}
+
+template <int NT>
+__device__ __forceinline__ void drag_block_finish(const DragPending &pd, int lane,
+                                                  double (&v)[NT][2]) {
+    const int r = lane & 3;
+    if (pd.jsel < 0) {
+#pragma unroll
+        for (int nn = 0; nn < NT; ++nn) { v[nn][0] = v[nn][0] * pd.f; v[nn][1] = v[nn][1] * pd.f; }
+    } else {
+#pragma unroll
+        for (int nn = 0; nn < NT; ++nn)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) v[nn][h] = (8 * nn + 2 * r + h == pd.jsel) ? pd.f : 0.0;
+    }
+}
+
 // direction (x radius x scale) of a block proposal of every chain of the warp in fragment
 // layout, from the chain's own visit counter (RandDirectionProposer, proposal.py:58-82;
 // RandProposer1D :85-93); advances the counter of the chains in `adv`.
@@ -148,36 +207,10 @@ __device__ __forceinline__ bool drag_block_vector(const ModelDev &M, const Windo
                                                   uint32_t sub, int b, long long *vis_q,
                                                   const long long *e0_q, bool adv, int lane,
                                                   bool vec, double (&v)[NT][2]) {
-    const int r = lane & 3;
-    const int n = M.bsize[b];
-    double rad, sign;
-    draw_radial(M, gid, t, sub, n, rad, sign);
-    bool ok = true;
-    if (n >= 2) {
-        const long long vb = vis_q[b];
-        const long long e = vb / n;
-        const int k = (int)(vb % n);
-        long long slot = e - e0_q[b];
-        if (slot < 0 || slot >= W.cnt[b]) { ok = false; slot = 0; }
-        int2 pl;
-        pl.x = (int)((chain * W.cnt[b] + slot) * n + k);
-        pl.y = b;
-        fetch_direction<NT>(M, W, pl, r, vec, v);
-        const double f = rad * M.proposal_scale;
-#pragma unroll
-        for (int nn = 0; nn < NT; ++nn) { v[nn][0] = v[nn][0] * f; v[nn][1] = v[nn][1] * f; }
-    } else {
-        const double f = (sign > 0) ? rad * M.proposal_scale : -(rad * M.proposal_scale);
-        const int j0 = M.jstart[b];
-#pragma unroll
-        for (int nn = 0; nn < NT; ++nn)
-#pragma unroll
-            for (int h = 0; h < 2; ++h) v[nn][h] = (8 * nn + 2 * r + h == j0) ? f : 0.0;
-    }
-    __syncwarp();
-    if (adv && r == 0) vis_q[b] += 1;
-    __syncwarp();
-    return ok;
+    const DragPending pd = drag_block_issue<NT>(M, W, chain, gid, t, sub, b, vis_q, e0_q, adv,
+                                                lane, vec, v);
+    drag_block_finish<NT>(pd, lane, v);
+    return pd.ok;
 }
 
 template <int NT>
@@ -268,23 +301,34 @@ k_step_drag(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gp
         double e_lp = e0v.post, e_prior = e0v.prior, e_ll = e0v.like;
         const bool live = e_lp != -CUDART_INF;   // :590-592: else weight += 1, no fast steps
         double s_acc = s_lp, e_acc = e_lp;
-        for (int i = 1; i <= nds; ++i) {          // :603
-            // fast cycler of this chain (advanced only while the chain is dragging)
+        // the fast cycler and the direction of step i + 1 are issued while step i is evaluated
+        // (`live` is fixed for the whole slow step, so the visit counters advance the same way)
+        double vn[NT][2];
+        DragPending pend;
+        double exn = 0.0;
+        auto issue_fast = [&](int i) {
             int bf;
-            {
-                const long long fi = vis_q[NB];
-                const long long rel = fi - e0_q[NB];
-                const bool inr = rel >= 0 && rel < W.len_fast;
-                bf = W.tape_fast ? (inr ? W.tape_fast[chain * W.len_fast + rel] : M.last_slow + 1)
-                                 : W.const_fast;
-                if (live && W.tape_fast && !inr) flags |= CB2_FLAG_INTERNAL;
-                __syncwarp();
-                if (live && r == 0) vis_q[NB] = fi + 1;
-                __syncwarp();
-            }
-            if (!drag_block_vector<NT>(M, W, chain, gid, t, (uint32_t)i, bf, vis_q, e0_q, live,
-                                       lane, vec, v) && live)
-                flags |= CB2_FLAG_INTERNAL;
+            const long long fi = vis_q[NB];
+            const long long rel = fi - e0_q[NB];
+            const bool inr = rel >= 0 && rel < W.len_fast;
+            bf = W.tape_fast ? (inr ? W.tape_fast[chain * W.len_fast + rel] : M.last_slow + 1)
+                             : W.const_fast;
+            if (live && W.tape_fast && !inr) flags |= CB2_FLAG_INTERNAL;
+            __syncwarp();
+            if (live && r == 0) vis_q[NB] = fi + 1;
+            __syncwarp();
+            pend = drag_block_issue<NT>(M, W, chain, gid, t, (uint32_t)i, bf, vis_q, e0_q, live,
+                                        lane, vec, vn);
+            exn = draw_accept_exp(M, gid, t, (uint32_t)i);   // off the accept decision's chain
+        };
+        if (nds >= 1) issue_fast(1);
+        for (int i = 1; i <= nds; ++i) {          // :603
+#pragma unroll
+            for (int n = 0; n < NT; ++n) { v[n][0] = vn[n][0]; v[n][1] = vn[n][1]; }
+            drag_block_finish<NT>(pend, lane, v);
+            if (!pend.ok && live) flags |= CB2_FLAG_INTERNAL;
+            const double ex_i = exn;
+            if (i < nds) issue_fast(i + 1);
 #pragma unroll
             for (int n = 0; n < NT; ++n) { dl[n][0] = 0.0; dl[n][1] = 0.0; }
             warp_matvec8<NT, true>(Tf, lane, v, dl);   // delta on a zero vector (:606-608)
@@ -303,7 +347,7 @@ k_step_drag(ModelDev M, ChainState S, WindowDev W, const double *__restrict__ gp
                 bool ad;
                 if (p_int == -CUDART_INF) ad = false;
                 else if (p_int > c_int) ad = true;
-                else ad = draw_accept_exp(M, gid, t, (uint32_t)i) > (c_int - p_int) / M.temperature;
+                else ad = ex_i > (c_int - p_int) / M.temperature;
                 if (ad) {                                                    // :640-645
 #pragma unroll
                     for (int n = 0; n < NT; ++n) {
