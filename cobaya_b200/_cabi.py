@@ -30,6 +30,7 @@ EXPORTS = [
     "cb2_copy_rows_bulk", "cb2_drain_start", "cb2_drain_wait", "cb2_drain_reset",
     "cb2_host_alloc", "cb2_host_free", "cb2_grow_rows", "cb2_mem_info", "cb2_load_rows_bulk", "cb2_window_counts", "cb2_debug_counters",
     "cb2_checkpoint_device", "cb2_checkpoint_cov", "cb2_adopt_proposal", "cb2_get_proposal",
+    "cb2_add_external_likelihood", "cb2_check_external_source",
 ]
 
 
@@ -75,6 +76,8 @@ def load():
     L.cb2_add_gaussian_mixture.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, i32]
     L.cb2_add_rosenbrock.argtypes = [vp, i32, vp, dbl]
     L.cb2_add_constant.argtypes = [vp, dbl]
+    L.cb2_add_external_likelihood.argtypes = [vp, i32, vp, C.c_char_p, C.c_char_p]
+    L.cb2_check_external_source.argtypes = [C.c_char_p, C.c_char_p, i32, C.c_char_p, i64]
     L.cb2_set_blocking.argtypes = [vp, i32, vp, vp, vp, i32, i32, i32]
     L.cb2_set_proposal.argtypes = [vp, vp, dbl]
     L.cb2_set_options.argtypes = [vp, dbl, i64, i64, i32, i64]

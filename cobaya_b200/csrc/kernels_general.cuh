@@ -216,6 +216,8 @@ __device__ __forceinline__ double warp_logpost(const ModelDev &M, const double *
             }
         } else if (L.kind == 2) {
             val = L.scale;  // `one` (likelihoods/one/one.py:26-28)
+        } else if (L.kind == 3) {
+            val = 0.0;      // external function: added by its own kernel (kernels_ext.cuh)
         } else {
             double acc = 0.0;
             for (int i = lane; i + 1 < d; i += 32) {

@@ -11,7 +11,8 @@ import ctypes as C
 import numpy as np
 
 from . import _cabi
-from .flatmodel import LIKE_CONSTANT, LIKE_GAUSSIAN_MIXTURE, LIKE_ROSENBROCK, FlatModel
+from .flatmodel import (LIKE_CONSTANT, LIKE_EXTERNAL, LIKE_GAUSSIAN_MIXTURE, LIKE_ROSENBROCK,
+                        FlatModel)
 
 FLAG_STUCK = 1
 FLAG_ROWS_FULL = 2
@@ -101,6 +102,9 @@ class Engine:
             elif lk.kind == LIKE_ROSENBROCK:
                 self._ck(self.lib.cb2_add_rosenbrock(self.h, lk.dim, p(_i32(lk.idx)),
                                                      float(lk.scale)))
+            elif lk.kind == LIKE_EXTERNAL:
+                self._ck(self.lib.cb2_add_external_likelihood(
+                    self.h, lk.dim, p(_i32(lk.idx)), lk.source.encode(), lk.fn_name.encode()))
             elif lk.kind == LIKE_CONSTANT:
                 self._ck(self.lib.cb2_add_constant(self.h, float(lk.scale)))
             else:

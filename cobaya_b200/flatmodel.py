@@ -26,6 +26,7 @@ from scipy.linalg import lapack as _lapack
 LIKE_GAUSSIAN_MIXTURE = 0
 LIKE_ROSENBROCK = 1
 LIKE_CONSTANT = 2
+LIKE_EXTERNAL = 3
 MAX_BLOCKS = 16
 
 PRIOR_UNIFORM = 0
@@ -146,6 +147,9 @@ class LikeSpec:
     derived_names: list = field(default_factory=list)
     # rosenbrock
     scale: float = 1.0
+    # external function (device functor): CUDA source and the name of its entry point
+    source: str | None = None
+    fn_name: str | None = None
 
     @property
     def dim(self) -> int:
@@ -203,6 +207,14 @@ class LikeSpec:
         else:
             lk.logdet = np.array([-d * np.log(2 * np.pi)])
         return lk
+
+    @classmethod
+    def external(cls, idx, source, fn_name, name="external"):
+        """An external likelihood function (likelihood.py:150-255) as a device functor:
+        ``source`` defines ``extern "C" __device__ double fn_name(const double *p, int n)``,
+        ``p`` holding the input parameters in the order of ``idx``; it returns log L."""
+        return cls(kind=LIKE_EXTERNAL, idx=np.asarray(idx, dtype=np.int32), name=name,
+                   source=str(source), fn_name=str(fn_name))
 
     @classmethod
     def constant(cls, value=0.0, name="one"):

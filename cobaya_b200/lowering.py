@@ -130,6 +130,7 @@ def lower_likelihoods(model, sampled):
     gm_cls = _reference_class("cobaya.likelihoods.gaussian_mixture", "GaussianMixture")
     g_cls = _reference_class("cobaya.likelihoods.gaussian", "Gaussian")
     one_cls = _reference_class("cobaya.likelihoods.one", "one")
+    ext_cls = _reference_class("cobaya.likelihood", "LikelihoodExternalFunction")
     if len(getattr(model, "theory", {}) or {}):
         raise UnsupportedModelError(
             "Theory components are not supported by the B200 ensemble engine: "
@@ -156,14 +157,27 @@ def lower_likelihoods(model, sampled):
                                            name=name))
         elif one_cls is not None and isinstance(like, one_cls) and not getattr(like, "noise", None):
             likes.append(LikeSpec.constant(0.0, name=name))
+        elif (ext_cls is not None and isinstance(like, ext_cls) and
+              getattr(like.external_function, "cuda_source", None)):
+            # an external function with its CUDA twin (cobaya_b200.functor.device_function)
+            if like.output_params or like.get_requirements():
+                raise UnsupportedModelError(
+                    f"External likelihood '{name}': derived outputs and requirements are not "
+                    "supported on the device.")
+            idx = _indices(like, name, sampled)
+            fn = like.external_function
+            likes.append(LikeSpec.external(idx, fn.cuda_source,
+                                           getattr(fn, "cuda_name", None) or fn.__name__,
+                                           name=name))
         elif hasattr(like, "b200_scale") and cls == "Rosenbrock":  # the engine's own built-in
             idx = _indices(like, name, sampled)
             likes.append(LikeSpec.rosenbrock(idx, scale=like.b200_scale, name=name))
         else:
             raise UnsupportedModelError(
                 f"Likelihood '{name}' ({cls}) cannot be evaluated on the device: the "
-                "engine recognises gaussian_mixture, gaussian, one (without noise) and the "
-                "built-in Rosenbrock. "
+                "engine recognises gaussian_mixture, gaussian, one (without noise), the "
+                "built-in Rosenbrock and external functions that carry their CUDA source "
+                "(cobaya_b200.functor.device_function). "
                 "No CPU fallback is provided."
             )
     return likes

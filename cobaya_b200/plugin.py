@@ -379,6 +379,23 @@ class MCMC(CovmatSampler):
         except FlatModelError as e:
             raise LoggedError(self.log, "%s", str(e)) from e
 
+    def _check_external_functions(self, ens, n_points=4):
+        """An external likelihood runs as CUDA on the device and as Python in the reference's
+        ``Model``: evaluate both at a few current points and refuse a disagreement."""
+        from .flatmodel import LIKE_EXTERNAL
+
+        if not any(lk.kind == LIKE_EXTERNAL for lk in self._fm.likes):
+            return
+        st = ens.engine.get_state()
+        for c in range(min(n_points, ens.n_chains_local)):
+            want = self.model.logposterior(st["x"][c])  # both untempered
+            got = st["logpost"][c]
+            if not np.isclose(got, want.logpost, rtol=1e-8, atol=1e-8):
+                raise LoggedError(
+                    self.log, "The CUDA source of an external likelihood disagrees with its "
+                    "Python callable: log-posterior %r (device) vs %r (Python) at %r.",
+                    float(got), float(want.logpost), st["x"][c].tolist())
+
     # ------------------------------------------------------------------ run
     def _options(self):
         keys = ["burn_in", "max_tries", "proposal_scale", "learn_every", "temperature",
@@ -414,6 +431,7 @@ class MCMC(CovmatSampler):
         except Exception as e:
             raise LoggedError(self.log, "Could not start the B200 engine: %s", e) from e
         ens = self._ens
+        self._check_external_functions(ens)
         if self._resume_snapshot is None:
             self._row_cursor = np.zeros(ens.n_chains_local, np.int64)
         self._resume_snapshot = None  # rows of the previous run: free the host copy

@@ -93,6 +93,21 @@ int cb2_add_gaussian_mixture(cb2_engine *h, int32_t dim, const int32_t *idx,
 /* Built-in external-likelihood stand-in for BASELINE.json configs[3]:
  * logp = -scale * sum_i [100 (x_{i+1}-x_i^2)^2 + (1-x_i)^2]. */
 int cb2_add_rosenbrock(cb2_engine *h, int32_t dim, const int32_t *idx, double scale);
+/* External likelihood functions (LikelihoodExternalFunction, cobaya/likelihood.py:150-255: the
+ * reference accepts any Python callable) as DEVICE FUNCTORS: `cuda_source` is CUDA C++ defining
+ *     extern "C" __device__ double <fn_name>(const double *p, int n)
+ * which returns log L of the point whose input parameters (sampled indices `idx`, in that
+ * order) are p[0..n).  The source is compiled at run time with NVRTC (loaded with dlopen; the
+ * library does not link it) for sm_100a into an evaluation kernel, one thread per chain; a
+ * Metropolis proposal then runs as propose / evaluate / accept launches on the engine's stream
+ * (csrc/kernels_ext.cuh), with the same proposals as every other step kernel.  CB2_EXT_DIM is
+ * predefined as `dim`.  Returns -6 if NVRTC cannot be loaded, -7 on a compile error (the
+ * compiler log is cb2_last_error).  Not supported together with dragging (cb2_set_state: -4). */
+int cb2_add_external_likelihood(cb2_engine *h, int32_t dim, const int32_t *idx,
+                                const char *cuda_source, const char *fn_name);
+/* Compile check of such a source without an engine or a GPU; the compiler log goes to `log`. */
+int cb2_check_external_source(const char *cuda_source, const char *fn_name, int32_t dim,
+                              char *log, int64_t log_cap);
 /* `one` (cobaya/likelihoods/one/one.py:26-28): a likelihood with no input parameters
  * whose log-value is a constant (0 for `one`); keeps its chi2__<name> column. */
 int cb2_add_constant(cb2_engine *h, double value);

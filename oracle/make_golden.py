@@ -452,6 +452,42 @@ def dump_g6(n_proposals=800, seed=106, cid=4):
     print("g6_gaussian_one", out["rows_raw"].shape, out["rows_norm"].shape)
 
 
+def dump_g8(n_proposals=1200, seed=108, cids=(0, 6)):
+    """External likelihood function (LikelihoodExternalFunction, likelihood.py:150-255): the
+    unmodified reference evaluates the PYTHON callable of tests/ext_functions.py; the engine
+    evaluates its CUDA twin through the device-functor route."""
+    from tests import ext_functions
+
+    info, S0 = ext_functions.info_g8()
+    out = {}
+    for cid in cids:
+        model, sampler, x0, rows = run_reference(info, n_proposals, seed, cid)
+        out[f"x0_{cid}"] = x0
+        out[f"rows_{cid}"] = rows
+        out[f"final_x_{cid}"] = sampler.current_point.values.copy()
+        out[f"final_weight_{cid}"] = sampler.current_point.weight
+    pr = sampler.proposer
+    rng = np.random.default_rng(88)
+    pts = np.column_stack([rng.uniform(-1.5, 1.5, 40), rng.uniform(-0.8, 2.5, 40),
+                           rng.normal(0, 1, 40)])
+    kat = []
+    for p_ in pts:
+        r = model.logposterior(p_)
+        kat.append([r.logpost, r.logprior] + list(r.loglikes))
+    out.update(columns=np.array(list(sampler.collection.columns)),
+               sampled=np.array(list(model.parameterization.sampled_params())),
+               likes=np.array(list(model.likelihood)), S0=S0,
+               proposal_cov=pr.get_covariance(), i_of_j=np.asarray(pr.i_of_j),
+               block_sizes=np.array([bp.n for bp in pr.proposer]),
+               oversampling=np.asarray(pr.oversampling_factors),
+               output_thin=sampler.current_point.output_thin,
+               n_proposals=n_proposals, seed=seed, chain_ids=np.array(cids),
+               max_tries=sampler.max_tries.value, kat_x=pts, kat=np.array(kat))
+    np.savez_compressed(os.path.join(GOLDEN, "g8_external.npz"), **out)
+    print("g8_external", {k: v.shape for k, v in out.items() if k.startswith("rows_")},
+          "blocks", out["block_sizes"], out["oversampling"], "thin", out["output_thin"])
+
+
 def dump_units():
     """Known answers from the reference's own functions on fixed inputs."""
     from cobaya.functions import _rvs, inverse_cholesky
@@ -551,5 +587,7 @@ if __name__ == "__main__":
             dump_case(name, fn, n, seed=seed, chain_ids=cids)
     if want("g6_gaussian_one"):
         dump_g6()
+    if want("g8_external"):
+        dump_g8()
     if want("checkpoint"):
         dump_checkpoint()

@@ -1,0 +1,209 @@
+"""
+External likelihood functions through the device-functor route
+(cb2_add_external_likelihood, csrc/kernels_ext.cuh, csrc/ext_functor.inl) against the
+UNMODIFIED reference running the Python callable (LikelihoodExternalFunction,
+cobaya/likelihood.py:150-255): tests/golden/g8_external.npz, made by oracle/make_golden.py
+from tests/ext_functions.py.  Floating point: rows to 1e-9 (the CUDA and the numpy versions of
+the function differ in the last bits), integer weights exact.
+"""
+
+import numpy as np
+import pytest
+
+from tests.util import load_golden
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-9, 1e-11
+
+
+def flat_g8(g, source=None):
+    from cobaya_b200.flatmodel import FlatModel, LikeSpec
+
+    from tests import ext_functions
+
+    names = [str(s) for s in g["sampled"]]
+    assert names == ["a", "b", "c"] and [str(s) for s in g["likes"]] == ["banana", "gaussian"]
+    kind = np.array([0, 0, 1], np.int32)
+    lower = np.array([-2.0, -1.0, -np.inf])
+    upper = np.array([2.0, 3.0, np.inf])
+    likes = [LikeSpec.external([0, 1], source or ext_functions.BANANA_CUDA, "banana",
+                               name="banana"),
+             LikeSpec.gaussian([2], [0.1], [[0.04]], normalized=True, name="gaussian")]
+    i_of_j = [int(i) for i in g["i_of_j"]]
+    blocks, j = [], 0
+    for n in g["block_sizes"]:
+        blocks.append(i_of_j[j: j + int(n)])
+        j += int(n)
+    return FlatModel(names=names, prior_kind=kind, lower=lower, upper=upper, loc=np.zeros(3),
+                     pscale=np.ones(3), periodic=np.zeros(3, np.int32), likes=likes,
+                     blocks=blocks, oversampling=[int(o) for o in g["oversampling"]],
+                     output_thin=int(g["output_thin"]),
+                     proposal_cov=np.asarray(g["proposal_cov"]), max_tries=int(g["max_tries"]))
+
+
+def _engine(fm, n, seed, id0=0, rows_cap=4096):
+    from cobaya_b200.engine import Engine
+
+    return Engine(fm, n_chains=n, seed=seed, chain_id0=id0, rows_cap=rows_cap)
+
+
+def test_external_logposterior_matches_reference_known_answers(cuda_lib):
+    g = load_golden("g8_external")
+    eng = _engine(flat_g8(g), 1, 1)
+    lp, pr, ll, _ = eng.logpost(g["kat_x"])
+    kat = g["kat"]
+    finite = np.isfinite(kat[:, 0])
+    assert finite.sum() >= 30 and (~finite).sum() >= 1   # some points outside the prior box
+    np.testing.assert_array_equal(np.isfinite(lp), finite)
+    np.testing.assert_allclose(lp[finite], kat[finite, 0], rtol=1e-12)
+    np.testing.assert_allclose(pr[finite], kat[finite, 1], rtol=1e-12)
+    np.testing.assert_allclose(ll[finite], kat[finite, 2:], rtol=1e-12, atol=1e-13)
+
+
+@pytest.mark.parametrize("cid", [0, 6])
+def test_external_chain_matches_reference_golden(cuda_lib, cid):
+    g = load_golden("g8_external")
+    fm = flat_g8(g)
+    n = int(g["n_proposals"])
+    eng = _engine(fm, 1, seed=int(g["seed"]), id0=cid)
+    eng.set_state(g[f"x0_{cid}"][None, :])
+    done = 0
+    for k in (1, 3, 40, n):   # windows are transparent
+        step = min(k, n - done)
+        if step > 0:
+            eng.advance(step)
+            done += step
+    st = eng.get_state()
+    assert st["flags"][0] == 0
+    ref, rows = g[f"rows_{cid}"], eng.rows(0)
+    assert rows.shape == ref.shape
+    np.testing.assert_array_equal(rows[:, 0], ref[:, 0])
+    np.testing.assert_allclose(rows, ref, rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(st["x"][0], g[f"final_x_{cid}"], rtol=RTOL, atol=ATOL)
+    assert st["weight"][0] == int(g[f"final_weight_{cid}"])
+
+
+GAUSS8_CUDA = r'''
+// the same 8-D Gaussian as the built-in mixture: -0.5 (8 log 2pi + logdet + |Linv (x - mu)|^2)
+__device__ const double LINV[8][8] = {%(linv)s};
+__device__ const double MU[8] = {%(mu)s};
+extern "C" __device__ double gauss8(const double *p, int n) {
+    double q = 0.0;
+    for (int i = 0; i < 8; ++i) {
+        double a = 0.0;
+        for (int j = 0; j <= i; ++j) a += LINV[i][j] * (p[j] - MU[j]);
+        q += a * a;
+    }
+    return -0.5 * (%(c0).17g + q);
+}
+'''
+
+
+def test_external_route_equals_builtin_kernels_on_the_same_function(cuda_lib):
+    """A Gaussian written as an external CUDA function walks like the built-in Gaussian on the
+    general kernel (same Philox draws; the log-likelihoods differ in summation order only)."""
+    from cobaya_b200.flatmodel import FlatModel, LikeSpec, synthetic_gaussian_cov
+
+    D, C, n = 8, 96, 400
+    cov = synthetic_gaussian_cov(D)
+    mu = np.linspace(-0.01, 0.01, D)
+    builtin = FlatModel.gaussian(mu[None], cov[None], proposal_cov=cov, bounds=(-1.0, 1.0))
+    lk = builtin.likes[0]
+    src = GAUSS8_CUDA % dict(
+        linv=", ".join("{" + ", ".join(f"{v:.17g}" for v in row) + "}" for row in lk.linv[0]),
+        mu=", ".join(f"{v:.17g}" for v in mu),
+        c0=D * np.log(2 * np.pi) + lk.logdet[0])
+    ext = FlatModel(names=list(builtin.names), prior_kind=builtin.prior_kind,
+                    lower=builtin.lower, upper=builtin.upper, loc=builtin.loc,
+                    pscale=builtin.pscale, periodic=builtin.periodic,
+                    likes=[LikeSpec.external(np.arange(D), src, "gauss8", name="gaussian_mixture")],
+                    proposal_cov=cov)
+    x0 = np.random.default_rng(4).multivariate_normal(mu, cov, size=C)
+    a, b = _engine(builtin, C, 21), _engine(ext, C, 21)
+    a.set_kernel_policy(1)   # general kernel
+    for e in (a, b):
+        e.set_state(x0)
+        e.advance(n)
+    sa, sb = a.get_state(), b.get_state()
+    assert not sb["flags"].any()
+    np.testing.assert_array_equal(sa["n_rows"], sb["n_rows"])
+    np.testing.assert_array_equal(sa["weight"], sb["weight"])
+    np.testing.assert_allclose(sa["x"], sb["x"], rtol=1e-10, atol=1e-13)
+    ra, ca = a.rows_bulk()
+    rb, cb = b.rows_bulk()
+    np.testing.assert_array_equal(ca, cb)
+    np.testing.assert_array_equal(ra[:, 0], rb[:, 0])
+    np.testing.assert_allclose(ra, rb, rtol=1e-10, atol=1e-12)
+    # the checkpoint statistics see the same chains
+    np.testing.assert_allclose(a.moments(), b.moments(), rtol=1e-9, atol=1e-14)
+
+
+def test_external_errors_are_loud(cuda_lib):
+    from cobaya_b200.engine import EngineError
+    from cobaya_b200.flatmodel import FlatModel, LikeSpec
+
+    def model(src, name="f", drag=False):
+        kw = dict(blocks=[[0], [1]], oversampling=[1, 2], drag=True, i_last_slow_block=0,
+                  drag_interp_steps=2) if drag else {}
+        return FlatModel(names=["a", "b"], prior_kind=np.zeros(2, np.int32),
+                         lower=np.full(2, -1.0), upper=np.full(2, 1.0), loc=np.zeros(2),
+                         pscale=np.ones(2), periodic=np.zeros(2, np.int32),
+                         likes=[LikeSpec.external([0, 1], src, name)],
+                         proposal_cov=np.eye(2) * 0.01, **kw)
+
+    ok = 'extern "C" __device__ double f(const double *p, int n) { return -p[0]*p[0]-p[1]*p[1]; }'
+    with pytest.raises(EngineError, match="undefined|error"):
+        _engine(model('extern "C" __device__ double f(const double *p, int n) { return zz; }'),
+                4, 1)
+    with pytest.raises(EngineError, match="dragging"):
+        e = _engine(model(ok, drag=True), 4, 1)
+        e.set_state(np.zeros((4, 2)))
+    # NaN from the function: the chain is flagged (the reference raises)
+    nan = ('extern "C" __device__ double f(const double *p, int n) '
+           '{ return p[0] > 0.05 ? nan("") : -50.0 * (p[0]*p[0] + p[1]*p[1]); }')
+    e = _engine(model(nan), 64, 3)
+    e.set_state(np.zeros((64, 2)))
+    e.advance(200)
+    from cobaya_b200.engine import FLAG_INTERNAL
+
+    assert (e.get_state()["flags"] & FLAG_INTERNAL).any()
+
+
+def test_external_function_through_cobaya_run(cuda_lib, tmp_path):
+    """The reference's own input with ``external: <callable>``: the plugin lowers the callable's
+    CUDA twin, checks it against the Python function and samples."""
+    import copy
+
+    from tests.refenv import enable_reference
+
+    enable_reference()
+    from cobaya.log import LoggedError
+    from cobaya.run import run
+
+    from tests import ext_functions
+    from cobaya_b200.functor import device_function
+
+    info, _ = ext_functions.info_g8()
+    opts = dict(info["sampler"]["mcmc"])
+    opts.update(chains_per_gpu=256, max_samples=300, learn_proposal=True, seed=3,
+                Rminus1_stop=0.0)
+    info["sampler"] = {"cobaya_b200.plugin.MCMC": opts}
+    _, smp = run(copy.deepcopy(info))
+    rows = smp.products()["sample"]
+    assert len(rows) >= 256 * 300
+    x = rows[["a", "b", "c"]].to_numpy()
+    w = rows["weight"].to_numpy()
+    mean = (w[:, None] * x).sum(0) / w.sum()
+    # c ~ N(0.1, 0.2) x N(0, 1) prior -> mean 0.1 / 1.04; b follows 2 a^2
+    assert abs(mean[2] - 0.1 / 1.04) < 0.02
+    assert abs(mean[1] - 2 * (w * x[:, 0] ** 2).sum() / w.sum()) < 0.02
+    assert np.allclose(rows["chi2__banana"].to_numpy(),
+                       -2 * ext_functions.banana(x[:, 0], x[:, 1]), rtol=1e-9, atol=1e-9)
+    # a CUDA twin that computes something else is refused before sampling
+    bad = device_function(ext_functions.BANANA_CUDA.replace("0.09", "0.08"))(
+        lambda a, b: ext_functions.banana(a, b))
+    info2 = copy.deepcopy(info)
+    info2["likelihood"]["banana"] = {"external": bad}
+    with pytest.raises(LoggedError, match="disagrees"):
+        run(info2)

@@ -420,3 +420,33 @@ def test_vectorised_start_points_follow_ref_and_prior():
     assert abs(x[:, 3].std() - 3.0) < 0.2
     for row in x[:20]:
         assert np.isfinite(model.logposterior(row).logpost)
+
+
+def test_external_function_sources_compile_and_lower_without_a_gpu():
+    """NVRTC needs no device: the CUDA twin of an external likelihood is compiled (and its
+    errors reported) on the CPU; the lowering turns the reference's
+    LikelihoodExternalFunction into an external LikeSpec."""
+    enable_reference()
+    from cobaya.model import get_model
+
+    from tests import ext_functions
+    from cobaya_b200.flatmodel import LIKE_EXTERNAL
+    from cobaya_b200.functor import DeviceFunctionError, check_source, device_function
+    from cobaya_b200.lowering import UnsupportedModelError, lower_likelihoods
+
+    assert check_source(ext_functions.BANANA_CUDA, dim=2) == ""
+    with pytest.raises(DeviceFunctionError, match="undefined"):
+        check_source('extern "C" __device__ double f(const double *p, int n) { return q; }')
+    with pytest.raises(DeviceFunctionError, match="exactly one"):
+        device_function("double f(double x) { return x; }")
+    info, _ = ext_functions.info_g8()
+    info.pop("sampler")
+    model = get_model(info)
+    sampled = list(model.parameterization.sampled_params())
+    likes = lower_likelihoods(model, sampled)
+    assert [lk.kind for lk in likes][0] == LIKE_EXTERNAL and likes[0].fn_name == "banana"
+    assert list(likes[0].idx) == [sampled.index("a"), sampled.index("b")]
+    # a plain Python callable has no device twin: refused, never a CPU fallback
+    info["likelihood"]["banana"] = {"external": lambda a, b: -a * a - b * b}
+    with pytest.raises(UnsupportedModelError, match="device_function"):
+        lower_likelihoods(get_model(info), sampled)
