@@ -468,12 +468,12 @@ def dump_g8(n_proposals=1200, seed=108, cids=(0, 6)):
         out[f"final_weight_{cid}"] = sampler.current_point.weight
     pr = sampler.proposer
     rng = np.random.default_rng(88)
-    pts = np.column_stack([rng.uniform(-1.5, 1.5, 40), rng.uniform(-0.8, 2.5, 40),
+    pts = np.column_stack([rng.uniform(-2.3, 2.3, 40), rng.uniform(-0.8, 2.5, 40),
                            rng.normal(0, 1, 40)])
     kat = []
     for p_ in pts:
         r = model.logposterior(p_)
-        kat.append([r.logpost, r.logprior] + list(r.loglikes))
+        kat.append([r.logpost, r.logprior] + (list(r.loglikes) if len(r.loglikes) else [np.nan] * 2))
     out.update(columns=np.array(list(sampler.collection.columns)),
                sampled=np.array(list(model.parameterization.sampled_params())),
                likes=np.array(list(model.likelihood)), S0=S0,

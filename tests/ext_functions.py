@@ -40,3 +40,42 @@ def info_g8():
                              "learn_proposal": False, "measure_speeds": False,
                              "burn_in": 0, "seed": 8}},
     }, S0
+
+
+GAUSS_CUDA = r'''
+// the same Gaussian as the built-in mixture: -0.5 (D log 2pi + logdet + |Linv (x - mu)|^2)
+__device__ const double LINV[%(D)d][%(D)d] = {%(linv)s};
+__device__ const double MU[%(D)d] = {%(mu)s};
+extern "C" __device__ double gauss_ext(const double *p, int n) {
+    double q = 0.0;
+    for (int i = 0; i < %(D)d; ++i) {
+        double a = 0.0;
+        for (int j = 0; j <= i; ++j) a += LINV[i][j] * (p[j] - MU[j]);
+        q += a * a;
+    }
+    return -0.5 * (%(c0).17g + q);
+}
+'''
+
+
+def gaussian_pair(D):
+    """The benchmark's correlated Gaussian twice: as the built-in mixture and as an external
+    CUDA function (same proposals, log-likelihoods equal up to the summation order)."""
+    from cobaya_b200.flatmodel import FlatModel, LikeSpec, synthetic_gaussian_cov
+
+    cov = synthetic_gaussian_cov(D)
+    mu = np.linspace(-0.01, 0.01, D)
+    builtin = FlatModel.gaussian(mu[None], cov[None], proposal_cov=cov, bounds=(-1.0, 1.0))
+    lk = builtin.likes[0]
+    src = GAUSS_CUDA % dict(
+        D=D,
+        linv=", ".join("{" + ", ".join(f"{v:.17g}" for v in row) + "}" for row in lk.linv[0]),
+        mu=", ".join(f"{v:.17g}" for v in mu),
+        c0=D * np.log(2 * np.pi) + lk.logdet[0])
+    ext = FlatModel(names=list(builtin.names), prior_kind=builtin.prior_kind,
+                    lower=builtin.lower, upper=builtin.upper, loc=builtin.loc,
+                    pscale=builtin.pscale, periodic=builtin.periodic,
+                    likes=[LikeSpec.external(np.arange(D), src, "gauss_ext",
+                                             name="gaussian_mixture")],
+                    proposal_cov=cov)
+    return builtin, ext, mu, cov

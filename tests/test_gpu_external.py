@@ -84,41 +84,15 @@ def test_external_chain_matches_reference_golden(cuda_lib, cid):
     assert st["weight"][0] == int(g[f"final_weight_{cid}"])
 
 
-GAUSS8_CUDA = r'''
-// the same 8-D Gaussian as the built-in mixture: -0.5 (8 log 2pi + logdet + |Linv (x - mu)|^2)
-__device__ const double LINV[8][8] = {%(linv)s};
-__device__ const double MU[8] = {%(mu)s};
-extern "C" __device__ double gauss8(const double *p, int n) {
-    double q = 0.0;
-    for (int i = 0; i < 8; ++i) {
-        double a = 0.0;
-        for (int j = 0; j <= i; ++j) a += LINV[i][j] * (p[j] - MU[j]);
-        q += a * a;
-    }
-    return -0.5 * (%(c0).17g + q);
-}
-'''
-
-
 def test_external_route_equals_builtin_kernels_on_the_same_function(cuda_lib):
     """A Gaussian written as an external CUDA function walks like the built-in Gaussian on the
     general kernel (same Philox draws; the log-likelihoods differ in summation order only)."""
     from cobaya_b200.flatmodel import FlatModel, LikeSpec, synthetic_gaussian_cov
 
+    from tests import ext_functions
+
     D, C, n = 8, 96, 400
-    cov = synthetic_gaussian_cov(D)
-    mu = np.linspace(-0.01, 0.01, D)
-    builtin = FlatModel.gaussian(mu[None], cov[None], proposal_cov=cov, bounds=(-1.0, 1.0))
-    lk = builtin.likes[0]
-    src = GAUSS8_CUDA % dict(
-        linv=", ".join("{" + ", ".join(f"{v:.17g}" for v in row) + "}" for row in lk.linv[0]),
-        mu=", ".join(f"{v:.17g}" for v in mu),
-        c0=D * np.log(2 * np.pi) + lk.logdet[0])
-    ext = FlatModel(names=list(builtin.names), prior_kind=builtin.prior_kind,
-                    lower=builtin.lower, upper=builtin.upper, loc=builtin.loc,
-                    pscale=builtin.pscale, periodic=builtin.periodic,
-                    likes=[LikeSpec.external(np.arange(D), src, "gauss8", name="gaussian_mixture")],
-                    proposal_cov=cov)
+    builtin, ext, mu, cov = ext_functions.gaussian_pair(D)
     x0 = np.random.default_rng(4).multivariate_normal(mu, cov, size=C)
     a, b = _engine(builtin, C, 21), _engine(ext, C, 21)
     a.set_kernel_policy(1)   # general kernel
