@@ -30,7 +30,7 @@ EXPORTS = [
     "cb2_copy_rows_bulk", "cb2_drain_start", "cb2_drain_wait", "cb2_drain_reset",
     "cb2_host_alloc", "cb2_host_free", "cb2_grow_rows", "cb2_mem_info", "cb2_load_rows_bulk", "cb2_window_counts", "cb2_debug_counters",
     "cb2_checkpoint_device", "cb2_checkpoint_cov", "cb2_adopt_proposal", "cb2_get_proposal",
-    "cb2_add_external_likelihood", "cb2_check_external_source",
+    "cb2_add_external_likelihood", "cb2_check_external_source", "cb2_measure_speeds",
 ]
 
 
@@ -89,6 +89,7 @@ def load():
     L.cb2_summary.argtypes = [vp, vp]
     L.cb2_moments.argtypes = [vp, i32, i32, vp, vp, vp]
     L.cb2_bounds.argtypes = [vp, i32, i32, dbl, vp, vp, vp]
+    L.cb2_measure_speeds.argtypes = [vp, vp, i64, i32, vp]
     L.cb2_checkpoint_device.argtypes = [vp, vp, vp]
     L.cb2_checkpoint_cov.argtypes = [vp, vp]
     L.cb2_adopt_proposal.argtypes = [vp]

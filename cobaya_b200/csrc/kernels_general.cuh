@@ -146,9 +146,11 @@ __global__ void k_basis_general(uint32_t key0, uint32_t key1, uint64_t chain_id0
 //   like  : GaussianMixture.logp (gaussian_mixture.py:138-163) in the Cholesky form
 //           -1/2 (d log 2pi + log|S_k| + |L_k^-1 (x - mu_k)|^2), logsumexp over modes;
 //           derived = L_k^-1 (x - mu_k) (:146-156)
+// `only` >= 0: that likelihood component alone, -2: none (cb2_measure_speeds); -1: all.
 __device__ __forceinline__ double warp_logpost(const ModelDev &M, const double *xs,
                                                double &lprior, double *ll, double *der,
-                                               double *z, double *lpk, int lane) {
+                                               double *z, double *lpk, int lane,
+                                               int only = -1) {
     const int D = M.D;
     bool bad = false;
     for (int i = lane; i < D; i += 32) {
@@ -178,6 +180,7 @@ __device__ __forceinline__ double warp_logpost(const ModelDev &M, const double *
     lprior = M.uniform_logp + s;
     double total = lprior;
     for (int l = 0; l < M.n_like; ++l) {
+        if (only != -1 && l != only) continue;
         const LikeDev &L = M.likes[l];
         const int d = L.dim;
         const int32_t *idx = M.ipool + L.idx_off;
@@ -239,7 +242,7 @@ __device__ __forceinline__ double warp_logpost(const ModelDev &M, const double *
 __global__ void k_logpost(ModelDev M, const double *__restrict__ X, int64_t n,
                           double *__restrict__ logpost, double *__restrict__ logprior,
                           double *__restrict__ loglikes, double *__restrict__ derived,
-                          int per_warp) {
+                          int per_warp, int only = -1) {
     extern __shared__ double sm[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t p = blockIdx.x * (int64_t)(blockDim.x >> 5) + wid;
@@ -253,7 +256,7 @@ __global__ void k_logpost(ModelDev M, const double *__restrict__ X, int64_t n,
     if (lane < CB2_MAX_LIKES) ll[lane] = CUDART_NAN;
     __syncwarp();
     double lp;
-    double v = warp_logpost(M, xs, lp, ll, der, z, lpk, lane);
+    double v = warp_logpost(M, xs, lp, ll, der, z, lpk, lane, only);
     __syncwarp();
     if (lane == 0) {
         logpost[p] = v;

@@ -177,6 +177,15 @@ class Engine:
                                       _cabi.ptr(out)))
         return out
 
+    def measure_speeds(self, X, repeats=3):
+        """Evaluations per second of every likelihood component on the device
+        (Model.measure_and_set_speeds, model.py:1543-1592)."""
+        X = _f64(np.atleast_2d(X))
+        out = np.zeros(self.fm.n_like)
+        self._ck(self.lib.cb2_measure_speeds(self.h, _cabi.ptr(X), X.shape[0], int(repeats),
+                                             _cabi.ptr(out)))
+        return out
+
     # ---- device checkpoint (D <= 64): R-1, W and the new transform without host LAPACK
     def checkpoint_device(self, dev_ptr=None):
         """cb2_checkpoint_device on the sums of the last ``moments`` call (``dev_ptr``: the

@@ -27,6 +27,8 @@ from collections.abc import Callable, Sequence
 from itertools import chain
 from typing import Any
 
+import os
+
 import numpy as np
 import pandas as pd
 from cobaya import mpi
@@ -229,7 +231,8 @@ class MCMC(CovmatSampler):
             self._x0[:] = np.nan  # replaced by the snapshot's current points in run()
         if self.measure_speeds and not self.blocking:
             n = None if self.measure_speeds is True else int(self.measure_speeds)
-            self.model.measure_and_set_speeds(n=n, discard=0, random_state=self._rng)
+            if not self._measure_speeds_on_device():
+                self.model.measure_and_set_speeds(n=n, discard=0, random_state=self._rng)
         self.current_point = _CurrentPointView(self)
         self.set_proposer_blocking()
         self.set_proposer_initial_covmat(load=True)
@@ -378,6 +381,36 @@ class MCMC(CovmatSampler):
                 **self._blocking_lowered)
         except FlatModelError as e:
             raise LoggedError(self.log, "%s", str(e)) from e
+
+    def _measure_speeds_on_device(self, n_points=4096, repeats=3):
+        """``Model.measure_and_set_speeds`` (model.py:1543-1592) with the components timed where
+        they run: every likelihood alone on the device at the start points
+        (``cb2_measure_speeds``, CUDA events).  The measured speeds feed the reference's own
+        automatic blocking.  Returns False (host measurement) for the CPU test engine or when
+        there are no start points yet (resuming)."""
+        if self._engine_factory is not None or not np.all(np.isfinite(self._x0)):
+            return False
+        from .engine import Engine
+
+        d = self.model.prior.d()
+        try:
+            fm = lower_model(self.model, proposal_cov=np.eye(d))
+        except FlatModelError as e:
+            raise LoggedError(self.log, "%s", str(e)) from e
+        dev = self.device if self.device is not None else int(os.environ.get("LOCAL_RANK", 0))
+        eng = Engine(fm, n_chains=1, seed=0, chain_id0=0, rows_cap=1, device=int(dev))
+        try:
+            speeds = eng.measure_speeds(self._x0[:n_points], repeats=repeats)
+        finally:
+            eng.close()
+        if mpi.more_than_one_process():
+            speeds = np.average(mpi.allgather(speeds), axis=0)
+        named = dict(zip(self.model.likelihood, speeds))
+        self.mpi_info("Setting measured speeds (per sec, on the device): %r",
+                      {k: float(f"{v:.3g}") for k, v in named.items()})
+        for like, speed in zip(self.model.likelihood.values(), speeds):
+            like.set_measured_speed(float(speed))
+        return True
 
     def _check_external_functions(self, ens, n_points=4):
         """An external likelihood runs as CUDA on the device and as Python in the reference's

@@ -200,6 +200,13 @@ int cb2_adopt_proposal(cb2_engine *h);
 /* the proposal transform in use (row-major D x D, block-sorted coordinates) */
 int cb2_get_proposal(cb2_engine *h, double *T_out);
 
+/* Model.measure_and_set_speeds (cobaya/model.py:1543-1592) for the device components:
+ * evaluations per second of every likelihood alone (speeds_out[n_like], in the order they were
+ * added) at the n host points X[n*D], timed with CUDA events over `repeats` passes; they feed
+ * the reference's automatic blocking (Model.get_param_blocking_for_sampler). */
+int cb2_measure_speeds(cb2_engine *h, const double *X, int64_t n, int32_t repeats,
+                       double *speeds_out);
+
 /* R-1 of the confidence-interval bounds (mcmc.py:918-1002): per (virtual) chain the raw
  * weighted sample quantiles at limfrac and 1-limfrac of every sampled parameter (GetDist
  * `MCSamples.confidence`, mcmc.py:926-929 with limfrac = Rminus1_cl_level/2), summed into

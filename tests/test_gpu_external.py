@@ -181,3 +181,49 @@ def test_external_function_through_cobaya_run(cuda_lib, tmp_path):
     info2["likelihood"]["banana"] = {"external": bad}
     with pytest.raises(LoggedError, match="disagrees"):
         run(info2)
+
+
+def test_speeds_are_measured_on_the_device(cuda_lib):
+    """cb2_measure_speeds (Model.measure_and_set_speeds, model.py:1543-1592): every component
+    alone, in evaluations per second; a heavier function is slower; the plugin feeds the
+    measured speeds to the reference's automatic blocking."""
+    import copy
+
+    from cobaya_b200.flatmodel import FlatModel, LikeSpec
+
+    heavy = ('extern "C" __device__ double heavy(const double *p, int n) { double s = 0.0; '
+             'for (int i = 0; i < 20000; ++i) s += sin(p[0] + i * 1e-3) * 1e-9; '
+             'return -p[0] * p[0] - p[1] * p[1] + s; }')
+    light = ('extern "C" __device__ double light(const double *p, int n) '
+             '{ return -p[0] * p[0]; }')
+    fm = FlatModel(names=["a", "b", "c"], prior_kind=np.zeros(3, np.int32),
+                   lower=np.full(3, -1.0), upper=np.full(3, 1.0), loc=np.zeros(3),
+                   pscale=np.ones(3), periodic=np.zeros(3, np.int32),
+                   likes=[LikeSpec.external([0, 1], heavy, "heavy", name="heavy"),
+                          LikeSpec.external([2], light, "light", name="light"),
+                          LikeSpec.gaussian([2], [0.0], [[0.04]], name="gaussian")],
+                   proposal_cov=np.eye(3) * 0.01)
+    eng = _engine(fm, 1, 1)
+    X = np.random.default_rng(0).uniform(-0.5, 0.5, (4096, 3))
+    sp = eng.measure_speeds(X, repeats=3)
+    assert sp.shape == (3,) and np.all(np.isfinite(sp)) and np.all(sp > 0)
+    assert sp[0] < sp[1] / 20 and sp[0] < sp[2] / 20
+    # the measurement leaves the posterior untouched
+    lp, pr, ll, _ = eng.logpost(X[:4])
+    assert np.allclose(ll[:, 1], -X[:4, 2] ** 2)
+
+    from tests.refenv import enable_reference
+
+    enable_reference()
+    from cobaya.run import run
+
+    from tests import ext_functions
+
+    info, _ = ext_functions.info_g8()
+    opts = dict(info["sampler"]["mcmc"])
+    opts.pop("blocking")
+    opts.update(chains_per_gpu=64, max_samples=20, measure_speeds=True, seed=3)
+    info["sampler"] = {"cobaya_b200.plugin.MCMC": opts}
+    _, smp = run(copy.deepcopy(info))
+    speeds = {k: v.speed for k, v in smp.model.likelihood.items()}
+    assert all(np.isfinite(v) and v > 1e3 for v in speeds.values()), speeds
