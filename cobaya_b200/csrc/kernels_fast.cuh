@@ -411,12 +411,7 @@ k_basis_wy(uint32_t key0, uint32_t key1, uint64_t chain_id0, int block, int n,
     }
     if (lane == 0) sign_cnt[w] = n_negative;
     __syncthreads();
-    {
-        int c = n - 1;
-#pragma unroll
-        for (int i = 0; i < NW; ++i) c += sign_cnt[i];
-        if (tid == 0) Dv[n - 1] = (c & 1) ? -1.0 : 1.0;
-    }
+    // D[n-1] (functions.py:59) stays in a register (d_last): nothing reads Dv[n-1]
     int c_all = n - 1;
 #pragma unroll
     for (int i = 0; i < NW; ++i) c_all += sign_cnt[i];
