@@ -64,6 +64,7 @@ struct LikeDev {
 
 struct ModelDev {
     int32_t D, n_like, n_der, width;
+    int32_t n_ep;   // external priors: extra minuslogprior__<name> columns in a row
     // prior
     const int32_t *prior_kind;  // [D]
     const double *lower, *upper, *loc, *pscale;

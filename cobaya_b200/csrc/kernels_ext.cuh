@@ -24,9 +24,11 @@ struct ExtStash {
     int64_t *e0;     // [C*(NB+1)] epochs of the blocks at window start
 };
 
+#define CB2_MAX_EXT (2 * CB2_MAX_LIKES)
 struct ExtSlots {
-    int32_t n;
-    int32_t slot[CB2_MAX_LIKES];  // likelihood index of external function k
+    int32_t n;                  // external functions: likelihoods and priors
+    int32_t n_ep;               // of which priors
+    int32_t slot[CB2_MAX_EXT];  // likelihood index of function k, or -(1 + j) for external prior j
 };
 
 __global__ void __launch_bounds__(256)
@@ -97,11 +99,25 @@ k_ext_accept(ModelDev M, ChainState S, StepSmem L, ExtStash E, ExtSlots X, int64
     R.burn_left = S.burn_left[chain]; R.added_w = S.added_w[chain];
     R.n_rows = S.n_rows[chain]; R.n_acc = S.n_acc[chain]; R.flags = S.flags[chain];
     __syncwarp();
-    const double tprior = E.prior[chain];
+    double tprior = E.prior[chain];
     double tl = E.lp[chain];
+    const int NP1 = X.n_ep + 1;
+    if (tprior != -CUDART_INF) {
+        // external priors after the internal one (prior.py:700-720)
+        double like_part = tl - tprior, esum = 0.0;
+        for (int k = 0; k < X.n; ++k) {
+            if (X.slot[k] >= 0) continue;
+            double e = E.ext[chain * X.n + k];
+            if (e != e) { R.flags |= CB2_FLAG_INTERNAL; e = -CUDART_INF; }
+            esum += e;
+        }
+        if (X.n_ep) { tprior += esum; tl = tprior + like_part; }
+    }
+    if (tprior == -CUDART_INF) tl = -CUDART_INF;
     if (tl != -CUDART_INF) {
         // the likelihoods are only evaluated where the prior is finite (model.py:640-678)
         for (int k = 0; k < X.n; ++k) {
+            if (X.slot[k] < 0) continue;
             double e = E.ext[chain * X.n + k];
             if (e != e) {                       // NaN: the reference raises; flag the chain
                 R.flags |= CB2_FLAG_INTERNAL;
@@ -114,8 +130,14 @@ k_ext_accept(ModelDev M, ChainState S, StepSmem L, ExtStash E, ExtSlots X, int64
     __syncwarp();
     bool acc = metropolis_accept(M, gid, t, 0, tl, R.logpost);               // :560
     acc = __shfl_sync(FULLMASK, (int)acc, 0);
-    warp_process(M, S, chain, R, acc, x, der, ll, trial, tder, tll, tl, tprior, lane);  // :561
+    warp_process(M, S, chain, R, acc, x, der, ll, trial, tder, tll, tl, tprior, lane,
+                 X.n_ep ? S.pl + chain * NP1 : nullptr);                     // :561
     __syncwarp();
+    if (acc && X.n_ep && lane == 0) {   // prior components of the new current point
+        S.pl[chain * NP1] = E.prior[chain];
+        for (int k = 0; k < X.n; ++k)
+            if (X.slot[k] < 0) S.pl[chain * NP1 - X.slot[k]] = E.ext[chain * X.n + k];
+    }
     for (int i = lane; i < D; i += 32) S.x[chain * D + i] = x[i];
     for (int i = lane; i < ND; i += 32) S.der[chain * ND + i] = der[i];
     for (int i = lane; i < NL; i += 32) S.ll[chain * NL + i] = ll[i];
@@ -130,18 +152,34 @@ k_ext_accept(ModelDev M, ChainState S, StepSmem L, ExtStash E, ExtSlots X, int64
 // logpost[i] += sum_k ext[i][k], ll[i][slot_k] = ext[i][k] for points with a finite prior
 // (cb2_set_state, cb2_logpost).  flags != nullptr: the start-point check of k_init_state.
 __global__ void k_ext_add(ExtSlots X, int64_t n, int NL, const double *__restrict__ ext,
-                          double *__restrict__ logpost, const double *__restrict__ logprior,
-                          double *__restrict__ ll, uint32_t *__restrict__ flags) {
+                          double *__restrict__ logpost, double *__restrict__ logprior,
+                          double *__restrict__ ll, uint32_t *__restrict__ flags,
+                          double *__restrict__ pl) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    double lp = logpost[i];
-    if (logprior[i] != -CUDART_INF && lp != -CUDART_INF) {
-        for (int k = 0; k < X.n; ++k) {
-            const double e = ext[i * X.n + k];
-            ll[i * NL + X.slot[k]] = e;
-            lp += e;
-        }
-        logpost[i] = lp;
+    double lp = logpost[i], pr = logprior[i];
+    const int NP1 = X.n_ep + 1;
+    if (pl) pl[i * NP1] = pr;
+    if (pr != -CUDART_INF) {
+        const double like_part = lp - pr;
+        double esum = 0.0;
+        for (int k = 0; k < X.n; ++k)
+            if (X.slot[k] < 0) {
+                const double e = ext[i * X.n + k];
+                if (pl) pl[i * NP1 - X.slot[k]] = e;
+                esum += e;
+            }
+        if (X.n_ep) { pr += esum; lp = pr + like_part; logprior[i] = pr; }
     }
+    if (pr == -CUDART_INF || pr != pr) lp = -CUDART_INF;
+    if (lp != -CUDART_INF) {
+        for (int k = 0; k < X.n; ++k)
+            if (X.slot[k] >= 0) {
+                const double e = ext[i * X.n + k];
+                ll[i * NL + X.slot[k]] = e;
+                lp += e;
+            }
+    }
+    logpost[i] = lp;
     if (flags) flags[i] = isfinite(lp) ? 0u : CB2_FLAG_INTERNAL;
 }

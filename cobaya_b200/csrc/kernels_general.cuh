@@ -276,6 +276,7 @@ struct ChainState {
     double *der;       // [chains*n_der]
     int64_t *weight, *prior_rej, *burn_left, *added_w, *n_rows, *n_acc;
     int64_t *vis;      // [chains*n_blocks] visits per block proposer
+    double *pl;        // [chains*(n_ep+1)] internal + external prior components (n_ep > 0)
     uint32_t *flags;
     double *rows;      // [chains*cap*width]
     int64_t cap;
@@ -375,8 +376,11 @@ __device__ __forceinline__ void warp_process(const ModelDev &M, const ChainState
                                              double *cur_x, double *cur_der, double *cur_ll,
                                              const double *new_x, const double *new_der,
                                              const double *new_ll, double new_logpost,
-                                             double new_logprior, int lane) {
-    const int D = M.D, ND = M.n_der, NL = M.n_like;
+                                             double new_logprior, int lane,
+                                             const double *cur_pl = nullptr) {
+    // cur_pl (models with external priors): {internal prior, external priors...} of the
+    // current point, the minuslogprior__0 / minuslogprior__<name> columns of its row
+    const int D = M.D, ND = M.n_der, NL = M.n_like, NE = M.n_ep;
     if (accept) {
         if (R.burn_left <= 0) {
             int64_t w = R.weight;
@@ -401,9 +405,11 @@ __device__ __forceinline__ void warp_process(const ModelDev &M, const ChainState
                         else if (e == 1) val = -(R.logpost / M.temperature);
                         else if (e < 2 + D) val = cur_x[e - 2];
                         else if (e < 2 + D + ND) val = cur_der[e - 2 - D];
-                        else if (e < 2 + D + ND + 2) val = -R.logprior;
-                        else if (e == 2 + D + ND + 2) val = -2 * llsum;
-                        else val = -2 * cur_ll[e - (2 + D + ND + 3)];
+                        else if (e < 2 + D + ND + 1) val = -R.logprior;
+                        else if (e < 2 + D + ND + 2) val = NE ? -cur_pl[0] : -R.logprior;
+                        else if (e < 2 + D + ND + 2 + NE) val = -cur_pl[1 + e - (2 + D + ND + 2)];
+                        else if (e == 2 + D + ND + 2 + NE) val = -2 * llsum;
+                        else val = -2 * cur_ll[e - (2 + D + ND + 3 + NE)];
                         row[e] = val;
                     }
                     R.n_rows += 1;

@@ -109,6 +109,9 @@ class Engine:
                 self._ck(self.lib.cb2_add_constant(self.h, float(lk.scale)))
             else:
                 raise EngineError(f"unknown likelihood kind {lk.kind}")
+        for ep in getattr(fm, "ext_priors", []):
+            self._ck(self.lib.cb2_add_external_prior(
+                self.h, ep.dim, p(_i32(ep.idx)), ep.source.encode(), ep.fn_name.encode()))
         self._ck(self.lib.cb2_set_blocking(
             self.h, len(fm.blocks), p(_i32(fm.block_sizes)), p(_i32(fm.oversampling)),
             p(_i32(fm.i_of_j)), int(fm.drag), int(fm.last_slow),

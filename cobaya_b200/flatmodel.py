@@ -255,6 +255,8 @@ class FlatModel:
     temperature: float = 1.0
     max_tries: int = 2**59  # 'no limit'; the sampler front ends set mcmc.yaml's value
     output_thin: int = 1
+    # external priors (prior.py:537-577) as device functors: LikeSpec.external entries
+    ext_priors: list = field(default_factory=list)
 
     def __post_init__(self):
         D = len(self.names)
@@ -311,7 +313,7 @@ class FlatModel:
     def row_width(self) -> int:
         """weight, minuslogpost, sampled, derived, minuslogprior, minuslogprior__0,
         chi2, chi2__<like>... (collection.py:154-159)."""
-        return 2 + self.D + self.n_derived + 2 + 1 + self.n_like
+        return 2 + self.D + self.n_derived + 2 + len(self.ext_priors) + 1 + self.n_like
 
     def columns(self) -> list:
         cols = ["weight", "minuslogpost"] + list(self.names)
@@ -321,7 +323,9 @@ class FlatModel:
                     f"{lk.name}_derived_{i}" for i in range(lk.n_derived)
                 ]
                 cols += list(names)
-        cols += ["minuslogprior", "minuslogprior__0", "chi2"]
+        cols += ["minuslogprior", "minuslogprior__0"]
+        cols += [f"minuslogprior__{ep.name}" for ep in self.ext_priors]
+        cols += ["chi2"]
         cols += [f"chi2__{lk.name}" for lk in self.likes]
         return cols
 

@@ -30,11 +30,6 @@ def lower_prior(prior):
     the device in closed form.  Each lowered parameter is checked against its own
     ``pdf.logpdf`` at a few points of the support before it is accepted."""
     D = prior.d()
-    if len(getattr(prior, "external", {}) or {}):
-        raise UnsupportedModelError(
-            "External priors are not supported by the B200 ensemble engine "
-            "(SURVEY.md section 8f row 3)."
-        )
     kind = np.zeros(D, np.int32)
     loc, scale = np.zeros(D), np.ones(D)
     pa, pb = np.zeros(D), np.zeros(D)
@@ -124,6 +119,27 @@ def _indices(like, name, sampled):
     return [sampled.index(p) for p in like.input_params]
 
 
+def lower_external_priors(prior, sampled):
+    """External priors (prior.py:537-577): Python callables under ``prior:``.  Those carrying
+    their CUDA twin (cobaya_b200.functor.device_function) become device functors; their
+    arguments are the function's parameters in signature order (``ExternalPrior.params``)."""
+    out = []
+    for name, ext in (getattr(prior, "external", {}) or {}).items():
+        fn = ext.logp
+        if not getattr(fn, "cuda_source", None):
+            raise UnsupportedModelError(
+                f"External prior '{name}' is a Python callable without a CUDA twin "
+                "(cobaya_b200.functor.device_function): it cannot be evaluated on the device. "
+                "No CPU fallback is provided.")
+        missing = [p for p in ext.params if p not in sampled]
+        if missing:
+            raise UnsupportedModelError(
+                f"External prior '{name}': parameter(s) {missing} are not sampled.")
+        out.append(LikeSpec.external([sampled.index(p) for p in ext.params], fn.cuda_source,
+                                     getattr(fn, "cuda_name", None) or fn.__name__, name=name))
+    return out
+
+
 def lower_likelihoods(model, sampled):
     """Recognised by CLASS (isinstance against the reference's classes), never by name: a
     user class that happens to be called ``GaussianMixture`` is not lowered as the built-in."""
@@ -196,6 +212,7 @@ def lower_model(model, sampler=None, *, blocks=None, oversampling=None, drag=Fal
         )
     kind, lower, upper, loc, scale, periodic, pa, pb = lower_prior(model.prior)
     likes = lower_likelihoods(model, sampled)
+    ext_priors = lower_external_priors(model.prior, sampled)
     derived_model = [p for p in par.derived_params()]
     derived_engine = [n for lk in likes for n in lk.derived_names]
     if derived_model != derived_engine:
@@ -224,5 +241,5 @@ def lower_model(model, sampler=None, *, blocks=None, oversampling=None, drag=Fal
         drag=drag, i_last_slow_block=i_last_slow_block,
         drag_interp_steps=drag_interp_steps, proposal_cov=proposal_cov,
         proposal_scale=proposal_scale, temperature=temperature, max_tries=int(max_tries),
-        output_thin=output_thin,
+        output_thin=output_thin, ext_priors=ext_priors,
     )

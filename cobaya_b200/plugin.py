@@ -417,7 +417,7 @@ class MCMC(CovmatSampler):
         ``Model``: evaluate both at a few current points and refuse a disagreement."""
         from .flatmodel import LIKE_EXTERNAL
 
-        if not any(lk.kind == LIKE_EXTERNAL for lk in self._fm.likes):
+        if not (any(lk.kind == LIKE_EXTERNAL for lk in self._fm.likes) or self._fm.ext_priors):
             return
         st = ens.engine.get_state()
         for c in range(min(n_points, ens.n_chains_local)):
@@ -425,7 +425,7 @@ class MCMC(CovmatSampler):
             got = st["logpost"][c]
             if not np.isclose(got, want.logpost, rtol=1e-8, atol=1e-8):
                 raise LoggedError(
-                    self.log, "The CUDA source of an external likelihood disagrees with its "
+                    self.log, "The CUDA source of an external likelihood / prior disagrees with its "
                     "Python callable: log-posterior %r (device) vs %r (Python) at %r.",
                     float(got), float(want.logpost), st["x"][c].tolist())
 

@@ -105,6 +105,13 @@ int cb2_add_rosenbrock(cb2_engine *h, int32_t dim, const int32_t *idx, double sc
  * compiler log is cb2_last_error).  Not supported together with dragging (cb2_set_state: -4). */
 int cb2_add_external_likelihood(cb2_engine *h, int32_t dim, const int32_t *idx,
                                 const char *cuda_source, const char *fn_name);
+/* External priors (cobaya/prior.py:537-577,765-772: any Python callable under `prior:`) through
+ * the same route: the function returns a log-prior term of its parameters; it is evaluated where
+ * the internal prior is finite, added to the log-prior, and reported in its own
+ * minuslogprior__<name> column after minuslogprior__0 (the row gets one column wider per external
+ * prior).  Call after cb2_set_prior (which removes them) and before cb2_set_state. */
+int cb2_add_external_prior(cb2_engine *h, int32_t dim, const int32_t *idx,
+                           const char *cuda_source, const char *fn_name);
 /* Compile check of such a source without an engine or a GPU; the compiler log goes to `log`. */
 int cb2_check_external_source(const char *cuda_source, const char *fn_name, int32_t dim,
                               char *log, int64_t log_cap);

@@ -488,6 +488,38 @@ def dump_g8(n_proposals=1200, seed=108, cids=(0, 6)):
           "blocks", out["block_sizes"], out["oversampling"], "thin", out["output_thin"])
 
 
+def dump_g9(n_proposals=1000, seed=109, cids=(3,)):
+    """External PRIOR (prior.py:537-577,765-772): the reference evaluates the Python callable of
+    tests/ext_functions.py; rows carry its own minuslogprior__ring column."""
+    from tests import ext_functions
+
+    info, cov = ext_functions.info_g9()
+    out = {}
+    for cid in cids:
+        model, sampler, x0, rows = run_reference(info, n_proposals, seed, cid)
+        out[f"x0_{cid}"] = x0
+        out[f"rows_{cid}"] = rows
+        out[f"final_x_{cid}"] = sampler.current_point.values.copy()
+        out[f"final_weight_{cid}"] = sampler.current_point.weight
+    pr = sampler.proposer
+    rng = np.random.default_rng(99)
+    pts = np.column_stack([rng.uniform(-1.7, 1.7, 40), rng.uniform(-1.4, 1.4, 40),
+                           rng.normal(0, 1, 40)])
+    kat = []
+    for p_ in pts:
+        r = model.logposterior(p_)
+        kat.append([r.logpost] + list(r.logpriors) + (list(r.loglikes) if len(r.loglikes)
+                                                      else [np.nan]))
+    out.update(columns=np.array(list(sampler.collection.columns)),
+               sampled=np.array(list(model.parameterization.sampled_params())),
+               cov=cov, proposal_cov=pr.get_covariance(),
+               n_proposals=n_proposals, seed=seed, chain_ids=np.array(cids),
+               max_tries=sampler.max_tries.value, kat_x=pts, kat=np.array(kat))
+    np.savez_compressed(os.path.join(GOLDEN, "g9_external_prior.npz"), **out)
+    print("g9_external_prior", {k: v.shape for k, v in out.items() if k.startswith("rows_")},
+          list(out["columns"]))
+
+
 def dump_units():
     """Known answers from the reference's own functions on fixed inputs."""
     from cobaya.functions import _rvs, inverse_cholesky
@@ -589,5 +621,7 @@ if __name__ == "__main__":
         dump_g6()
     if want("g8_external"):
         dump_g8()
+    if want("g9_external_prior"):
+        dump_g9()
     if want("checkpoint"):
         dump_checkpoint()

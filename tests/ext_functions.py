@@ -23,6 +23,41 @@ def banana(a, b):
     return -0.5 * (a * a / 0.09 + u * u / 0.01) - 0.1 * np.log1p(np.exp(-3.0 * a))
 
 
+RING_CUDA = r'''
+// a soft ring prior on (a, b): log N(sqrt(a^2 + b^2); 0.5, 0.1), not normalised
+extern "C" __device__ double ring(const double *p, int n) {
+    const double rr = sqrt(p[0] * p[0] + p[1] * p[1]);
+    return -0.5 * (rr - 0.5) * (rr - 0.5) / 0.01;
+}
+'''
+
+
+@device_function(RING_CUDA)
+def ring(a, b):
+    rr = np.sqrt(a * a + b * b)
+    return -0.5 * (rr - 0.5) ** 2 / 0.01
+
+
+def info_g9():
+    """3-D: the reference's ``gaussian_mixture`` on (a, b, c) with an EXTERNAL PRIOR on (a, b)
+    (prior.py:537-577) and a normal 1-D prior on c."""
+    names = ["a", "b", "c"]
+    cov = np.diag([0.3, 0.3, 0.2]) ** 2
+    cov[0, 1] = cov[1, 0] = 0.03
+    return {
+        "params": {"a": {"prior": {"min": -1.5, "max": 1.5}, "ref": 0.5, "proposal": 0.1},
+                   "b": {"prior": {"min": -1.5, "max": 1.5}, "ref": 0.05, "proposal": 0.1},
+                   "c": {"prior": {"dist": "norm", "loc": 0.0, "scale": 1.0}, "ref": 0.1,
+                         "proposal": 0.1}},
+        "prior": {"ring": ring},
+        "likelihood": {"gaussian_mixture": {"means": [[0.1, 0.0, 0.05]], "covs": [cov.tolist()],
+                                            "input_params": names, "derived": False}},
+        "sampler": {"mcmc": {"covmat": np.diag([0.1, 0.1, 0.1]) ** 2, "covmat_params": names,
+                             "learn_proposal": False, "measure_speeds": False,
+                             "burn_in": 0, "seed": 9}},
+    }, cov
+
+
 def info_g8():
     """3-D: external function of (a, b) + the reference's 1-D ``gaussian`` on c; two blocks."""
     names = ["a", "b", "c"]

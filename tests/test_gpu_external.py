@@ -227,3 +227,87 @@ def test_speeds_are_measured_on_the_device(cuda_lib):
     _, smp = run(copy.deepcopy(info))
     speeds = {k: v.speed for k, v in smp.model.likelihood.items()}
     assert all(np.isfinite(v) and v > 1e3 for v in speeds.values()), speeds
+
+
+def flat_g9(g):
+    from cobaya_b200.flatmodel import FlatModel, LikeSpec
+
+    from tests import ext_functions
+
+    names = [str(s) for s in g["sampled"]]
+    assert names == ["a", "b", "c"]
+    assert [str(c) for c in g["columns"]][5:8] == ["minuslogprior", "minuslogprior__0",
+                                                   "minuslogprior__ring"]
+    kind = np.array([0, 0, 1], np.int32)
+    lower = np.array([-1.5, -1.5, -np.inf])
+    upper = np.array([1.5, 1.5, np.inf])
+    likes = [LikeSpec.gaussian_mixture([0, 1, 2], [[0.1, 0.0, 0.05]], g["cov"][None],
+                                       name="gaussian_mixture")]
+    fm = FlatModel(names=names, prior_kind=kind, lower=lower, upper=upper, loc=np.zeros(3),
+                   pscale=np.ones(3), periodic=np.zeros(3, np.int32), likes=likes,
+                   ext_priors=[LikeSpec.external([0, 1], ext_functions.RING_CUDA, "ring",
+                                                 name="ring")],
+                   proposal_cov=np.asarray(g["proposal_cov"]), max_tries=int(g["max_tries"]))
+    assert fm.columns() == [str(c) for c in g["columns"]]
+    return fm
+
+
+def test_external_prior_matches_reference(cuda_lib):
+    """An external prior (prior.py:537-577,765-772) as a device functor: known answers and the
+    chain of the unmodified reference, including its own minuslogprior__ring column."""
+    g = load_golden("g9_external_prior")
+    fm = flat_g9(g)
+    eng = _engine(fm, 1, seed=int(g["seed"]), id0=3)
+    lp, pr, ll, _ = eng.logpost(g["kat_x"])
+    kat = g["kat"]            # logpost, logprior__0, logprior__ring, loglike
+    finite = np.isfinite(kat[:, 0])
+    assert finite.sum() >= 25 and (~finite).sum() >= 1
+    np.testing.assert_array_equal(np.isfinite(lp), finite)
+    np.testing.assert_allclose(lp[finite], kat[finite, 0], rtol=1e-12)
+    np.testing.assert_allclose(pr[finite], kat[finite, 1] + kat[finite, 2], rtol=1e-12)
+    np.testing.assert_allclose(ll[finite, 0], kat[finite, 3], rtol=1e-12)
+    n = int(g["n_proposals"])
+    eng.set_state(g["x0_3"][None, :])
+    eng.advance(9)
+    eng.advance(n - 9)
+    st = eng.get_state()
+    assert st["flags"][0] == 0
+    ref, rows = g["rows_3"], eng.rows(0)
+    assert rows.shape == ref.shape
+    np.testing.assert_array_equal(rows[:, 0], ref[:, 0])
+    np.testing.assert_allclose(rows, ref, rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(st["x"][0], g["final_x_3"], rtol=RTOL, atol=ATOL)
+    # snapshot / restore keeps the prior components of the current point
+    blob = eng.export_state()
+    twin = _engine(fm, 1, seed=int(g["seed"]), id0=3)
+    twin.import_state(blob, eng.rows(0), np.array([len(rows)], np.int64))
+    for e in (eng, twin):
+        e.advance(200)
+    np.testing.assert_array_equal(eng.rows(0), twin.rows(0))
+
+
+def test_external_prior_through_cobaya_run(cuda_lib):
+    import copy
+
+    from tests.refenv import enable_reference
+
+    enable_reference()
+    from cobaya.run import run
+
+    from tests import ext_functions
+
+    info, _ = ext_functions.info_g9()
+    opts = dict(info["sampler"]["mcmc"])
+    opts.update(chains_per_gpu=128, max_samples=200, seed=5, Rminus1_stop=0.0)
+    info["sampler"] = {"cobaya_b200.plugin.MCMC": opts}
+    _, smp = run(copy.deepcopy(info))
+    rows = smp.products()["sample"]
+    a, b = rows["a"].to_numpy(), rows["b"].to_numpy()
+    np.testing.assert_allclose(rows["minuslogprior__ring"].to_numpy(),
+                               -ext_functions.ring(a, b), rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(rows["minuslogprior"].to_numpy(),
+                               rows["minuslogprior__0"].to_numpy()
+                               + rows["minuslogprior__ring"].to_numpy(), rtol=1e-12)
+    w = rows["weight"].to_numpy()
+    rr = np.sqrt(a * a + b * b)
+    assert abs((w * rr).sum() / w.sum() - 0.5) < 0.1   # the ring holds the radius near 0.5
