@@ -265,7 +265,7 @@ def test_external_prior_matches_reference(cuda_lib):
     np.testing.assert_array_equal(np.isfinite(lp), finite)
     np.testing.assert_allclose(lp[finite], kat[finite, 0], rtol=1e-12)
     np.testing.assert_allclose(pr[finite], kat[finite, 1] + kat[finite, 2], rtol=1e-12)
-    np.testing.assert_allclose(ll[finite, 0], kat[finite, 3], rtol=1e-12)
+    np.testing.assert_allclose(ll[finite, 0], kat[finite, 3], rtol=1e-12, atol=1e-13)
     n = int(g["n_proposals"])
     eng.set_state(g["x0_3"][None, :])
     eng.advance(9)

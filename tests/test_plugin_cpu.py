@@ -450,3 +450,15 @@ def test_external_function_sources_compile_and_lower_without_a_gpu():
     info["likelihood"]["banana"] = {"external": lambda a, b: -a * a - b * b}
     with pytest.raises(UnsupportedModelError, match="device_function"):
         lower_likelihoods(get_model(info), sampled)
+    # external priors (prior.py:537-577) the same way; the row gets their own column
+    from cobaya_b200.lowering import lower_model
+
+    info9, _ = ext_functions.info_g9()
+    info9.pop("sampler")
+    fm = lower_model(get_model(info9), proposal_cov=np.eye(3))
+    assert [ep.name for ep in fm.ext_priors] == ["ring"] and list(fm.ext_priors[0].idx) == [0, 1]
+    assert fm.columns()[5:8] == ["minuslogprior", "minuslogprior__0", "minuslogprior__ring"]
+    assert fm.row_width == len(fm.columns()) == 10
+    info9["prior"] = {"ring": lambda a, b: -(a * a + b * b)}
+    with pytest.raises(UnsupportedModelError, match="External prior 'ring'"):
+        lower_model(get_model(info9), proposal_cov=np.eye(3))
