@@ -25,6 +25,7 @@ static int pack_fast(cb2_engine *h) {
     // parameters) for the Metropolis and dragging kernels, or the built-in Rosenbrock over
     // the parameters in sampler order for the dragging kernel (kernels_drag.cuh)
     if (h->D > 64 || h->likes.size() != 1) return 0;
+    if (!h->exts.empty()) return 0;  // external functions / priors: kernels_ext.cuh only
     const bool gauss = fast_step_supported_like(h->M);
     const bool rosen = h->likes[0].d.kind == 1 && h->drag && h->likes[0].d.dim == h->D;
     if (!gauss && !rosen) return 0;
@@ -174,6 +175,7 @@ static int pack_stream(cb2_engine *h) {
     // D <= 64 is the territory of the register-resident kernels; the streamed path takes what
     // they refuse (several components over disjoint parameters)
     if ((h->D <= 64 && h->fast_ready) || !stream_step_supported(h->M, h->likes.size())) return 0;
+    if (!h->exts.empty()) return 0;  // external functions / priors: kernels_ext.cuh only
     const int D = h->D, NT = (D + 7) / 8, DP = 8 * NT;
     const int NL = (int)h->likes.size();
     // whitened coordinate a = aoff[l] + a' for component l; every sampled parameter must be

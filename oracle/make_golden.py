@@ -513,6 +513,9 @@ def dump_g9(n_proposals=1000, seed=109, cids=(3,)):
     out.update(columns=np.array(list(sampler.collection.columns)),
                sampled=np.array(list(model.parameterization.sampled_params())),
                cov=cov, proposal_cov=pr.get_covariance(),
+               i_of_j=np.asarray(pr.i_of_j), block_sizes=np.array([bp.n for bp in pr.proposer]),
+               oversampling=np.asarray(pr.oversampling_factors),
+               output_thin=sampler.current_point.output_thin,
                n_proposals=n_proposals, seed=seed, chain_ids=np.array(cids),
                max_tries=sampler.max_tries.value, kat_x=pts, kat=np.array(kat))
     np.savez_compressed(os.path.join(GOLDEN, "g9_external_prior.npz"), **out)
