@@ -119,24 +119,29 @@ def _indices(like, name, sampled):
     return [sampled.index(p) for p in like.input_params]
 
 
-def lower_external_priors(prior, sampled):
+def lower_external_priors(prior, sampled, sources=None):
     """External priors (prior.py:537-577): Python callables under ``prior:``.  Those carrying
     their CUDA twin (cobaya_b200.functor.device_function) become device functors; their
-    arguments are the function's parameters in signature order (``ExternalPrior.params``)."""
+    arguments are the function's parameters in signature order (``ExternalPrior.params``).
+    ``sources``: the ``prior`` block of the input (lambda strings are translated)."""
+    from .functor import DeviceFunctionError, twin_of
+
     out = []
     for name, ext in (getattr(prior, "external", {}) or {}).items():
         fn = ext.logp
-        if not getattr(fn, "cuda_source", None):
+        try:
+            source, entry = twin_of(fn, (sources or {}).get(name), name)
+        except DeviceFunctionError as e:
             raise UnsupportedModelError(
-                f"External prior '{name}' is a Python callable without a CUDA twin "
-                "(cobaya_b200.functor.device_function): it cannot be evaluated on the device. "
-                "No CPU fallback is provided.")
+                f"External prior '{name}' cannot be evaluated on the device: {e}. Attach its "
+                "CUDA source with cobaya_b200.functor.device_function. "
+                "No CPU fallback is provided.") from e
         missing = [p for p in ext.params if p not in sampled]
         if missing:
             raise UnsupportedModelError(
                 f"External prior '{name}': parameter(s) {missing} are not sampled.")
-        out.append(LikeSpec.external([sampled.index(p) for p in ext.params], fn.cuda_source,
-                                     getattr(fn, "cuda_name", None) or fn.__name__, name=name))
+        out.append(LikeSpec.external([sampled.index(p) for p in ext.params], source, entry,
+                                     name=name))
     return out
 
 
@@ -173,17 +178,33 @@ def lower_likelihoods(model, sampled):
                                            name=name))
         elif one_cls is not None and isinstance(like, one_cls) and not getattr(like, "noise", None):
             likes.append(LikeSpec.constant(0.0, name=name))
-        elif (ext_cls is not None and isinstance(like, ext_cls) and
-              getattr(like.external_function, "cuda_source", None)):
-            # an external function with its CUDA twin (cobaya_b200.functor.device_function)
+        elif ext_cls is not None and isinstance(like, ext_cls):
+            # an external function: its CUDA twin (cobaya_b200.functor.device_function) or the
+            # automatic translation of its lambda string (functor.cuda_from_lambda)
+            from inspect import getfullargspec
+
+            from .functor import DeviceFunctionError, twin_of
+
             if like.output_params or like.get_requirements():
                 raise UnsupportedModelError(
                     f"External likelihood '{name}': derived outputs and requirements are not "
                     "supported on the device.")
-            idx = _indices(like, name, sampled)
             fn = like.external_function
-            likes.append(LikeSpec.external(idx, fn.cuda_source,
-                                           getattr(fn, "cuda_name", None) or fn.__name__,
+            try:
+                source, entry = twin_of(fn, getattr(like, "external", None), name)
+            except DeviceFunctionError as e:
+                raise UnsupportedModelError(
+                    f"External likelihood '{name}' cannot be evaluated on the device: {e}. "
+                    "Attach its CUDA source with cobaya_b200.functor.device_function. "
+                    "No CPU fallback is provided.") from e
+            # p[] follows the function's signature
+            order = [a for a in getfullargspec(fn).args if a in like.input_params]
+            if sorted(order) != sorted(like.input_params):
+                raise UnsupportedModelError(
+                    f"External likelihood '{name}': inputs {list(like.input_params)} do not "
+                    f"match the function's named arguments {order}.")
+            _indices(like, name, sampled)
+            likes.append(LikeSpec.external([sampled.index(p_) for p_ in order], source, entry,
                                            name=name))
         elif hasattr(like, "b200_scale") and cls == "Rosenbrock":  # the engine's own built-in
             idx = _indices(like, name, sampled)
@@ -212,7 +233,11 @@ def lower_model(model, sampler=None, *, blocks=None, oversampling=None, drag=Fal
         )
     kind, lower, upper, loc, scale, periodic, pa, pb = lower_prior(model.prior)
     likes = lower_likelihoods(model, sampled)
-    ext_priors = lower_external_priors(model.prior, sampled)
+    try:
+        prior_sources = dict(model.info().get("prior") or {})
+    except Exception:
+        prior_sources = {}
+    ext_priors = lower_external_priors(model.prior, sampled, prior_sources)
     derived_model = [p for p in par.derived_params()]
     derived_engine = [n for lk in likes for n in lk.derived_names]
     if derived_model != derived_engine:

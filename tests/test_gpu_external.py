@@ -311,3 +311,34 @@ def test_external_prior_through_cobaya_run(cuda_lib):
     w = rows["weight"].to_numpy()
     rr = np.sqrt(a * a + b * b)
     assert abs((w * rr).sum() / w.sum() - 0.5) < 0.1   # the ring holds the radius near 0.5
+
+
+def test_yaml_style_lambda_strings_run_on_the_device(cuda_lib):
+    """External likelihood and prior given as lambda STRINGS (the YAML form): translated to
+    CUDA, checked against the Python callables by the plugin, sampled."""
+    from tests.refenv import enable_reference
+
+    enable_reference()
+    from cobaya.run import run
+
+    info = {"params": {"a": {"prior": {"min": -2, "max": 2}, "ref": 0.4, "proposal": 0.1},
+                       "b": {"prior": {"min": -2, "max": 2}, "ref": 0.1, "proposal": 0.1}},
+            "prior": {"ring": "lambda a,b: stats.norm.logpdf(np.sqrt(a**2+b**2), loc=0.5, scale=0.1)"},
+            "likelihood": {"like1": "lambda b,a: -0.5*((a-0.1)**2+b**2)/0.09 - np.log1p(np.exp(-a))",
+                           "like2": {"external": "lambda b: -0.5 * b**2 if b > -1.5 else -np.inf"}},
+            "sampler": {"cobaya_b200.plugin.MCMC": {
+                "chains_per_gpu": 128, "max_samples": 150, "seed": 2, "Rminus1_stop": 0.0,
+                "measure_speeds": False, "covmat": np.eye(2) * 0.01, "covmat_params": ["a", "b"]}}}
+    _, smp = run(info)
+    rows = smp.products()["sample"]
+    a, b = rows["a"].to_numpy(), rows["b"].to_numpy()
+    rr = np.sqrt(a * a + b * b)
+    np.testing.assert_allclose(rows["minuslogprior__ring"].to_numpy(),
+                               0.5 * ((rr - 0.5) / 0.1) ** 2 + np.log(0.1)
+                               + 0.5 * np.log(2 * np.pi), rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(rows["chi2__like1"].to_numpy(),
+                               ((a - 0.1) ** 2 + b * b) / 0.09 + 2 * np.log1p(np.exp(-a)),
+                               rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(rows["chi2__like2"].to_numpy(), b * b, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(rows["chi2"].to_numpy(), rows["chi2__like1"].to_numpy()
+                               + rows["chi2__like2"].to_numpy(), rtol=1e-12)

@@ -462,3 +462,37 @@ def test_external_function_sources_compile_and_lower_without_a_gpu():
     info9["prior"] = {"ring": lambda a, b: -(a * a + b * b)}
     with pytest.raises(UnsupportedModelError, match="External prior 'ring'"):
         lower_model(get_model(info9), proposal_cov=np.eye(3))
+
+
+def test_lambda_strings_are_translated_to_cuda_on_the_cpu():
+    """YAML-style external functions (lambda strings, tools.py:344-384) get their CUDA twin
+    automatically; what the small grammar does not cover is refused with a reason."""
+    enable_reference()
+    from cobaya.model import get_model
+
+    from cobaya_b200.functor import DeviceFunctionError, check_source, cuda_from_lambda
+    from cobaya_b200.lowering import UnsupportedModelError, lower_model
+
+    src, entry, args = cuda_from_lambda(
+        "lambda a, b: stats.norm.logpdf(a - b**2, loc=0, scale=0.1) - np.log1p(a*a) "
+        "+ (0 if a > -1 and b < 2 else -np.inf) + np.minimum(a, 0.5) * np.pi", "my like")
+    assert args == ["a", "b"] and entry == "cb2_fn_my_like"
+    assert check_source(src, entry, dim=2) == ""
+    for bad in ("lambda a: [a]", "lambda a: a.real", "lambda a, _self: a", "lambda *a: 1.0",
+                "lambda a: scipy.special.gamma(a)", "lambda a: q + a", "import os"):
+        with pytest.raises(DeviceFunctionError):
+            cuda_from_lambda(bad, "f")
+    info = {"params": {"a": {"prior": {"min": -1, "max": 1}},
+                       "b": {"prior": {"min": -1, "max": 1}}},
+            "prior": {"ring": "lambda a,b: stats.norm.logpdf(np.sqrt(a**2+b**2), loc=0.5, scale=0.1)"},
+            "likelihood": {"like1": "lambda b,a: -0.5*(a**2+b**2)/0.04",
+                           "like2": {"external": "lambda b: -b**2"}}}
+    fm = lower_model(get_model(info), proposal_cov=np.eye(2))
+    assert [list(lk.idx) for lk in fm.likes] == [[1, 0], [1]]   # p[] follows the signature
+    assert fm.columns()[4:] == ["minuslogprior", "minuslogprior__0", "minuslogprior__ring",
+                                "chi2", "chi2__like1", "chi2__like2"]
+    for lk in fm.likes + fm.ext_priors:
+        assert check_source(lk.source, lk.fn_name, dim=lk.dim) == ""
+    info["likelihood"]["like1"] = "lambda a, b: float(np.linalg.norm([a, b]))"
+    with pytest.raises(UnsupportedModelError, match="cannot be evaluated on the device"):
+        lower_model(get_model(info), proposal_cov=np.eye(2))
