@@ -183,3 +183,266 @@ __global__ void k_ext_add(ExtSlots X, int64_t n, int NL, const double *__restric
     logpost[i] = lp;
     if (flags) flags[i] = isfinite(lp) ? 0u : CB2_FLAG_INTERNAL;
 }
+
+// =========================================================================================
+// Dragging (mcmc.py:564-668) with external likelihood functions: BASELINE configs[3] as it is
+// stated ("Rosenbrock external-likelihood, dragging").  A slow proposal needs 1 + 2 n_drag
+// posterior evaluations, each fast step depending on the accept decision of the one before,
+// so the step is split at every evaluation:
+//   k_extd_begin         slow proposal on the end point              -> 1 point per chain
+//   <user kernel>, k_extd_begin_finish   e_lp, `live`, running sums
+//   n_drag x { k_extd_fast_propose  (2 points per chain) , <user kernel>, k_extd_fast_accept }
+//   k_extd_end           final accept on the averaged log-posteriors, bookkeeping, row
+// following the drag branch of k_step_general statement by statement (same Philox draws,
+// cyclers and Haar bases).  External PRIORS are not supported together with dragging.
+// =========================================================================================
+struct DragStash {
+    double *s_pt, *e_pt;   // [C*D] current start / end point
+    double *pts;           // [2*C*D] evaluation points: slow step [0, C), fast step ps | pe
+    double *lp, *prior;    // [2*C]   partial log-posterior / prior of the evaluation points
+    double *ll, *der;      // [2*C*NL], [2*C*ND]
+    double *s_lp, *e_lp, *e_prior, *s_acc, *e_acc;   // [C]
+    double *e_ll, *e_der;  // [C*NL], [C*ND]
+    int32_t *live;         // [C]
+    double *ext;           // [2*C*n_ext]
+    int64_t *e0;           // [C*(NB+1)]
+};
+
+// log-posterior of an evaluation point from its partial value and the external terms;
+// ll_row (global, optional) receives the external log-likelihoods
+__device__ __forceinline__ double ext_like_total(const ExtSlots &X, const double *ext_row,
+                                                 double partial_lp, double prior, double *ll_row,
+                                                 bool &nan_seen) {
+    if (prior == -CUDART_INF || partial_lp == -CUDART_INF) return -CUDART_INF;
+    double tl = partial_lp;
+    for (int k = 0; k < X.n; ++k) {
+        if (X.slot[k] < 0) continue;
+        double e = ext_row[k];
+        if (e != e) { nan_seen = true; e = -CUDART_INF; }
+        if (ll_row) ll_row[X.slot[k]] = e;
+        tl += e;
+    }
+    return tl;
+}
+
+__global__ void __launch_bounds__(256)
+k_extd_begin(ModelDev M, ChainState S, WindowDev W, StepSmem L, DragStash E, int64_t n_chains,
+             uint64_t t, int first) {
+    extern __shared__ double sm[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t chain = blockIdx.x * (int64_t)(blockDim.x >> 5) + wid;
+    if (chain >= n_chains) return;
+    const uint64_t gid = M.chain_id0 + (uint64_t)chain;
+    const int D = M.D, ND = M.n_der, NL = M.n_like, NV = M.n_blocks + 1;
+    double *base = sm + (size_t)wid * L.total;
+    double *e_pt = base + L.e_pt, *v = base + L.v, *z = base + L.z, *lpk = base + L.lpk;
+    double *e_der = base + L.e_der, *e_ll = base + L.e_ll;
+    int64_t *vis = reinterpret_cast<int64_t *>(base + L.vis);
+    int64_t *e0s = vis + NV;
+    for (int i = lane; i < D; i += 32) {                                  // mcmc.py:579-581
+        const double xi = S.x[chain * D + i];
+        e_pt[i] = xi;
+        E.s_pt[chain * D + i] = xi;
+    }
+    for (int i = lane; i < NV; i += 32) {
+        const int64_t vv = S.vis[chain * NV + i];
+        vis[i] = vv;
+        if (first) {
+            const int64_t e = (i < M.n_blocks) ? vv / M.bsize[i] : vv;
+            e0s[i] = e;
+            E.e0[chain * NV + i] = e;
+        } else {
+            e0s[i] = E.e0[chain * NV + i];
+        }
+    }
+    for (int i = lane; i < ND; i += 32) e_der[i] = 0.0;
+    __syncwarp();
+    const int b = W.tape_slow ? W.tape_slow[chain * W.len_slow + (int64_t)(t - W.base_slow)]
+                              : W.const_slow;
+    const bool ok = warp_block_proposal(M, W, chain, gid, t, 0, b, e_pt, v, vis, e0s, lane);  // :582
+    warp_reduce_periodic(M, e_pt, lane);                                   // :583
+    double e_prior;
+    const double e_lp = warp_logpost(M, e_pt, e_prior, e_ll, e_der, z, lpk, lane);  // :589
+    __syncwarp();
+    for (int i = lane; i < D; i += 32) {
+        E.e_pt[chain * D + i] = e_pt[i];
+        E.pts[chain * D + i] = e_pt[i];
+    }
+    for (int i = lane; i < ND; i += 32) E.der[chain * ND + i] = e_der[i];
+    for (int i = lane; i < NL; i += 32) E.ll[chain * NL + i] = e_ll[i];
+    for (int i = lane; i < NV; i += 32) S.vis[chain * NV + i] = vis[i];
+    if (lane == 0) {
+        E.lp[chain] = e_lp;
+        E.prior[chain] = e_prior;
+        E.s_lp[chain] = S.logpost[chain];                                  // :580
+        if (!ok) S.flags[chain] |= CB2_FLAG_INTERNAL;
+    }
+}
+
+__global__ void k_extd_begin_finish(ModelDev M, ChainState S, DragStash E, ExtSlots X,
+                                    int64_t n_chains) {
+    const int64_t chain = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (chain >= n_chains) return;
+    const int NL = M.n_like, ND = M.n_der;
+    bool nan_seen = false;
+    const double e_lp = ext_like_total(X, E.ext + chain * X.n, E.lp[chain], E.prior[chain],
+                                       E.ll + chain * NL, nan_seen);
+    if (nan_seen) S.flags[chain] |= CB2_FLAG_INTERNAL;
+    const bool live = e_lp != -CUDART_INF;                                 // :590-592
+    E.live[chain] = live ? 1 : 0;
+    if (!live) {
+        S.weight[chain] += 1;   // the fast cycler is not advanced on this path
+        return;
+    }
+    E.e_lp[chain] = e_lp;
+    E.e_prior[chain] = E.prior[chain];
+    for (int i = 0; i < NL; ++i) E.e_ll[chain * NL + i] = E.ll[chain * NL + i];
+    for (int i = 0; i < ND; ++i) E.e_der[chain * ND + i] = E.der[chain * ND + i];
+    E.s_acc[chain] = E.s_lp[chain];                                        // :595-596
+    E.e_acc[chain] = e_lp;
+}
+
+__global__ void __launch_bounds__(256)
+k_extd_fast_propose(ModelDev M, ChainState S, WindowDev W, StepSmem L, DragStash E,
+                    int64_t n_chains, uint64_t t, int i_step) {
+    extern __shared__ double sm[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t chain = blockIdx.x * (int64_t)(blockDim.x >> 5) + wid;
+    if (chain >= n_chains || !E.live[chain]) return;
+    const uint64_t gid = M.chain_id0 + (uint64_t)chain;
+    const int D = M.D, ND = M.n_der, NL = M.n_like, NV = M.n_blocks + 1;
+    const int64_t C = n_chains;
+    double *base = sm + (size_t)wid * L.total;
+    double *ps = base + L.ps, *pe = base + L.pe, *delta = base + L.delta, *v = base + L.v,
+           *z = base + L.z, *lpk = base + L.lpk, *pe_der = base + L.pe_der,
+           *pe_ll = base + L.pe_ll, *tmp_ll = base + L.tmp_ll;
+    int64_t *vis = reinterpret_cast<int64_t *>(base + L.vis);
+    int64_t *e0s = vis + NV;
+    for (int k = lane; k < NV; k += 32) {
+        vis[k] = S.vis[chain * NV + k];
+        e0s[k] = E.e0[chain * NV + k];
+    }
+    for (int k = lane; k < D; k += 32) delta[k] = 0.0;                     // :606
+    for (int k = lane; k < ND; k += 32) pe_der[k] = 0.0;
+    __syncwarp();
+    int bf;
+    {
+        const int64_t fi = vis[M.n_blocks];  // fast-cycler visit counter
+        const int64_t rel = fi - e0s[M.n_blocks];
+        const bool inr = rel >= 0 && rel < W.len_fast;
+        bf = W.tape_fast ? (inr ? W.tape_fast[chain * W.len_fast + rel] : 0) : W.const_fast;
+        if (W.tape_fast && !inr && lane == 0) S.flags[chain] |= CB2_FLAG_INTERNAL;
+        __syncwarp();
+        if (lane == 0) vis[M.n_blocks] = fi + 1;
+    }
+    if (!warp_block_proposal(M, W, chain, gid, t, (uint32_t)i_step, bf, delta, v, vis, e0s, lane)
+        && lane == 0)
+        S.flags[chain] |= CB2_FLAG_INTERNAL;                               // :607
+    warp_reduce_periodic(M, delta, lane);                                  // :608
+    for (int k = lane; k < D; k += 32) {
+        ps[k] = E.s_pt[chain * D + k] + delta[k];                          // :610
+        pe[k] = E.e_pt[chain * D + k] + delta[k];                          // :622
+    }
+    __syncwarp();
+    double ps_prior, pe_prior;
+    const double ps_lp = warp_logpost(M, ps, ps_prior, tmp_ll, nullptr, z, lpk, lane);
+    __syncwarp();
+    for (int k = lane; k < NL; k += 32) E.ll[chain * NL + k] = tmp_ll[k];
+    const double pe_lp = warp_logpost(M, pe, pe_prior, pe_ll, pe_der, z, lpk, lane);
+    __syncwarp();
+    for (int k = lane; k < D; k += 32) {
+        E.pts[chain * D + k] = ps[k];
+        E.pts[(C + chain) * D + k] = pe[k];
+    }
+    for (int k = lane; k < NL; k += 32) E.ll[(C + chain) * NL + k] = pe_ll[k];
+    for (int k = lane; k < ND; k += 32) E.der[(C + chain) * ND + k] = pe_der[k];
+    for (int k = lane; k < NV; k += 32) S.vis[chain * NV + k] = vis[k];
+    if (lane == 0) {
+        E.lp[chain] = ps_lp; E.prior[chain] = ps_prior;
+        E.lp[C + chain] = pe_lp; E.prior[C + chain] = pe_prior;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_extd_fast_accept(ModelDev M, ChainState S, DragStash E, ExtSlots X, int64_t n_chains,
+                   uint64_t t, int i_step) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t chain = blockIdx.x * (int64_t)(blockDim.x >> 5) + wid;
+    if (chain >= n_chains || !E.live[chain]) return;
+    const uint64_t gid = M.chain_id0 + (uint64_t)chain;
+    const int D = M.D, ND = M.n_der, NL = M.n_like;
+    const int64_t C = n_chains;
+    bool nan_seen = false;
+    double ps_lp = 0.0, pe_lp = 0.0;
+    if (lane == 0) {
+        ps_lp = ext_like_total(X, E.ext + chain * X.n, E.lp[chain], E.prior[chain], nullptr,
+                               nan_seen);
+        pe_lp = ext_like_total(X, E.ext + (C + chain) * X.n, E.lp[C + chain], E.prior[C + chain],
+                               E.ll + (C + chain) * NL, nan_seen);
+        if (nan_seen) S.flags[chain] |= CB2_FLAG_INTERNAL;
+    }
+    ps_lp = __shfl_sync(FULLMASK, ps_lp, 0);
+    pe_lp = __shfl_sync(FULLMASK, pe_lp, 0);
+    double s_lp = E.s_lp[chain], e_lp = E.e_lp[chain];
+    if (ps_lp != -CUDART_INF && pe_lp != -CUDART_INF) {                    // :621,:628
+        const double frac = (double)i_step / (double)(1 + M.drag_steps);   // :630
+        const double p_int = (1 - frac) * ps_lp + frac * pe_lp;
+        const double c_int = (1 - frac) * s_lp + frac * e_lp;
+        bool ad = metropolis_accept(M, gid, t, (uint32_t)i_step, p_int, c_int);
+        ad = __shfl_sync(FULLMASK, (int)ad, 0);
+        if (ad) {                                                          // :640-645
+            for (int k = lane; k < D; k += 32) {
+                E.s_pt[chain * D + k] = E.pts[chain * D + k];
+                E.e_pt[chain * D + k] = E.pts[(C + chain) * D + k];
+            }
+            for (int k = lane; k < ND; k += 32) E.e_der[chain * ND + k] = E.der[(C + chain) * ND + k];
+            for (int k = lane; k < NL; k += 32) E.e_ll[chain * NL + k] = E.ll[(C + chain) * NL + k];
+            s_lp = ps_lp; e_lp = pe_lp;
+            if (lane == 0) {
+                E.s_lp[chain] = s_lp; E.e_lp[chain] = e_lp;
+                E.e_prior[chain] = E.prior[C + chain];
+            }
+        }
+    }
+    if (lane == 0) {                                                       // :655-656
+        E.s_acc[chain] += s_lp;
+        E.e_acc[chain] += e_lp;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_extd_end(ModelDev M, ChainState S, StepSmem L, DragStash E, int64_t n_chains, uint64_t t) {
+    extern __shared__ double sm[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t chain = blockIdx.x * (int64_t)(blockDim.x >> 5) + wid;
+    if (chain >= n_chains || !E.live[chain]) return;
+    const uint64_t gid = M.chain_id0 + (uint64_t)chain;
+    const int D = M.D, ND = M.n_der, NL = M.n_like;
+    double *base = sm + (size_t)wid * L.total;
+    double *x = base + L.x, *e_pt = base + L.e_pt;
+    double *der = base + L.der, *e_der = base + L.e_der, *ll = base + L.ll, *e_ll = base + L.e_ll;
+    for (int i = lane; i < D; i += 32) { x[i] = S.x[chain * D + i]; e_pt[i] = E.e_pt[chain * D + i]; }
+    for (int i = lane; i < ND; i += 32) { der[i] = S.der[chain * ND + i]; e_der[i] = E.e_der[chain * ND + i]; }
+    for (int i = lane; i < NL; i += 32) { ll[i] = S.ll[chain * NL + i]; e_ll[i] = E.e_ll[chain * NL + i]; }
+    ChainRegs R;
+    R.logpost = S.logpost[chain]; R.logprior = S.logprior[chain];
+    R.weight = S.weight[chain]; R.prior_rej = S.prior_rej[chain];
+    R.burn_left = S.burn_left[chain]; R.added_w = S.added_w[chain];
+    R.n_rows = S.n_rows[chain]; R.n_acc = S.n_acc[chain]; R.flags = S.flags[chain];
+    __syncwarp();
+    const double navg = (double)(1 + M.drag_steps);                        // :658
+    bool acc = metropolis_accept(M, gid, t, 0, E.e_acc[chain] / navg, E.s_acc[chain] / navg);
+    acc = __shfl_sync(FULLMASK, (int)acc, 0);
+    warp_process(M, S, chain, R, acc, x, der, ll, e_pt, e_der, e_ll, E.e_lp[chain],
+                 E.e_prior[chain], lane);                                  // :666
+    __syncwarp();
+    for (int i = lane; i < D; i += 32) S.x[chain * D + i] = x[i];
+    for (int i = lane; i < ND; i += 32) S.der[chain * ND + i] = der[i];
+    for (int i = lane; i < NL; i += 32) S.ll[chain * NL + i] = ll[i];
+    if (lane == 0) {
+        S.logpost[chain] = R.logpost; S.logprior[chain] = R.logprior;
+        S.weight[chain] = R.weight; S.prior_rej[chain] = R.prior_rej;
+        S.burn_left[chain] = R.burn_left; S.added_w[chain] = R.added_w;
+        S.n_rows[chain] = R.n_rows; S.n_acc[chain] = R.n_acc; S.flags[chain] = R.flags;
+    }
+}

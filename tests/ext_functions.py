@@ -114,3 +114,31 @@ def gaussian_pair(D):
                                              name="gaussian_mixture")],
                     proposal_cov=cov)
     return builtin, ext, mu, cov
+
+
+ROSENBROCK_CUDA = r'''
+// -scale * sum_i [100 (x_{i+1} - x_i^2)^2 + (1 - x_i)^2]  (BASELINE configs[3])
+extern "C" __device__ double rosenbrock_ext(const double *p, int n) {
+    double acc = 0.0;
+    for (int i = 0; i + 1 < n; ++i) {
+        const double t1 = p[i + 1] - p[i] * p[i], t2 = 1.0 - p[i];
+        acc += 100.0 * t1 * t1 + t2 * t2;
+    }
+    return -(1.0 / 20.0) * acc;
+}
+'''
+
+
+def rosenbrock_pair():
+    """configs[3] twice: with the built-in Rosenbrock and with the same function as an external
+    CUDA function (dragging, 10 slow + 20 fast parameters)."""
+    import copy
+
+    from cobaya_b200 import problems
+    from cobaya_b200.flatmodel import LikeSpec
+
+    p = problems.config3()
+    ext = copy.deepcopy(p.fm)
+    ext.likes = [LikeSpec.external(np.arange(ext.D), ROSENBROCK_CUDA, "rosenbrock_ext",
+                                   name=p.fm.likes[0].name)]
+    return p.fm, ext, p.start

@@ -130,9 +130,10 @@ def test_external_errors_are_loud(cuda_lib):
     with pytest.raises(EngineError, match="undefined|error"):
         _engine(model('extern "C" __device__ double f(const double *p, int n) { return zz; }'),
                 4, 1)
-    with pytest.raises(EngineError, match="dragging"):
-        e = _engine(model(ok, drag=True), 4, 1)
-        e.set_state(np.zeros((4, 2)))
+    e = _engine(model(ok, drag=True), 4, 1)   # dragging with an external function: supported
+    e.set_state(np.zeros((4, 2)))
+    e.advance(5)
+    assert not e.get_state()["flags"].any()
     # NaN from the function: the chain is flagged (the reference raises)
     nan = ('extern "C" __device__ double f(const double *p, int n) '
            '{ return p[0] > 0.05 ? nan("") : -50.0 * (p[0]*p[0] + p[1]*p[1]); }')
@@ -342,3 +343,63 @@ def test_yaml_style_lambda_strings_run_on_the_device(cuda_lib):
     np.testing.assert_allclose(rows["chi2__like2"].to_numpy(), b * b, rtol=1e-9, atol=1e-12)
     np.testing.assert_allclose(rows["chi2"].to_numpy(), rows["chi2__like1"].to_numpy()
                                + rows["chi2__like2"].to_numpy(), rtol=1e-12)
+
+
+def test_external_function_under_dragging_equals_the_builtin_kernel(cuda_lib):
+    """BASELINE configs[3] as stated -- Rosenbrock as an EXTERNAL likelihood, dragging: the
+    split-launch route (k_extd_*) walks like k_step_general on the built-in Rosenbrock (same
+    draws; the two sums differ in the order of the terms only)."""
+    from tests import ext_functions
+
+    builtin, ext, start = ext_functions.rosenbrock_pair()
+    C, n = 48, 70
+    x0 = start(C, 0)
+    a, b = _engine(builtin, C, 31), _engine(ext, C, 31)
+    a.set_kernel_policy(1)   # general kernel
+    for e in (a, b):
+        e.set_state(x0)
+        e.advance(7)
+        e.advance(n - 7)
+    sa, sb = a.get_state(), b.get_state()
+    assert not sb["flags"].any() and not sa["flags"].any()
+    np.testing.assert_array_equal(sa["n_rows"], sb["n_rows"])
+    np.testing.assert_array_equal(sa["weight"], sb["weight"])
+    assert sa["n_rows"].sum() > C * 5
+    np.testing.assert_allclose(sa["x"], sb["x"], rtol=1e-9, atol=1e-12)
+    ra, ca = a.rows_bulk()
+    rb, cb = b.rows_bulk()
+    np.testing.assert_array_equal(ra[:, 0], rb[:, 0])
+    np.testing.assert_allclose(ra, rb, rtol=1e-9, atol=1e-11)
+    # and like the fused dragging kernel (k_step_drag) on the built-in function
+    c = _engine(builtin, C, 31)
+    c.set_state(x0)
+    c.advance(n)
+    assert c.last_step_kernel() == 1
+    rc_, cc = c.rows_bulk()
+    np.testing.assert_array_equal(cc, cb)
+    np.testing.assert_allclose(rc_, rb, rtol=1e-9, atol=1e-11)
+
+
+def test_external_dragging_through_cobaya_run(cuda_lib):
+    from tests.refenv import enable_reference
+
+    enable_reference()
+    from cobaya.run import run
+
+    names = ["a", "b", "c", "d"]
+    info = {"params": {p: {"prior": {"min": -3, "max": 3}, "ref": 0.9, "proposal": 0.1}
+                       for p in names},
+            "likelihood": {"rosen": "lambda a, b, c, d: -(100*(b-a**2)**2 + (1-a)**2 + "
+                                    "100*(c-b**2)**2 + (1-b)**2 + 100*(d-c**2)**2 + (1-c)**2)/20"},
+            "sampler": {"cobaya_b200.plugin.MCMC": {
+                "chains_per_gpu": 64, "max_samples": 60, "seed": 4, "Rminus1_stop": 0.0,
+                "drag": True, "blocking": [[1, ["a", "b"]], [4, ["c", "d"]]],
+                "measure_speeds": False, "covmat": np.eye(4) * 0.01, "covmat_params": names}}}
+    _, smp = run(info)
+    assert smp._fm.drag and smp._fm.drag_interp_steps >= 1
+    rows = smp.products()["sample"]
+    a, b, c, d = (rows[p].to_numpy() for p in names)
+    want = (100 * (b - a**2) ** 2 + (1 - a) ** 2 + 100 * (c - b**2) ** 2 + (1 - b) ** 2
+            + 100 * (d - c**2) ** 2 + (1 - c) ** 2) / 10
+    np.testing.assert_allclose(rows["chi2__rosen"].to_numpy(), want, rtol=1e-9, atol=1e-9)
+    assert len(rows) >= 64 * 60
