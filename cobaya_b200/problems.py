@@ -95,5 +95,29 @@ def config3() -> Problem:
                    (2 * n_drag + 1) * 6.0 * D + 4.0 * D * D)
 
 
+ROSENBROCK_CUDA = r'''
+// -scale * sum_i [100 (x_{i+1} - x_i^2)^2 + (1 - x_i)^2]  (BASELINE configs[3])
+extern "C" __device__ double rosenbrock_ext(const double *p, int n) {
+    double acc = 0.0;
+    for (int i = 0; i + 1 < n; ++i) {
+        const double t1 = p[i + 1] - p[i] * p[i], t2 = 1.0 - p[i];
+        acc += 100.0 * t1 * t1 + t2 * t2;
+    }
+    return -(1.0 / 20.0) * acc;
+}
+'''
+
+
+def config3_external() -> Problem:
+    """configs[3] literally: the Rosenbrock function as an EXTERNAL likelihood (CUDA source
+    compiled with NVRTC at run time), dragging through the split-launch route."""
+    p = config3()
+    p.fm.likes = [LikeSpec.external(np.arange(p.fm.D), ROSENBROCK_CUDA, "rosenbrock_ext",
+                                    name=p.fm.likes[0].name)]
+    return Problem("c3x", p.workload.replace("(BASELINE", "as an external CUDA function "
+                                                          "(NVRTC), split launches (BASELINE"),
+                   p.fm, p.start, p.evals_per_proposal, p.flops_per_proposal)
+
+
 def get(key: str) -> Problem:
-    return {"c1": config1, "c2": config2, "c3": config3}[key]()
+    return {"c1": config1, "c2": config2, "c3": config3, "c3x": config3_external}[key]()

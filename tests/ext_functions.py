@@ -116,17 +116,7 @@ def gaussian_pair(D):
     return builtin, ext, mu, cov
 
 
-ROSENBROCK_CUDA = r'''
-// -scale * sum_i [100 (x_{i+1} - x_i^2)^2 + (1 - x_i)^2]  (BASELINE configs[3])
-extern "C" __device__ double rosenbrock_ext(const double *p, int n) {
-    double acc = 0.0;
-    for (int i = 0; i + 1 < n; ++i) {
-        const double t1 = p[i + 1] - p[i] * p[i], t2 = 1.0 - p[i];
-        acc += 100.0 * t1 * t1 + t2 * t2;
-    }
-    return -(1.0 / 20.0) * acc;
-}
-'''
+from cobaya_b200.problems import ROSENBROCK_CUDA  # noqa: E402
 
 
 def rosenbrock_pair():
