@@ -33,7 +33,8 @@ struct ExtSlots {
 
 __global__ void __launch_bounds__(256)
 k_ext_propose(ModelDev M, ChainState S, WindowDev W, StepSmem L, ExtStash E, int64_t n_chains,
-              uint64_t t, int first) {
+              uint64_t t_arg, const uint64_t *__restrict__ t_dev) {
+    const uint64_t t = t_dev ? *t_dev : t_arg;
     extern __shared__ double sm[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t chain = blockIdx.x * (int64_t)(blockDim.x >> 5) + wid;
@@ -50,13 +51,7 @@ k_ext_propose(ModelDev M, ChainState S, WindowDev W, StepSmem L, ExtStash E, int
     for (int i = lane; i < NV; i += 32) {
         const int64_t vv = S.vis[chain * NV + i];
         vis[i] = vv;
-        if (first) {
-            const int64_t e = (i < M.n_blocks) ? vv / M.bsize[i] : vv;
-            e0s[i] = e;
-            E.e0[chain * NV + i] = e;
-        } else {
-            e0s[i] = E.e0[chain * NV + i];
-        }
+        e0s[i] = E.e0[chain * NV + i];   // epochs at window start (k_ext_window_begin)
     }
     for (int i = lane; i < ND; i += 32) tder[i] = 0.0;
     __syncwarp();
@@ -80,7 +75,8 @@ k_ext_propose(ModelDev M, ChainState S, WindowDev W, StepSmem L, ExtStash E, int
 
 __global__ void __launch_bounds__(256)
 k_ext_accept(ModelDev M, ChainState S, StepSmem L, ExtStash E, ExtSlots X, int64_t n_chains,
-             uint64_t t) {
+             uint64_t t_arg, const uint64_t *__restrict__ t_dev) {
+    const uint64_t t = t_dev ? *t_dev : t_arg;
     extern __shared__ double sm[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t chain = blockIdx.x * (int64_t)(blockDim.x >> 5) + wid;
@@ -227,7 +223,8 @@ __device__ __forceinline__ double ext_like_total(const ExtSlots &X, const double
 
 __global__ void __launch_bounds__(256)
 k_extd_begin(ModelDev M, ChainState S, WindowDev W, StepSmem L, DragStash E, int64_t n_chains,
-             uint64_t t, int first) {
+             uint64_t t_arg, const uint64_t *__restrict__ t_dev) {
+    const uint64_t t = t_dev ? *t_dev : t_arg;
     extern __shared__ double sm[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t chain = blockIdx.x * (int64_t)(blockDim.x >> 5) + wid;
@@ -247,13 +244,7 @@ k_extd_begin(ModelDev M, ChainState S, WindowDev W, StepSmem L, DragStash E, int
     for (int i = lane; i < NV; i += 32) {
         const int64_t vv = S.vis[chain * NV + i];
         vis[i] = vv;
-        if (first) {
-            const int64_t e = (i < M.n_blocks) ? vv / M.bsize[i] : vv;
-            e0s[i] = e;
-            E.e0[chain * NV + i] = e;
-        } else {
-            e0s[i] = E.e0[chain * NV + i];
-        }
+        e0s[i] = E.e0[chain * NV + i];
     }
     for (int i = lane; i < ND; i += 32) e_der[i] = 0.0;
     __syncwarp();
@@ -304,7 +295,9 @@ __global__ void k_extd_begin_finish(ModelDev M, ChainState S, DragStash E, ExtSl
 
 __global__ void __launch_bounds__(256)
 k_extd_fast_propose(ModelDev M, ChainState S, WindowDev W, StepSmem L, DragStash E,
-                    int64_t n_chains, uint64_t t, int i_step) {
+                    int64_t n_chains, uint64_t t_arg, const uint64_t *__restrict__ t_dev,
+                    int i_step) {
+    const uint64_t t = t_dev ? *t_dev : t_arg;
     extern __shared__ double sm[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t chain = blockIdx.x * (int64_t)(blockDim.x >> 5) + wid;
@@ -365,7 +358,8 @@ k_extd_fast_propose(ModelDev M, ChainState S, WindowDev W, StepSmem L, DragStash
 
 __global__ void __launch_bounds__(256)
 k_extd_fast_accept(ModelDev M, ChainState S, DragStash E, ExtSlots X, int64_t n_chains,
-                   uint64_t t, int i_step) {
+                   uint64_t t_arg, const uint64_t *__restrict__ t_dev, int i_step) {
+    const uint64_t t = t_dev ? *t_dev : t_arg;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t chain = blockIdx.x * (int64_t)(blockDim.x >> 5) + wid;
     if (chain >= n_chains || !E.live[chain]) return;
@@ -411,7 +405,9 @@ k_extd_fast_accept(ModelDev M, ChainState S, DragStash E, ExtSlots X, int64_t n_
 }
 
 __global__ void __launch_bounds__(256)
-k_extd_end(ModelDev M, ChainState S, StepSmem L, DragStash E, int64_t n_chains, uint64_t t) {
+k_extd_end(ModelDev M, ChainState S, StepSmem L, DragStash E, int64_t n_chains, uint64_t t_arg,
+           const uint64_t *__restrict__ t_dev) {
+    const uint64_t t = t_dev ? *t_dev : t_arg;
     extern __shared__ double sm[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t chain = blockIdx.x * (int64_t)(blockDim.x >> 5) + wid;
@@ -446,3 +442,18 @@ k_extd_end(ModelDev M, ChainState S, StepSmem L, DragStash E, int64_t n_chains, 
         S.n_rows[chain] = R.n_rows; S.n_acc[chain] = R.n_acc; S.flags[chain] = R.flags;
     }
 }
+
+
+// epochs of every block at window start (the bases of a window are numbered from them) and the
+// device-side proposal counter of the captured step graph
+__global__ void k_ext_window_begin(ModelDev M, ChainState S, int64_t *__restrict__ e0,
+                                   int64_t n_chains, uint64_t *__restrict__ t_dev, uint64_t t0) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int NV = M.n_blocks + 1;
+    if (i == 0 && t_dev) *t_dev = t0;
+    if (i >= n_chains * NV) return;
+    const int b = (int)(i % NV);
+    const int64_t vv = S.vis[i];
+    e0[i] = (b < M.n_blocks) ? vv / M.bsize[b] : vv;
+}
+__global__ void k_ext_next_step(uint64_t *__restrict__ t_dev) { *t_dev += 1; }
