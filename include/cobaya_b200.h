@@ -102,7 +102,8 @@ int cb2_add_rosenbrock(cb2_engine *h, int32_t dim, const int32_t *idx, double sc
  * Metropolis proposal then runs as propose / evaluate / accept launches on the engine's stream
  * (csrc/kernels_ext.cuh), with the same proposals as every other step kernel.  CB2_EXT_DIM is
  * predefined as `dim`.  Returns -6 if NVRTC cannot be loaded, -7 on a compile error (the
- * compiler log is cb2_last_error).  Not supported together with dragging (cb2_set_state: -4). */
+ * compiler log is cb2_last_error).  With dragging the step is split at every posterior
+ * evaluation (k_extd_*). */
 int cb2_add_external_likelihood(cb2_engine *h, int32_t dim, const int32_t *idx,
                                 const char *cuda_source, const char *fn_name);
 /* External priors (cobaya/prior.py:537-577,765-772: any Python callable under `prior:`) through
