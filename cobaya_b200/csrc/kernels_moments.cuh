@@ -337,8 +337,8 @@ k_task_moments_dmma(const double *__restrict__ rows, int64_t cap, int width, int
 // sample whose cumulative weight reaches limfrac*norm (lower) or (1-limfrac)*norm (upper)
 // (getdist/chains.py `confidence`, GetDist>=1.3.1; not vendored: parity unpinned).
 // One CTA per (task, parameter): bitonic sort of (value, weight) in shared memory, inclusive
-// scan of the weights, two binary searches.  Windows longer than `cap_rows` are thinned by a
-// constant stride (documented deviation).
+// scan of the weights, two binary searches.  Windows longer than the sort size go to
+// k_task_bounds_select (below).
 __global__ void __launch_bounds__(256)
 k_task_bounds(const double *__restrict__ rows, int64_t cap, int width, int D,
               const MomentTask *__restrict__ tasks, int n_pow2, double limfrac,
@@ -403,6 +403,78 @@ k_task_bounds(const double *__restrict__ rows, int64_t cap, int width, int D,
         if (lo > n - 1) lo = n - 1;
         bounds[((size_t)task * D + par) * 2 + tid] = val[lo];
     }
+}
+
+// Windows that do not fit the shared-memory sort: the same quantile by RADIX SELECTION on the
+// order-preserving 64-bit key of the values -- 8 passes over the column, each building a
+// 256-bin histogram of the weights of the rows that match the key prefix found so far, for
+// the lower and the upper bound at once.  The answer is the smallest sample value v with
+// W(values <= v) >= target, i.e. exactly what sorting + cumulating + searchsorted returns
+// (integer-valued weights: the sums are exact in any order).  No thinning.
+__device__ __forceinline__ unsigned long long f64_order_key(double v) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double f64_from_order_key(unsigned long long k) {
+    const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+
+__global__ void __launch_bounds__(256)
+k_task_bounds_select(const double *__restrict__ rows, int64_t cap, int width, int D,
+                     const MomentTask *__restrict__ tasks, double limfrac,
+                     double *__restrict__ bounds /* [task][D][2] */) {
+    __shared__ double hist[2][256];
+    __shared__ double s_norm;
+    __shared__ unsigned long long s_prefix[2];
+    __shared__ double s_below[2];
+    const int tid = threadIdx.x;
+    const int64_t task = blockIdx.x / D;
+    const int par = blockIdx.x % D;
+    const MomentTask T = tasks[task];
+    const double *base = rows + ((size_t)T.chain * cap + T.first) * width;
+    const int64_t n = T.last - T.first;
+    // total weight
+    double wsum = 0.0;
+    for (int64_t e = tid; e < n; e += 256) wsum += base[(size_t)e * width];
+    wsum = warp_sum(wsum);
+    if (tid == 0) { s_norm = 0.0; s_prefix[0] = s_prefix[1] = 0ull; s_below[0] = s_below[1] = 0.0; }
+    __syncthreads();
+    if ((tid & 31) == 0) atomicAdd(&s_norm, wsum);
+    __syncthreads();
+    const double norm = s_norm;
+    const double target[2] = {norm * limfrac, norm * (1.0 - limfrac)};
+    for (int pass = 0; pass < 8; ++pass) {
+        const int shift = 56 - 8 * pass;
+        hist[0][tid] = 0.0;
+        hist[1][tid] = 0.0;
+        __syncthreads();
+        const unsigned long long p0 = s_prefix[0], p1 = s_prefix[1];
+        // rows whose key agrees with the prefix on the bits above `shift + 8`
+        const unsigned long long mask = (pass == 0) ? 0ull : (~0ull << (shift + 8));
+        for (int64_t e = tid; e < n; e += 256) {
+            const double *row = base + (size_t)e * width;
+            const unsigned long long k = f64_order_key(row[2 + par]);
+            const double w = row[0];
+            const int digit = (int)((k >> shift) & 0xffull);
+            if ((k & mask) == p0) atomicAdd(&hist[0][digit], w);
+            if ((k & mask) == p1) atomicAdd(&hist[1][digit], w);
+        }
+        __syncthreads();
+        if (tid < 2) {
+            double below = s_below[tid];
+            int d = 0;
+            for (; d < 255; ++d) {
+                if (below + hist[tid][d] >= target[tid]) break;
+                below += hist[tid][d];
+            }
+            s_below[tid] = below;
+            s_prefix[tid] |= (unsigned long long)d << shift;
+        }
+        __syncthreads();
+    }
+    if (tid < 2)
+        bounds[((size_t)task * D + par) * 2 + tid] = f64_from_order_key(s_prefix[tid]);
 }
 
 // out = { M, sum (low-s)[D], sum (low-s)^2[D], sum (up-s)[D], sum (up-s)^2[D] }

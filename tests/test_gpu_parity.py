@@ -621,13 +621,19 @@ def test_snapshot_resume_is_bit_exact(cuda_lib, case):
         c2.import_state(blob, rows)
 
 
-def test_confidence_bounds_match_numpy(cuda_lib):
+@pytest.mark.parametrize("n,select", [(900, False), (900, True), (90000, False)])
+def test_confidence_bounds_match_numpy(cuda_lib, monkeypatch, n, select):
     """cb2_bounds vs the weighted-quantile definition (sort, cumsum, searchsorted) restated
-    with numpy on the same rows; Rminus1_cl as mcmc.py:977-982."""
+    with numpy on the same rows; Rminus1_cl as mcmc.py:977-982.  Short windows are sorted in
+    shared memory (k_task_bounds); windows above 8192 rows -- and every window with
+    CB2_BOUNDS_SELECT=1 -- go through the radix selection (k_task_bounds_select): the same
+    numbers, no thinning."""
     from cobaya_b200.convergence import rminus1_cl_from_sums, rminus1_from_sums
     from cobaya_b200.flatmodel import FlatModel, synthetic_gaussian_cov
 
-    D, C, n = 7, 13, 900
+    if select:
+        monkeypatch.setenv("CB2_BOUNDS_SELECT", "1")
+    D, C = 7, 13
     cov = synthetic_gaussian_cov(D)
     fm = FlatModel.gaussian(np.full(D, 0.1), cov, proposal_cov=cov)
     x0 = 0.1 + np.random.default_rng(3).multivariate_normal(np.zeros(D), cov, size=C)
@@ -637,6 +643,8 @@ def test_confidence_bounds_match_numpy(cuda_lib):
     shift = np.full(D, 0.1)
     limfrac = 0.95 / 2
     bs = eng.bounds(limfrac, shift=shift)
+    if n > 20000:   # the long case really is longer than the shared-memory sort
+        assert eng.get_state()["n_rows"].min() // 2 > 8192
     lows, ups = [], []
     for c in range(C):
         rows = eng.rows(c)
