@@ -398,9 +398,14 @@ class MCMC(CovmatSampler):
         except FlatModelError as e:
             raise LoggedError(self.log, "%s", str(e)) from e
         dev = self.device if self.device is not None else int(os.environ.get("LOCAL_RANK", 0))
-        eng = Engine(fm, n_chains=1, seed=0, chain_id0=0, rows_cap=1, device=int(dev))
+        try:
+            eng = Engine(fm, n_chains=1, seed=0, chain_id0=0, rows_cap=1, device=int(dev))
+        except Exception as e:
+            raise LoggedError(self.log, "Could not start the B200 engine: %s", e) from e
         try:
             speeds = eng.measure_speeds(self._x0[:n_points], repeats=repeats)
+        except Exception as e:
+            raise LoggedError(self.log, "Measuring speeds on the device failed: %s", e) from e
         finally:
             eng.close()
         if mpi.more_than_one_process():
