@@ -670,7 +670,8 @@ def test_confidence_bounds_match_numpy(cuda_lib, monkeypatch, n, select):
     np.testing.assert_allclose(rminus1_cl_from_sums(bs, D, res["W"]), want, rtol=1e-7)
 
 
-@pytest.mark.parametrize("case", ["pc", "fast_blocks", "streamed", "dragging"])
+@pytest.mark.parametrize("case", ["pc", "fast_blocks", "streamed", "dragging",
+                                  "external_prior", "external_dragging"])
 def test_windows_chunked_over_chains_are_bit_identical(cuda_lib, case, monkeypatch):
     """cb2_advance runs a window chunk by chunk over the chains when the per-window buffers
     (Haar bases, streamed products) of all chains do not fit in device memory; the chunks see
@@ -694,6 +695,17 @@ def test_windows_chunked_over_chains_are_bit_identical(cuda_lib, case, monkeypat
         fm = FlatModel.gaussian(np.zeros(D), cov, proposal_cov=cov)
         x0 = rng.multivariate_normal(np.zeros(D), cov, size=C)
         burn = 0
+    elif case == "external_prior":   # external-function route, prior components per chain
+        from tests.test_gpu_external import flat_g9
+
+        fm, C, n, burn = flat_g9(load_golden("g9_external_prior")), 40, 120, 0
+        x0 = np.array([0.5, 0.05, 0.1]) + rng.normal(0, 0.02, (C, 3))
+    elif case == "external_dragging":   # split-launch dragging with an external Rosenbrock
+        from tests import ext_functions
+
+        _, fm, start = ext_functions.rosenbrock_pair()
+        C, n, burn = 40, 40, 0
+        x0 = start(C, 0)
     else:
         g = load_golden("g3_dragging")
         fm, C, n, burn = flat_from_golden(g), 40, 150, 0
