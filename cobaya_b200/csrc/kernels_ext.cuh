@@ -186,9 +186,13 @@ __global__ void k_ext_add(ExtSlots X, int64_t n, int NL, const double *__restric
 // posterior evaluations, each fast step depending on the accept decision of the one before,
 // so the step is split at every evaluation:
 //   k_extd_begin         slow proposal on the end point              -> 1 point per chain
-//   <user kernel>, k_extd_begin_finish   e_lp, `live`, running sums
-//   n_drag x { k_extd_fast_propose  (2 points per chain) , <user kernel>, k_extd_fast_accept }
-//   k_extd_end           final accept on the averaged log-posteriors, bookkeeping, row
+//   <user kernel>
+//   k_extd_mid(1)        e_lp, `live`, running sums; fast proposal 1   -> 2 points per chain
+//   <user kernel>
+//   k_extd_mid(i)        decision of fast step i-1; fast proposal i    (i = 2 .. n_drag)
+//   <user kernel>
+//   k_extd_last          decision of fast step n_drag; final accept on the averaged
+//                        log-posteriors, bookkeeping, row
 // following the drag branch of k_step_general statement by statement (same Philox draws,
 // cyclers and Haar bases).  External PRIORS are not supported together with dragging.
 // =========================================================================================
@@ -270,10 +274,10 @@ k_extd_begin(ModelDev M, ChainState S, WindowDev W, StepSmem L, DragStash E, int
     }
 }
 
-__global__ void k_extd_begin_finish(ModelDev M, ChainState S, DragStash E, ExtSlots X,
-                                    int64_t n_chains) {
-    const int64_t chain = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (chain >= n_chains) return;
+// e_lp of the slow proposal, `live`, running sums (one thread per chain)
+__device__ __forceinline__ bool extd_finish_body(const ModelDev &M, const ChainState &S,
+                                                 const DragStash &E, const ExtSlots &X,
+                                                 int64_t chain) {
     const int NL = M.n_like, ND = M.n_der;
     bool nan_seen = false;
     const double e_lp = ext_like_total(X, E.ext + chain * X.n, E.lp[chain], E.prior[chain],
@@ -283,7 +287,7 @@ __global__ void k_extd_begin_finish(ModelDev M, ChainState S, DragStash E, ExtSl
     E.live[chain] = live ? 1 : 0;
     if (!live) {
         S.weight[chain] += 1;   // the fast cycler is not advanced on this path
-        return;
+        return false;
     }
     E.e_lp[chain] = e_lp;
     E.e_prior[chain] = E.prior[chain];
@@ -291,17 +295,14 @@ __global__ void k_extd_begin_finish(ModelDev M, ChainState S, DragStash E, ExtSl
     for (int i = 0; i < ND; ++i) E.e_der[chain * ND + i] = E.der[chain * ND + i];
     E.s_acc[chain] = E.s_lp[chain];                                        // :595-596
     E.e_acc[chain] = e_lp;
+    return true;
 }
 
-__global__ void __launch_bounds__(256)
-k_extd_fast_propose(ModelDev M, ChainState S, WindowDev W, StepSmem L, DragStash E,
-                    int64_t n_chains, uint64_t t_arg, const uint64_t *__restrict__ t_dev,
-                    int i_step) {
-    const uint64_t t = t_dev ? *t_dev : t_arg;
-    extern __shared__ double sm[];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int64_t chain = blockIdx.x * (int64_t)(blockDim.x >> 5) + wid;
-    if (chain >= n_chains || !E.live[chain]) return;
+__device__ __forceinline__ void extd_fast_propose_body(const ModelDev &M, const ChainState &S,
+                                                       const WindowDev &W, const StepSmem &L,
+                                                       const DragStash &E, int64_t n_chains,
+                                                       int64_t chain, uint64_t t, int i_step,
+                                                       double *sm, int lane, int wid) {
     const uint64_t gid = M.chain_id0 + (uint64_t)chain;
     const int D = M.D, ND = M.n_der, NL = M.n_like, NV = M.n_blocks + 1;
     const int64_t C = n_chains;
@@ -356,13 +357,10 @@ k_extd_fast_propose(ModelDev M, ChainState S, WindowDev W, StepSmem L, DragStash
     }
 }
 
-__global__ void __launch_bounds__(256)
-k_extd_fast_accept(ModelDev M, ChainState S, DragStash E, ExtSlots X, int64_t n_chains,
-                   uint64_t t_arg, const uint64_t *__restrict__ t_dev, int i_step) {
-    const uint64_t t = t_dev ? *t_dev : t_arg;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int64_t chain = blockIdx.x * (int64_t)(blockDim.x >> 5) + wid;
-    if (chain >= n_chains || !E.live[chain]) return;
+__device__ __forceinline__ void extd_fast_accept_body(const ModelDev &M, const ChainState &S,
+                                                      const DragStash &E, const ExtSlots &X,
+                                                      int64_t n_chains, int64_t chain,
+                                                      uint64_t t, int i_step, int lane) {
     const uint64_t gid = M.chain_id0 + (uint64_t)chain;
     const int D = M.D, ND = M.n_der, NL = M.n_like;
     const int64_t C = n_chains;
@@ -375,6 +373,7 @@ k_extd_fast_accept(ModelDev M, ChainState S, DragStash E, ExtSlots X, int64_t n_
                                E.ll + (C + chain) * NL, nan_seen);
         if (nan_seen) S.flags[chain] |= CB2_FLAG_INTERNAL;
     }
+    __syncwarp();   // the external log-likelihoods lane 0 wrote into E.ll are read by all lanes
     ps_lp = __shfl_sync(FULLMASK, ps_lp, 0);
     pe_lp = __shfl_sync(FULLMASK, pe_lp, 0);
     double s_lp = E.s_lp[chain], e_lp = E.e_lp[chain];
@@ -404,14 +403,10 @@ k_extd_fast_accept(ModelDev M, ChainState S, DragStash E, ExtSlots X, int64_t n_
     }
 }
 
-__global__ void __launch_bounds__(256)
-k_extd_end(ModelDev M, ChainState S, StepSmem L, DragStash E, int64_t n_chains, uint64_t t_arg,
-           const uint64_t *__restrict__ t_dev) {
-    const uint64_t t = t_dev ? *t_dev : t_arg;
-    extern __shared__ double sm[];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int64_t chain = blockIdx.x * (int64_t)(blockDim.x >> 5) + wid;
-    if (chain >= n_chains || !E.live[chain]) return;
+__device__ __forceinline__ void extd_end_body(const ModelDev &M, const ChainState &S,
+                                              const StepSmem &L, const DragStash &E,
+                                              int64_t chain, uint64_t t, double *sm, int lane,
+                                              int wid) {
     const uint64_t gid = M.chain_id0 + (uint64_t)chain;
     const int D = M.D, ND = M.n_der, NL = M.n_like;
     double *base = sm + (size_t)wid * L.total;
@@ -443,6 +438,53 @@ k_extd_end(ModelDev M, ChainState S, StepSmem L, DragStash E, int64_t n_chains, 
     }
 }
 
+
+// The launches of the fast steps, merged pairwise: the decision of fast step i-1 (or, for
+// i = 1, the evaluation of the slow proposal) and the proposal of fast step i need the same
+// warp and the same stash, so they share a kernel; the last one closes the step.
+//   k_extd_begin, U, k_extd_mid(1), U, k_extd_mid(2), U, ..., k_extd_mid(n_drag), U, k_extd_last
+__global__ void __launch_bounds__(256)
+k_extd_mid(ModelDev M, ChainState S, WindowDev W, StepSmem L, DragStash E, ExtSlots X,
+           int64_t n_chains, uint64_t t_arg, const uint64_t *__restrict__ t_dev, int i_step) {
+    const uint64_t t = t_dev ? *t_dev : t_arg;
+    extern __shared__ double sm[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t chain = blockIdx.x * (int64_t)(blockDim.x >> 5) + wid;
+    if (chain >= n_chains) return;
+    if (i_step == 1) {
+        int live = 0;
+        if (lane == 0) live = extd_finish_body(M, S, E, X, chain) ? 1 : 0;
+        live = __shfl_sync(FULLMASK, live, 0);
+        __syncwarp();
+        if (!live) return;
+    } else {
+        if (!E.live[chain]) return;
+        extd_fast_accept_body(M, S, E, X, n_chains, chain, t, i_step - 1, lane);
+        __syncwarp();
+    }
+    extd_fast_propose_body(M, S, W, L, E, n_chains, chain, t, i_step, sm, lane, wid);
+}
+
+__global__ void __launch_bounds__(256)
+k_extd_last(ModelDev M, ChainState S, StepSmem L, DragStash E, ExtSlots X, int64_t n_chains,
+            uint64_t t_arg, const uint64_t *__restrict__ t_dev) {
+    const uint64_t t = t_dev ? *t_dev : t_arg;
+    extern __shared__ double sm[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t chain = blockIdx.x * (int64_t)(blockDim.x >> 5) + wid;
+    if (chain >= n_chains) return;
+    if (M.drag_steps >= 1) {
+        if (!E.live[chain]) return;
+        extd_fast_accept_body(M, S, E, X, n_chains, chain, t, M.drag_steps, lane);
+    } else {
+        int live = 0;
+        if (lane == 0) live = extd_finish_body(M, S, E, X, chain) ? 1 : 0;
+        live = __shfl_sync(FULLMASK, live, 0);
+        if (!live) return;
+    }
+    __syncwarp();
+    extd_end_body(M, S, L, E, chain, t, sm, lane, wid);
+}
 
 // epochs of every block at window start (the bases of a window are numbered from them) and the
 // device-side proposal counter of the captured step graph
