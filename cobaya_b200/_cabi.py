@@ -31,7 +31,7 @@ EXPORTS = [
     "cb2_host_alloc", "cb2_host_free", "cb2_grow_rows", "cb2_mem_info", "cb2_load_rows_bulk", "cb2_window_counts", "cb2_debug_counters",
     "cb2_checkpoint_device", "cb2_checkpoint_cov", "cb2_adopt_proposal", "cb2_get_proposal",
     "cb2_add_external_likelihood", "cb2_check_external_source", "cb2_measure_speeds",
-    "cb2_add_external_prior",
+    "cb2_add_external_prior", "cb2_check_external_fused", "cb2_ext_route_counts",
 ]
 
 
@@ -80,6 +80,8 @@ def load():
     L.cb2_add_external_likelihood.argtypes = [vp, i32, vp, C.c_char_p, C.c_char_p]
     L.cb2_add_external_prior.argtypes = [vp, i32, vp, C.c_char_p, C.c_char_p]
     L.cb2_check_external_source.argtypes = [C.c_char_p, C.c_char_p, i32, C.c_char_p, i64]
+    L.cb2_check_external_fused.argtypes = [C.c_char_p, C.c_char_p, i32, C.c_char_p, i64]
+    L.cb2_ext_route_counts.argtypes = [vp, vp]
     L.cb2_set_blocking.argtypes = [vp, i32, vp, vp, vp, i32, i32, i32]
     L.cb2_set_proposal.argtypes = [vp, vp, dbl]
     L.cb2_set_options.argtypes = [vp, dbl, i64, i64, i32, i64]

@@ -7,11 +7,26 @@
 // thread can produce any draw and the CPU oracle consumes identical values
 // (layout: DESIGN.md section 4).
 #pragma once
+#ifdef __CUDACC_RTC__
+// run-time compilation (ext_functor.inl: the general step kernel with the user's functions
+// inlined): NVRTC has no host headers
+typedef signed char int8_t;
+typedef unsigned char uint8_t;
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+#define CUDART_INF (__longlong_as_double(0x7ff0000000000000LL))
+#define CUDART_NAN (__longlong_as_double(0xfff8000000000000LL))
+#define CUDART_PI 3.1415926535897931e+0
+#include "cobaya_b200.h"
+#else
 #include <cstdint>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
 #include "../../include/cobaya_b200.h"
+#endif
 
 #define CB2_TAG_STEP 0u
 #define CB2_TAG_ACCEPT 1u

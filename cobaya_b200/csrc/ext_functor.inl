@@ -4,6 +4,9 @@
 // (cudaLibraryLoadData / cudaLibraryGetKernel) and launched with cudaLaunchKernel.
 #include <dlfcn.h>
 
+#include <map>
+#include <mutex>
+
 namespace {
 
 typedef struct _nvrtcProgram *nvrtcProgram_t;
@@ -127,6 +130,97 @@ int ext_compile(const char *source, const char *fn, int d, const int32_t *idx,
         return -7;
     }
     api.DestroyProgram(&prog);
+    return 0;
+}
+
+// ---- the general step kernel with the user's functions inlined ----------------------------
+#include "embedded_sources.inc"
+
+struct FusedUser {
+    std::string source, name;
+    int dim;
+    int user_id;   // index the kernel dispatches on (LikeDev.n_modes of a kind-3 likelihood)
+};
+
+// k_step_general (csrc/kernels_general.cuh, compiled again from the copy embedded in the
+// library) + the user's likelihood functions in ONE translation unit: the functions are
+// inlined where warp_logpost evaluates a kind-3 likelihood, so a whole window -- Metropolis or
+// dragging -- is one launch, as for the built-in likelihoods.
+std::string fused_translation_unit(const std::vector<FusedUser> &users) {
+    std::string s;
+    s += "#define CB2_NVRTC_USER 1\n#include \"kernels_general.cuh\"\n";
+    for (const FusedUser &u : users) {
+        s += "#undef CB2_EXT_DIM\n#define CB2_EXT_DIM " + std::to_string(u.dim) + "\n";
+        s += "namespace cb2_user_" + std::to_string(u.user_id) + " {\n";
+        s += "#line 1 \"external_" + u.name + ".cu\"\n";
+        s += u.source;
+        s += "\n}\n";
+    }
+    s += "#line 1 \"cb2_user_dispatch.cu\"\n";
+    s += "__device__ double cb2_user_like(int user_id, const double *p, int n) {\n"
+         "    switch (user_id) {\n";
+    for (const FusedUser &u : users)
+        s += "        case " + std::to_string(u.user_id) + ": return cb2_user_" +
+             std::to_string(u.user_id) + "::" + u.name + "(p, n);\n";
+    s += "    }\n    return 0.0;\n}\n";
+    s += "extern \"C\" __global__ void __launch_bounds__(256) cb2_step_user(ModelDev M, "
+         "ChainState S, WindowDev W,\n        StepSmem L, long long n_chains, "
+         "unsigned long long t0, int n_steps) {\n"
+         "    step_general_body(M, S, W, L, n_chains, t0, n_steps);\n}\n";
+    return s;
+}
+
+int fused_compile(const std::vector<FusedUser> &users, std::vector<char> &image,
+                  std::string &log) {
+    NvrtcApi &api = nvrtc_api();
+    if (!api.lib) { log = api.error; return -6; }
+    const std::string tu = fused_translation_unit(users);
+    // engines of one process that share their functions share the compiled image (the compile
+    // takes ~6 s: the whole general step kernel)
+    static std::map<std::string, std::vector<char>> cache;
+    static std::mutex cache_mutex;
+    {
+        std::lock_guard<std::mutex> g(cache_mutex);
+        auto it = cache.find(tu);
+        if (it != cache.end()) { image = it->second; return 0; }
+    }
+    const int nh = (int)(sizeof(cb2_embedded_names) / sizeof(cb2_embedded_names[0]));
+    nvrtcProgram_t prog = nullptr;
+    int rc = api.CreateProgram(&prog, tu.c_str(), "cb2_step_user.cu", nh, cb2_embedded_sources,
+                               cb2_embedded_names);
+    if (rc) { log = std::string("nvrtcCreateProgram: ") + api.GetErrorString(rc); return -6; }
+    const char *opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "--fmad=true",
+                          "-default-device", "-lineinfo"};
+    rc = api.CompileProgram(prog, 5, opts);
+    size_t ls = 0;
+    api.GetProgramLogSize(prog, &ls);
+    if (ls > 1) {
+        std::vector<char> buf(ls + 1, 0);
+        api.GetProgramLog(prog, buf.data());
+        log = buf.data();
+    }
+    if (rc) {
+        if (log.empty()) log = api.GetErrorString(rc);
+        api.DestroyProgram(&prog);
+        return -7;
+    }
+    size_t n = 0;
+    if (api.GetCUBINSize(prog, &n) == 0 && n > 0) {
+        image.resize(n);
+        api.GetCUBIN(prog, image.data());
+    } else if (api.GetPTXSize(prog, &n) == 0 && n > 0) {
+        image.resize(n);
+        api.GetPTX(prog, image.data());
+    } else {
+        log += " (no device code produced)";
+        api.DestroyProgram(&prog);
+        return -7;
+    }
+    api.DestroyProgram(&prog);
+    {
+        std::lock_guard<std::mutex> g(cache_mutex);
+        cache[tu] = image;
+    }
     return 0;
 }
 

@@ -7,6 +7,7 @@
 // CB2_FLAG_INTERNAL: include/cobaya_b200.h
 #define FULLMASK 0xffffffffu
 
+#ifndef CB2_NVRTC_USER   // host-launched kernels the run-time compiled unit does not need
 // ------------------------------------------------------------------ cycler tapes
 // CyclicIndexRandomizer.next (proposal.py:46-55) for visits [i0, i0+len) of one
 // cycler: tape[chain*len + v] = indices[(i0+v) % n] of cycle (i0+v)/n, where the
@@ -139,6 +140,7 @@ __global__ void k_basis_general(uint32_t key0, uint32_t key1, uint64_t chain_id0
     }
 }
 
+#endif  // CB2_NVRTC_USER
 // ------------------------------------------------------------------ log-posterior
 // Model.logposterior (model.py:579-678) for the recognised model set, evaluated by
 // one warp on a point staged in shared memory.  Returns logpost (warp-uniform).
@@ -146,6 +148,9 @@ __global__ void k_basis_general(uint32_t key0, uint32_t key1, uint64_t chain_id0
 //   like  : GaussianMixture.logp (gaussian_mixture.py:138-163) in the Cholesky form
 //           -1/2 (d log 2pi + log|S_k| + |L_k^-1 (x - mu_k)|^2), logsumexp over modes;
 //           derived = L_k^-1 (x - mu_k) (:146-156)
+#ifdef CB2_NVRTC_USER
+__device__ double cb2_user_like(int user_id, const double *p, int n);  // generated (ext_functor.inl)
+#endif
 // `only` >= 0: that likelihood component alone, -2: none (cb2_measure_speeds); -1: all.
 __device__ __forceinline__ double warp_logpost(const ModelDev &M, const double *xs,
                                                double &lprior, double *ll, double *der,
@@ -220,7 +225,23 @@ __device__ __forceinline__ double warp_logpost(const ModelDev &M, const double *
         } else if (L.kind == 2) {
             val = L.scale;  // `one` (likelihoods/one/one.py:26-28)
         } else if (L.kind == 3) {
+#ifdef CB2_NVRTC_USER
+            // run-time compiled kernel: the user's function is part of this translation unit
+            // (ext_functor.inl); its inputs are gathered into the warp's scratch vector
+            __syncwarp();
+            for (int i = lane; i < d; i += 32) z[i] = xs[idx[i]];
+            __syncwarp();
+            val = 0.0;
+            if (lane == 0) val = cb2_user_like(L.n_modes, z, d);
+            val = __shfl_sync(FULLMASK, val, 0);
+            if (val != val) {   // NaN (the reference raises): the slot keeps it for
+                if (lane == 0) ll[l] = val;   // user_nan_check, the point is rejected
+                total += -CUDART_INF;
+                continue;
+            }
+#else
             val = 0.0;      // external function: added by its own kernel (kernels_ext.cuh)
+#endif
         } else {
             double acc = 0.0;
             for (int i = lane; i + 1 < d; i += 32) {
@@ -238,6 +259,17 @@ __device__ __forceinline__ double warp_logpost(const ModelDev &M, const double *
     return total;
 }
 
+// a NaN from a user function inlined by run-time compilation: flag the chain (the split route
+// does the same in k_ext_accept)
+__device__ __forceinline__ void user_nan_check(const ModelDev &M, const double *ll,
+                                               uint32_t &flags) {
+#ifdef CB2_NVRTC_USER
+    for (int l = 0; l < M.n_like; ++l)
+        if (M.likes[l].kind == 3 && ll[l] != ll[l]) flags |= CB2_FLAG_INTERNAL;
+#endif
+}
+
+#ifndef CB2_NVRTC_USER
 // parity entry point (cb2_logpost): one warp per point
 __global__ void k_logpost(ModelDev M, const double *__restrict__ X, int64_t n,
                           double *__restrict__ logpost, double *__restrict__ logprior,
@@ -266,6 +298,8 @@ __global__ void k_logpost(ModelDev M, const double *__restrict__ X, int64_t n,
     if (derived)
         for (int i = lane; i < M.n_der; i += 32) derived[p * M.n_der + i] = der[i];
 }
+
+#endif  // CB2_NVRTC_USER
 
 // ------------------------------------------------------------------ chain state
 struct ChainState {
@@ -439,9 +473,9 @@ __device__ __forceinline__ void warp_process(const ModelDev &M, const ChainState
 
 // The hot loop (MCMC.run, mcmc.py:470-472): every chain makes n_steps proposals,
 // proposal counters t0 .. t0+n_steps-1.  One warp per chain.
-__global__ void __launch_bounds__(256)
-k_step_general(ModelDev M, ChainState S, WindowDev W, StepSmem L, int64_t n_chains,
-               uint64_t t0, int n_steps) {
+__device__ __forceinline__ void step_general_body(const ModelDev &M, const ChainState &S,
+                                                  const WindowDev &W, const StepSmem &L,
+                                                  int64_t n_chains, uint64_t t0, int n_steps) {
     extern __shared__ double sm[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t chain = blockIdx.x * (int64_t)(blockDim.x >> 5) + wid;
@@ -485,6 +519,7 @@ k_step_general(ModelDev M, ChainState S, WindowDev W, StepSmem L, int64_t n_chai
             warp_reduce_periodic(M, trial, lane);                      // :558
             double tprior;
             double tl = warp_logpost(M, trial, tprior, tll, tder, z, lpk, lane);  // :559
+            if (tprior != -CUDART_INF) user_nan_check(M, tll, R.flags);
             bool acc = metropolis_accept(M, gid, t, 0, tl, R.logpost);  // :560
             acc = __shfl_sync(FULLMASK, (int)acc, 0);
             warp_process(M, S, chain, R, acc, x, der, ll, trial, tder, tll, tl, tprior,
@@ -510,6 +545,7 @@ k_step_general(ModelDev M, ChainState S, WindowDev W, StepSmem L, int64_t n_chai
             warp_reduce_periodic(M, e_pt, lane);                       // :583
             double e_prior;
             double e_lp = warp_logpost(M, e_pt, e_prior, e_ll, e_der, z, lpk, lane);  // :589
+            if (e_prior != -CUDART_INF) user_nan_check(M, e_ll, R.flags);
             if (e_lp == -CUDART_INF) {                                 // :590-592
                 R.weight += 1;  // the fast cycler is not advanced on this path
                 continue;
@@ -537,11 +573,13 @@ k_step_general(ModelDev M, ChainState S, WindowDev W, StepSmem L, int64_t n_chai
                 __syncwarp();
                 double ps_prior;
                 double ps_lp = warp_logpost(M, ps, ps_prior, tmp_ll, nullptr, z, lpk, lane);
+                if (ps_prior != -CUDART_INF) user_nan_check(M, tmp_ll, R.flags);
                 if (ps_lp != -CUDART_INF) {                            // :621
                     for (int k = lane; k < D; k += 32) pe[k] = e_pt[k] + delta[k];  // :622
                     __syncwarp();
                     double pe_prior;
                     double pe_lp = warp_logpost(M, pe, pe_prior, pe_ll, pe_der, z, lpk, lane);
+                    if (pe_prior != -CUDART_INF) user_nan_check(M, pe_ll, R.flags);
                     if (pe_lp != -CUDART_INF) {                        // :628
                         double frac = (double)i / (double)(1 + nds);   // :630
                         double p_int = (1 - frac) * ps_lp + frac * pe_lp;
@@ -579,3 +617,11 @@ k_step_general(ModelDev M, ChainState S, WindowDev W, StepSmem L, int64_t n_chai
         S.n_rows[chain] = R.n_rows; S.n_acc[chain] = R.n_acc; S.flags[chain] = R.flags;
     }
 }
+
+#ifndef CB2_NVRTC_USER
+__global__ void __launch_bounds__(256)
+k_step_general(ModelDev M, ChainState S, WindowDev W, StepSmem L, int64_t n_chains,
+               uint64_t t0, int n_steps) {
+    step_general_body(M, S, W, L, n_chains, t0, n_steps);
+}
+#endif

@@ -406,6 +406,13 @@ class Engine:
                  "chunked_over_chains"]
         return {k: int(x) for k, x in zip(names, v)}
 
+    def ext_route_counts(self):
+        """Route of the windows of a model with external functions (cb2_ext_route_counts)."""
+        v = np.zeros(4, np.int64)
+        self._ck(self.lib.cb2_ext_route_counts(self.h, _cabi.ptr(v)))
+        return dict(fused_windows=int(v[0]), graph_replays=int(v[1]),
+                    fused_loaded=bool(v[2]), fused_failed=bool(v[3]))
+
     def debug_message(self):
         return self.lib.cb2_debug_message(self.h).decode()
 

@@ -17,7 +17,9 @@
 #ifndef COBAYA_B200_H
 #define COBAYA_B200_H
 
+#ifndef __CUDACC_RTC__
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -116,6 +118,16 @@ int cb2_add_external_prior(cb2_engine *h, int32_t dim, const int32_t *idx,
 /* Compile check of such a source without an engine or a GPU; the compiler log goes to `log`. */
 int cb2_check_external_source(const char *cuda_source, const char *fn_name, int32_t dim,
                               char *log, int64_t log_cap);
+/* The same check for the FUSED form: when a model has external likelihood functions (and no
+ * external prior), the engine recompiles its general step kernel (csrc/kernels_general.cuh, a
+ * copy of which is embedded in the library) with the functions inlined, and a whole window --
+ * Metropolis or dragging -- is one launch; CB2_EXT_FUSED=0 keeps the split launches. */
+int cb2_check_external_fused(const char *cuda_source, const char *fn_name, int32_t dim,
+                             char *log, int64_t log_cap);
+/* Instrumentation: out = { windows run on the fused (run-time compiled) step kernel, proposals
+ * replayed as a CUDA graph on the split route, fused kernel loaded (0/1), fused compile
+ * failed (0/1) }. */
+int cb2_ext_route_counts(cb2_engine *h, int64_t out[4]);
 /* `one` (cobaya/likelihoods/one/one.py:26-28): a likelihood with no input parameters
  * whose log-value is a constant (0 for `one`); keeps its chi2__<name> column. */
 int cb2_add_constant(cb2_engine *h, double value);

@@ -61,8 +61,25 @@ def test_external_logposterior_matches_reference_known_answers(cuda_lib):
     np.testing.assert_allclose(ll[finite], kat[finite, 2:], rtol=1e-12, atol=1e-13)
 
 
+@pytest.fixture(params=["split", "fused"])
+def route(request, monkeypatch):
+    """The two device routes of external likelihood functions: split launches around the user
+    kernels (CB2_EXT_FUSED=0) and the general step kernel recompiled with the functions inlined
+    (CB2_EXT_FUSED=1; the default for runs of >= 1024 chains)."""
+    monkeypatch.setenv("CB2_EXT_FUSED", "1" if request.param == "fused" else "0")
+    return request.param
+
+
+def _check_route(eng, route):
+    rc = eng.ext_route_counts()
+    if route == "fused":
+        assert rc["fused_loaded"] and rc["fused_windows"] > 0 and not rc["fused_failed"], rc
+    else:
+        assert rc["fused_windows"] == 0 and not rc["fused_loaded"], rc
+
+
 @pytest.mark.parametrize("cid", [0, 6])
-def test_external_chain_matches_reference_golden(cuda_lib, cid):
+def test_external_chain_matches_reference_golden(cuda_lib, cid, route):
     g = load_golden("g8_external")
     fm = flat_g8(g)
     n = int(g["n_proposals"])
@@ -82,9 +99,10 @@ def test_external_chain_matches_reference_golden(cuda_lib, cid):
     np.testing.assert_allclose(rows, ref, rtol=RTOL, atol=ATOL)
     np.testing.assert_allclose(st["x"][0], g[f"final_x_{cid}"], rtol=RTOL, atol=ATOL)
     assert st["weight"][0] == int(g[f"final_weight_{cid}"])
+    _check_route(eng, route)
 
 
-def test_external_route_equals_builtin_kernels_on_the_same_function(cuda_lib):
+def test_external_route_equals_builtin_kernels_on_the_same_function(cuda_lib, route):
     """A Gaussian written as an external CUDA function walks like the built-in Gaussian on the
     general kernel (same Philox draws; the log-likelihoods differ in summation order only)."""
     from cobaya_b200.flatmodel import FlatModel, LikeSpec, synthetic_gaussian_cov
@@ -111,9 +129,10 @@ def test_external_route_equals_builtin_kernels_on_the_same_function(cuda_lib):
     np.testing.assert_allclose(ra, rb, rtol=1e-10, atol=1e-12)
     # the checkpoint statistics see the same chains
     np.testing.assert_allclose(a.moments(), b.moments(), rtol=1e-9, atol=1e-14)
+    _check_route(b, route)
 
 
-def test_external_errors_are_loud(cuda_lib):
+def test_external_errors_are_loud(cuda_lib, route):
     from cobaya_b200.engine import EngineError
     from cobaya_b200.flatmodel import FlatModel, LikeSpec
 
@@ -345,7 +364,7 @@ def test_yaml_style_lambda_strings_run_on_the_device(cuda_lib):
                                + rows["chi2__like2"].to_numpy(), rtol=1e-12)
 
 
-def test_external_function_under_dragging_equals_the_builtin_kernel(cuda_lib):
+def test_external_function_under_dragging_equals_the_builtin_kernel(cuda_lib, route):
     """BASELINE configs[3] as stated -- Rosenbrock as an EXTERNAL likelihood, dragging: the
     split-launch route (k_extd_*) walks like k_step_general on the built-in Rosenbrock (same
     draws; the two sums differ in the order of the terms only)."""
@@ -370,6 +389,7 @@ def test_external_function_under_dragging_equals_the_builtin_kernel(cuda_lib):
     rb, cb = b.rows_bulk()
     np.testing.assert_array_equal(ra[:, 0], rb[:, 0])
     np.testing.assert_allclose(ra, rb, rtol=1e-9, atol=1e-11)
+    _check_route(b, route)
     # and like the fused dragging kernel (k_step_drag) on the built-in function
     c = _engine(builtin, C, 31)
     c.set_state(x0)

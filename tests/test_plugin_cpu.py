@@ -496,3 +496,24 @@ def test_lambda_strings_are_translated_to_cuda_on_the_cpu():
     info["likelihood"]["like1"] = "lambda a, b: float(np.linalg.norm([a, b]))"
     with pytest.raises(UnsupportedModelError, match="cannot be evaluated on the device"):
         lower_model(get_model(info), proposal_cov=np.eye(2))
+
+
+def test_the_fused_external_kernel_compiles_without_a_gpu():
+    """The general step kernel is recompiled at run time with the user's likelihood functions
+    inlined (csrc/ext_functor.inl, from the copy of the kernel sources embedded in the library):
+    the NVRTC compile needs no device."""
+    import ctypes as C
+
+    from cobaya_b200 import _cabi
+    from cobaya_b200.functor import cuda_from_lambda
+    from cobaya_b200.problems import ROSENBROCK_CUDA
+
+    lib = _cabi.load()
+    log = C.create_string_buffer(1 << 14)
+    assert lib.cb2_check_external_fused(ROSENBROCK_CUDA.encode(), b"rosenbrock_ext", 30, log,
+                                        len(log)) == 0, log.value.decode()
+    src, entry, _ = cuda_from_lambda("lambda a, b: -a**2 - np.log1p(b * b)", "f")
+    assert lib.cb2_check_external_fused(src.encode(), entry.encode(), 2, log, len(log)) == 0
+    bad = 'extern "C" __device__ double f(const double *p, int n) { return nope; }'
+    assert lib.cb2_check_external_fused(bad.encode(), b"f", 2, log, len(log)) == -7
+    assert "nope" in log.value.decode()
