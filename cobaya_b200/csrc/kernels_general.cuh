@@ -155,7 +155,7 @@ __device__ double cb2_user_like(int user_id, const double *p, int n);  // genera
 __device__ __forceinline__ double warp_logpost(const ModelDev &M, const double *xs,
                                                double &lprior, double *ll, double *der,
                                                double *z, double *lpk, int lane,
-                                               int only = -1) {
+                                               int only = -1, bool skip_user = false) {
     const int D = M.D;
     bool bad = false;
     for (int i = lane; i < D; i += 32) {
@@ -224,6 +224,8 @@ __device__ __forceinline__ double warp_logpost(const ModelDev &M, const double *
             }
         } else if (L.kind == 2) {
             val = L.scale;  // `one` (likelihoods/one/one.py:26-28)
+        } else if (L.kind == 3 && skip_user) {
+            val = 0.0;      // added by user_pair_eval (dragging: two points at once)
         } else if (L.kind == 3) {
 #ifdef CB2_NVRTC_USER
             // run-time compiled kernel: the user's function is part of this translation unit
@@ -270,6 +272,41 @@ __device__ __forceinline__ void user_nan_check(const ModelDev &M, const double *
 }
 
 #ifndef CB2_NVRTC_USER
+#ifdef CB2_NVRTC_USER
+// Dragging evaluates the moved start and end point of a fast step together: the user's
+// functions of both points run side by side on lanes 0 and 1 (warp_logpost was called with
+// skip_user for both).  lp_a / lp_b: log-posteriors without the external terms (-inf: the
+// point is out and is not evaluated); za / zb: scratch vectors of max(dim) doubles.
+__device__ __forceinline__ void user_pair_eval(const ModelDev &M, const double *pa,
+                                               const double *pb, double *za, double *zb,
+                                               double *lla, double *llb, double &lp_a,
+                                               double &lp_b, uint32_t &flags, int lane) {
+    const bool ok_a = lp_a != -CUDART_INF, ok_b = lp_b != -CUDART_INF;
+    for (int l = 0; l < M.n_like; ++l) {
+        const LikeDev &L = M.likes[l];
+        if (L.kind != 3) continue;
+        const int d = L.dim;
+        const int32_t *idx = M.ipool + L.idx_off;
+        __syncwarp();
+        for (int i = lane; i < d; i += 32) { za[i] = pa[idx[i]]; zb[i] = pb[idx[i]]; }
+        __syncwarp();
+        double val = 0.0;
+        if (lane == 0 && ok_a) val = cb2_user_like(L.n_modes, za, d);
+        if (lane == 1 && ok_b) val = cb2_user_like(L.n_modes, zb, d);
+        const double va = __shfl_sync(FULLMASK, val, 0), vb = __shfl_sync(FULLMASK, val, 1);
+        if (ok_a) {
+            if (va != va) { flags |= CB2_FLAG_INTERNAL; lp_a = -CUDART_INF; }
+            else { if (lane == 0) lla[l] = va; if (lp_a != -CUDART_INF) lp_a += va; }
+        }
+        if (ok_b) {
+            if (vb != vb) { flags |= CB2_FLAG_INTERNAL; lp_b = -CUDART_INF; }
+            else { if (lane == 0) llb[l] = vb; if (lp_b != -CUDART_INF) lp_b += vb; }
+        }
+    }
+    __syncwarp();
+}
+#endif
+
 // parity entry point (cb2_logpost): one warp per point
 __global__ void k_logpost(ModelDev M, const double *__restrict__ X, int64_t n,
                           double *__restrict__ logpost, double *__restrict__ logprior,
@@ -572,15 +609,29 @@ __device__ __forceinline__ void step_general_body(const ModelDev &M, const Chain
                 for (int k = lane; k < D; k += 32) ps[k] = s_pt[k] + delta[k];  // :610
                 __syncwarp();
                 double ps_prior;
+#ifdef CB2_NVRTC_USER
+                // built-in parts of both points, then the user's functions of the two points
+                // side by side (lanes 0 and 1); delta is free once ps and pe exist
+                for (int k = lane; k < D; k += 32) pe[k] = e_pt[k] + delta[k];      // :622
+                __syncwarp();
+                double pe_prior;
+                double ps_lp = warp_logpost(M, ps, ps_prior, tmp_ll, nullptr, z, lpk, lane, -1, true);
+                double pe_lp = -CUDART_INF;
+                pe_prior = -CUDART_INF;
+                if (ps_lp != -CUDART_INF)
+                    pe_lp = warp_logpost(M, pe, pe_prior, pe_ll, pe_der, z, lpk, lane, -1, true);
+                user_pair_eval(M, ps, pe, z, delta, tmp_ll, pe_ll, ps_lp, pe_lp, R.flags, lane);
+                if (ps_lp != -CUDART_INF) {                            // :621
+                    if (pe_lp != -CUDART_INF) {                        // :628
+#else
                 double ps_lp = warp_logpost(M, ps, ps_prior, tmp_ll, nullptr, z, lpk, lane);
-                if (ps_prior != -CUDART_INF) user_nan_check(M, tmp_ll, R.flags);
                 if (ps_lp != -CUDART_INF) {                            // :621
                     for (int k = lane; k < D; k += 32) pe[k] = e_pt[k] + delta[k];  // :622
                     __syncwarp();
                     double pe_prior;
                     double pe_lp = warp_logpost(M, pe, pe_prior, pe_ll, pe_der, z, lpk, lane);
-                    if (pe_prior != -CUDART_INF) user_nan_check(M, pe_ll, R.flags);
                     if (pe_lp != -CUDART_INF) {                        // :628
+#endif
                         double frac = (double)i / (double)(1 + nds);   // :630
                         double p_int = (1 - frac) * ps_lp + frac * pe_lp;
                         double c_int = (1 - frac) * s_lp + frac * e_lp;
