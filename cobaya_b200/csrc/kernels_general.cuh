@@ -271,7 +271,6 @@ __device__ __forceinline__ void user_nan_check(const ModelDev &M, const double *
 #endif
 }
 
-#ifndef CB2_NVRTC_USER
 #ifdef CB2_NVRTC_USER
 // Dragging evaluates the moved start and end point of a fast step together: the user's
 // functions of both points run side by side on lanes 0 and 1 (warp_logpost was called with
@@ -307,6 +306,7 @@ __device__ __forceinline__ void user_pair_eval(const ModelDev &M, const double *
 }
 #endif
 
+#ifndef CB2_NVRTC_USER
 // parity entry point (cb2_logpost): one warp per point
 __global__ void k_logpost(ModelDev M, const double *__restrict__ X, int64_t n,
                           double *__restrict__ logpost, double *__restrict__ logprior,
