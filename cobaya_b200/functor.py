@@ -102,6 +102,7 @@ _MODULES = {"np", "numpy", "math"}
 class _Lambda2Cuda(ast.NodeVisitor):
     def __init__(self, args):
         self.args = {a: i for i, a in enumerate(args)}
+        self.in_test = 0   # inside the condition of a conditional expression
 
     def bad(self, node, why):
         raise DeviceFunctionError(f"cannot translate to CUDA: {why} "
@@ -160,14 +161,24 @@ class _Lambda2Cuda(ast.NodeVisitor):
         op = ops.get(type(n.ops[0]))
         if op is None:
             self.bad(n, "comparison operator")
-        return f"({self.visit(n.left)} {op} {self.visit(n.comparators[0])})"
+        expr = f"({self.visit(n.left)} {op} {self.visit(n.comparators[0])})"
+        return expr if self.in_test else f"({expr} ? 1.0 : 0.0)"
 
     def v_BoolOp(self, n):
+        # Python's and/or return one of their operands; only as a truth value (the condition
+        # of `x if cond else y`) do they mean what && / || mean
+        if not self.in_test:
+            self.bad(n, "and/or outside the condition of a conditional expression")
         op = " && " if isinstance(n.op, ast.And) else " || "
         return "(" + op.join(self.visit(v) for v in n.values) + ")"
 
     def v_IfExp(self, n):
-        return f"({self.visit(n.test)} ? {self.visit(n.body)} : {self.visit(n.orelse)})"
+        self.in_test += 1
+        test = self.visit(n.test)
+        self.in_test -= 1
+        if not isinstance(n.test, (ast.Compare, ast.BoolOp)):
+            test = f"({test} != 0.0)"
+        return f"({test} ? {self.visit(n.body)} : {self.visit(n.orelse)})"
 
     def v_Attribute(self, n):   # np.pi, math.e, np.inf
         if isinstance(n.value, ast.Name) and n.value.id in _MODULES and n.attr in _CONST:

@@ -479,6 +479,7 @@ def test_lambda_strings_are_translated_to_cuda_on_the_cpu():
     assert args == ["a", "b"] and entry == "cb2_fn_my_like"
     assert check_source(src, entry, dim=2) == ""
     for bad in ("lambda a: [a]", "lambda a: a.real", "lambda a, _self: a", "lambda *a: 1.0",
+                "lambda a, b: a and b", "lambda a: a // 2", "lambda a: a % 2",
                 "lambda a: scipy.special.gamma(a)", "lambda a: q + a", "import os"):
         with pytest.raises(DeviceFunctionError):
             cuda_from_lambda(bad, "f")
@@ -517,3 +518,51 @@ def test_the_fused_external_kernel_compiles_without_a_gpu():
     bad = 'extern "C" __device__ double f(const double *p, int n) { return nope; }'
     assert lib.cb2_check_external_fused(bad.encode(), b"f", 2, log, len(log)) == -7
     assert "nope" in log.value.decode()
+
+
+LAMBDAS = [
+    "lambda a, b: stats.norm.logpdf(a - b**2, loc=0.1, scale=0.3) - np.log1p(a*a) + 0.5*np.pi",
+    "lambda a, b: -0.5*((a-0.1)**2+b**2)/0.09 - np.log1p(np.exp(-a)) if b > -1.5 else -np.inf",
+    "lambda a, b: np.minimum(a, 0.3) * np.maximum(b, -0.2) - abs(a - b) + np.arctan2(a, 1 + b*b)",
+    "lambda a, b: stats.uniform.logpdf(a, loc=-2, scale=4) + np.sqrt(a*a + b*b + 1e-3)**3 / 7",
+    "lambda b, a: -(100*(b-a**2)**2 + (1-a)**2)/20 + np.tanh(a) * np.cos(b) - np.power(1.5, a)",
+    "lambda a, b: (a if (a > 0 and b > 0) or a < -1 else -a) + math.erf(b) - np.log10(2 + a*a)",
+    "lambda a, b: -50 * (a > 1.2) + (a - b)**2 * (b <= 0.4) - (1 if a else 2)",
+]
+
+
+@pytest.mark.parametrize("text", LAMBDAS)
+def test_translated_lambdas_compute_what_python_computes(text, tmp_path):
+    """functor.cuda_from_lambda is a small compiler: its output is plain C arithmetic, so it
+    is compiled here with g++ as host code (the CUDA qualifiers defined away) and compared with
+    the Python callable the reference would evaluate (tools.py:344-384: ``np`` and ``stats``
+    in scope) on random points."""
+    import ctypes as C
+    import math
+    import subprocess
+
+    from scipy import stats
+
+    from cobaya_b200.functor import cuda_from_lambda
+
+    src, entry, args = cuda_from_lambda(text, "f")
+    prelude = ("#include <cmath>\n#include <cstring>\n#define __device__\n"
+               "#define __forceinline__ inline\n"
+               "static inline double __longlong_as_double(long long x) "
+               "{ double d; std::memcpy(&d, &x, 8); return d; }\n")
+    cfile, so = tmp_path / "f.cpp", tmp_path / "f.so"
+    cfile.write_text(prelude + src)
+    subprocess.run(["g++", "-O1", "-shared", "-fPIC", "-o", str(so), str(cfile)], check=True)
+    fn = getattr(C.CDLL(str(so)), entry)
+    fn.restype = C.c_double
+    fn.argtypes = [C.POINTER(C.c_double), C.c_int]
+    py = eval(text, {"np": np, "stats": stats, "math": math})
+    rng = np.random.default_rng(7)
+    pts = rng.uniform(-1.9, 1.9, (300, len(args)))
+    for p in pts:
+        want = float(py(*p))
+        got = fn((C.c_double * len(p))(*p), len(p))
+        if np.isfinite(want):
+            assert got == pytest.approx(want, rel=1e-12, abs=1e-13), (text, p)
+        else:
+            assert got == want
