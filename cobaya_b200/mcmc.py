@@ -251,6 +251,11 @@ class EnsembleMCMC:
             self._check_snapshot(snap)
             self.seed = int(snap["seed"])
             fm.set_covariance(np.asarray(snap["proposal_cov"]))  # the learned proposal
+            if "proposal_T" in snap:
+                # the transform exactly as the stopped run used it: the device checkpoint
+                # (cb2_checkpoint_device) and LAPACK agree to rounding only, and a resumed run
+                # continues bit for bit
+                fm.T = np.array(snap["proposal_T"], dtype=np.float64, copy=True)
             need = int(np.max(snap["n_rows"])) + self.launch_steps
             rows_want = max(rows_want, need + 2 * self.learn_every.value)
             if self.rows_per_chain is not None:
@@ -317,7 +322,8 @@ class EnsembleMCMC:
         return dict(
             version=self.SNAPSHOT_VERSION, blob=eng.export_state(),
             n_rows=np.asarray(n_rows, np.int64), rows=rows_all,
-            proposal_cov=self.fm.get_covariance(), seed=np.uint64(self.seed),
+            proposal_cov=self.fm.get_covariance(), proposal_T=np.asarray(self.fm.T),
+            seed=np.uint64(self.seed),
             rank=self.dist.rank, world=self.dist.size, n_chains_local=self.n_chains_local,
             D=self.fm.D, row_width=self.fm.row_width,
             converged=bool(self.converged), Rminus1_last=float(self.Rminus1_last),
