@@ -9,7 +9,10 @@
  * INTEGRATION.md).  Each entry point names the reference code it replaces.
  *
  * Conventions: extern "C"; plain pointers and sizes; return 0 = ok, negative =
- * error (message via cb2_last_error); the caller owns every HOST buffer, the
+ * error (message via cb2_last_error): -1 bad argument / call order, -2 CUDA error,
+ * -3 no device or library (there is no CPU fallback), -4 not supported for this model,
+ * -5 not enough rows yet, -6 NVRTC not available, -7 run-time compile error (external
+ * functions); the caller owns every HOST buffer, the
  * library owns all DEVICE memory behind the opaque handle; one host thread per
  * handle; all work is enqueued on the handle's CUDA stream, cb2_sync blocks.
  * All floating-point data is IEEE binary64; matrices are row-major.
@@ -34,8 +37,9 @@ typedef struct cb2_engine cb2_engine;
 /* flags returned per chain by cb2_get_flags */
 #define CB2_FLAG_STUCK 1u        /* mcmc.py:717-743 "chain has been stuck" */
 #define CB2_FLAG_ROWS_FULL 2u    /* per-chain sample capacity exhausted */
-#define CB2_FLAG_INTERNAL 4u     /* engine invariant violated (basis/tape window, or a
-                                    non-finite start point in cb2_set_state) */
+#define CB2_FLAG_INTERNAL 4u     /* engine invariant violated (basis/tape window), a
+                                    non-finite start point in cb2_set_state, or a NaN
+                                    returned by an external function */
 
 /* moment modes of cb2_moments */
 #define CB2_MOMENTS_HALVES 0     /* multi-chain rule, mcmc.py:785-793 */
