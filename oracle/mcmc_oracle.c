@@ -314,6 +314,12 @@ double orc_logpost(const orc_model *m, const double *x, double *logprior,
             if (L->derived) doff += L->dim * L->n_modes;
         } else if (L->kind == ORC_LIKE_CONSTANT) {
             v = L->scale; /* one.logp_one (likelihoods/one/one.py:26-28) */
+        } else if (L->kind == ORC_LIKE_EXTERNAL) {
+            /* LikelihoodExternalFunction.logp (likelihood.py:226-255): the callable on the
+             * likelihood's own input parameters */
+            double p[256];
+            for (int i = 0; i < L->dim && i < 256; ++i) p[i] = x[L->idx[i]];
+            v = L->fn(p, L->dim);
         } else {
             v = like_rosenbrock(L, x);
         }

@@ -34,6 +34,9 @@ extern "C" {
 #define ORC_LIKE_GAUSSIAN_MIXTURE 0
 #define ORC_LIKE_ROSENBROCK 1
 #define ORC_LIKE_CONSTANT 2 /* likelihoods/one/one.py:26-28: logp = scale (0 for `one`) */
+#define ORC_LIKE_EXTERNAL 3 /* LikelihoodExternalFunction (likelihood.py:150-255): a host
+                               function of the inputs (the tests compile the SAME source the
+                               engine hands to NVRTC as host code) */
 
 typedef struct {
     int32_t kind;      /* ORC_LIKE_* */
@@ -46,6 +49,7 @@ typedef struct {
     const double *logdet; /* [n_modes] log|Sigma_k| */
     const double *weights;/* [n_modes] (already normalised) */
     double scale;         /* rosenbrock: logp = -scale * sum(...) */
+    double (*fn)(const double *p, int n); /* external: log L of the gathered inputs */
 } orc_like;
 
 /* scipy.stats distributions reached through pdf.logpdf (cobaya/prior.py:520-525);

@@ -36,6 +36,7 @@ class _Like(C.Structure):
         ("derived", C.c_int32),
         ("idx", C.c_void_p), ("means", C.c_void_p), ("linv", C.c_void_p),
         ("logdet", C.c_void_p), ("weights", C.c_void_p), ("scale", C.c_double),
+        ("fn", C.c_void_p),
     ]
 
 
@@ -100,6 +101,38 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+_HOST_PRELUDE = ("#include <cmath>\n#include <cstring>\n#define __device__\n"
+                 "#define __forceinline__ inline\n#define __restrict__\n"
+                 "static inline double __longlong_as_double(long long x) "
+                 "{ double d; std::memcpy(&d, &x, 8); return d; }\n")
+_host_functions = {}
+
+
+def host_function(source: str, name: str, keep=None):
+    """Address of the external likelihood function ``name`` of ``source`` -- the CUDA source
+    the engine compiles with NVRTC -- compiled as HOST code with g++ (the CUDA qualifiers
+    defined away), so that the oracle evaluates the same arithmetic (test infrastructure)."""
+    import hashlib
+    import subprocess
+    import tempfile
+
+    key = hashlib.sha1((source + "\0" + name).encode()).hexdigest()
+    if key not in _host_functions:
+        d = tempfile.mkdtemp(prefix="cb2_oracle_ext_")
+        cpp, so = os.path.join(d, "f.cpp"), os.path.join(d, "f.so")
+        with open(cpp, "w") as f:
+            f.write(_HOST_PRELUDE + source)
+        res = subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", so, cpp],
+                             capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("host build of the external function failed:\n" + res.stderr)
+        _host_functions[key] = C.CDLL(so)
+    lib = _host_functions[key]
+    if keep is not None:
+        keep.append(lib)
+    return C.cast(getattr(lib, name), C.c_void_p).value
+
+
 class OracleModel:
     """Keeps the numpy arrays alive behind an ``orc_model`` struct."""
 
@@ -126,6 +159,8 @@ class OracleModel:
                 likes[i].means = _p(k(lk.means)); likes[i].linv = _p(k(lk.linv))
                 likes[i].logdet = _p(k(lk.logdet)); likes[i].weights = _p(k(lk.weights))
             likes[i].scale = lk.scale
+            if lk.kind == 3:   # external function: the engine's CUDA source compiled for the host
+                likes[i].fn = host_function(lk.source, lk.fn_name, keep=self._keep)
         self._likes = likes
         m.n_like = fm.n_like
         m.likes = C.cast(likes, C.c_void_p)

@@ -10,36 +10,11 @@ the function differ in the last bits), integer weights exact.
 import numpy as np
 import pytest
 
-from tests.util import load_golden
+from tests.util import flat_g8, load_golden
 
 pytestmark = pytest.mark.gpu
 
 RTOL, ATOL = 1e-9, 1e-11
-
-
-def flat_g8(g, source=None):
-    from cobaya_b200.flatmodel import FlatModel, LikeSpec
-
-    from tests import ext_functions
-
-    names = [str(s) for s in g["sampled"]]
-    assert names == ["a", "b", "c"] and [str(s) for s in g["likes"]] == ["banana", "gaussian"]
-    kind = np.array([0, 0, 1], np.int32)
-    lower = np.array([-2.0, -1.0, -np.inf])
-    upper = np.array([2.0, 3.0, np.inf])
-    likes = [LikeSpec.external([0, 1], source or ext_functions.BANANA_CUDA, "banana",
-                               name="banana"),
-             LikeSpec.gaussian([2], [0.1], [[0.04]], normalized=True, name="gaussian")]
-    i_of_j = [int(i) for i in g["i_of_j"]]
-    blocks, j = [], 0
-    for n in g["block_sizes"]:
-        blocks.append(i_of_j[j: j + int(n)])
-        j += int(n)
-    return FlatModel(names=names, prior_kind=kind, lower=lower, upper=upper, loc=np.zeros(3),
-                     pscale=np.ones(3), periodic=np.zeros(3, np.int32), likes=likes,
-                     blocks=blocks, oversampling=[int(o) for o in g["oversampling"]],
-                     output_thin=int(g["output_thin"]),
-                     proposal_cov=np.asarray(g["proposal_cov"]), max_tries=int(g["max_tries"]))
 
 
 def _engine(fm, n, seed, id0=0, rows_cap=4096):

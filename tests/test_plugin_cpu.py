@@ -566,3 +566,45 @@ def test_translated_lambdas_compute_what_python_computes(text, tmp_path):
             assert got == pytest.approx(want, rel=1e-12, abs=1e-13), (text, p)
         else:
             assert got == want
+
+
+def test_external_functions_through_the_plugin_on_the_cpu_test_engine():
+    """The plugin's handling of external functions (lowering of the callable's CUDA twin or
+    lambda string, the start-point check of the twin against the Python callable, rows with
+    the function's own chi2 column) with the oracle-backed test engine, which evaluates the
+    SAME CUDA source compiled as host code: no GPU needed for the host logic."""
+    enable_reference()
+    from cobaya.log import LoggedError
+    from cobaya.run import run
+
+    import cobaya_b200.plugin as plugin
+    from cobaya_b200.functor import device_function
+    from tests import ext_functions
+    from tests.oracle_engine import OracleEngine
+
+    info, _ = ext_functions.info_g8()
+    opts = dict(info["sampler"]["mcmc"])
+    opts.update(chains_per_gpu=6, max_samples=60, learn_proposal=False, seed=3,
+                Rminus1_stop=1e-9)
+    info["sampler"] = {"cobaya_b200.plugin.MCMC": opts}
+    # a second external component given as a lambda string (the YAML form)
+    info["likelihood"]["soft"] = "lambda c: -0.5 * c**2 / 4.0 - np.log1p(c*c)"
+    plugin.MCMC._engine_factory = OracleEngine
+    try:
+        _, smp = run(copy.deepcopy(info))
+        rows = smp.products()["sample"]
+        a, b, c = (rows[p].to_numpy() for p in "abc")
+        np.testing.assert_allclose(rows["chi2__banana"].to_numpy(),
+                                   -2 * ext_functions.banana(a, b), rtol=1e-10, atol=1e-11)
+        np.testing.assert_allclose(rows["chi2__soft"].to_numpy(),
+                                   c**2 / 4.0 + 2 * np.log1p(c * c), rtol=1e-10, atol=1e-11)
+        assert len(rows) >= 6 * 60
+        # a twin that computes something else is refused before sampling
+        bad = device_function(ext_functions.BANANA_CUDA.replace("0.09", "0.08"))(
+            lambda a, b: ext_functions.banana(a, b))
+        info2 = copy.deepcopy(info)
+        info2["likelihood"]["banana"] = {"external": bad}
+        with pytest.raises(LoggedError, match="disagrees"):
+            run(info2)
+    finally:
+        plugin.MCMC._engine_factory = None
