@@ -185,7 +185,7 @@ int32_t orc_n_derived(const orc_model *m) {
 }
 
 int32_t orc_row_width(const orc_model *m) {
-    return 2 + m->D + orc_n_derived(m) + 2 + 1 + m->n_like; /* collection.py:154-159 */
+    return 2 + m->D + orc_n_derived(m) + 2 + m->n_ext_prior + 1 + m->n_like; /* collection.py:154-159 */
 }
 
 /* log(Phi(b) - Phi(a)) for a < b (scipy.stats truncnorm's normalisation, restated from
@@ -292,6 +292,11 @@ static double like_rosenbrock(const orc_like *L, const double *x) {
 /* Model.logposterior (model.py:579-678): prior first; -inf prior skips likelihoods */
 double orc_logpost(const orc_model *m, const double *x, double *logprior,
                    double *loglikes, double *derived) {
+    return orc_logpost_ex(m, x, logprior, loglikes, derived, NULL);
+}
+
+double orc_logpost_ex(const orc_model *m, const double *x, double *logprior,
+                      double *loglikes, double *derived, double *pl) {
     for (int i = 0; i < m->D; ++i)
         if (!isfinite(x[i])) { /* model.py:623-630 non-finite -> -inf */
             *logprior = -INFINITY;
@@ -299,6 +304,20 @@ double orc_logpost(const orc_model *m, const double *x, double *logprior,
             return -INFINITY;
         }
     double lp = logprior_internal(m, x);
+    if (pl) pl[0] = lp;
+    if (lp != -INFINITY) {
+        /* Prior.logps (prior.py:700-720): external priors after a finite internal one */
+        double ext = 0.0;
+        for (int k = 0; k < m->n_ext_prior; ++k) {
+            const orc_like *P = &m->ext_priors[k];
+            double p[256];
+            for (int i = 0; i < P->dim && i < 256; ++i) p[i] = x[P->idx[i]];
+            const double v = P->fn(p, P->dim);
+            if (pl) pl[1 + k] = v;
+            ext += v;
+        }
+        if (m->n_ext_prior) lp += ext;
+    }
     *logprior = lp;
     if (lp == -INFINITY) {
         for (int l = 0; l < m->n_like; ++l) loglikes[l] = NAN;
@@ -353,6 +372,7 @@ struct orc_chain {
     int32_t j_start[ORC_MAX_BLOCKS];
     double *x, *trial, *der, *trial_der, *loglikes, *trial_loglikes;
     double logpost, logprior;
+    double pl[1 + ORC_MAX_EXT_PRIORS], trial_pl[1 + ORC_MAX_EXT_PRIORS]; /* prior components */
     int64_t weight, prior_rej, burn_in_left, added_weight;
     int64_t n_steps, n_accepted;
     cycler_t cyc_main, cyc_slow, cyc_fast;
@@ -403,7 +423,7 @@ orc_chain *orc_chain_new(const orc_model *m, uint64_t seed, uint64_t chain_id,
     c->pe_ll = (double *)calloc(nl, sizeof(double));
     c->tmp_ll = (double *)calloc(nl, sizeof(double));
     memcpy(c->x, x0, sizeof(double) * D);
-    c->logpost = orc_logpost(m, c->x, &c->logprior, c->loglikes, c->der);
+    c->logpost = orc_logpost_ex(m, c->x, &c->logprior, c->loglikes, c->der, c->pl);
     c->weight = 1;                              /* OneSamplePoint.add, collection.py:1355 */
     c->prior_rej = 0;
     c->burn_in_left = burn_in * m->output_thin + 1; /* mcmc.py:265 */
@@ -513,7 +533,8 @@ static void write_row(const orc_chain *c, double *row, double weight) {
     for (int i = 0; i < c->D; ++i) row[k++] = c->x[i];
     for (int i = 0; i < c->n_der; ++i) row[k++] = c->der[i];
     row[k++] = -c->logprior;
-    row[k++] = -c->logprior; /* minuslogprior__0 (no external priors) */
+    row[k++] = m->n_ext_prior ? -c->pl[0] : -c->logprior; /* minuslogprior__0 */
+    for (int e = 0; e < m->n_ext_prior; ++e) row[k++] = -c->pl[1 + e];
     double ll = 0.0;
     for (int l = 0; l < c->n_like; ++l) ll += c->loglikes[l];
     row[k++] = -2 * ll;
@@ -548,6 +569,7 @@ static int process(orc_chain *c, int accept, const double *trial, double t_logpo
         } else c->burn_in_left -= 1;
         memcpy(c->x, trial, sizeof(double) * c->D);
         c->logpost = t_logpost; c->logprior = t_logprior;
+        if (m->n_ext_prior) memcpy(c->pl, c->trial_pl, sizeof(c->pl));
         memcpy(c->loglikes, t_ll, sizeof(double) * c->n_like);
         if (c->n_der) memcpy(c->der, t_der, sizeof(double) * c->n_der);
         c->weight = 1;
@@ -571,7 +593,8 @@ static int step_metropolis(orc_chain *c, double *rows, int64_t cap, int64_t *n_r
     block_proposal(c, c->trial, b, 0);                             /* :557 */
     reduce_periodic(m, c->trial);                                  /* :558 */
     double lp;
-    double lpost = orc_logpost(m, c->trial, &lp, c->trial_loglikes, c->trial_der);
+    double lpost = orc_logpost_ex(m, c->trial, &lp, c->trial_loglikes, c->trial_der,
+                                  c->trial_pl);
     int acc = metropolis_accept(c, lpost, c->logpost, 0);          /* :560 */
     return process(c, acc, c->trial, lpost, lp, c->trial_loglikes, c->trial_der, rows,
                    cap, n_rows);

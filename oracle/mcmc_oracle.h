@@ -90,12 +90,20 @@ typedef struct {
     double temperature;
     int64_t max_tries;         /* already in absolute units */
     int32_t output_thin;
+    /* external priors (cobaya/prior.py:537-577,765-772): host functions of some sampled
+     * parameters, evaluated where the internal prior is finite; each has its own
+     * minuslogprior__<name> column after minuslogprior__0.  Metropolis only. */
+    int32_t n_ext_prior;
+    const orc_like *ext_priors; /* kind ORC_LIKE_EXTERNAL entries: idx, dim, fn */
 } orc_model;
+
+#define ORC_MAX_EXT_PRIORS 8
 
 typedef struct orc_chain orc_chain;
 
 /* row width: weight, minuslogpost, D sampled, n_derived, minuslogprior,
- * minuslogprior__0, chi2, n_like chi2__x  (collection.py:154-159) */
+ * minuslogprior__0, n_ext_prior minuslogprior__x, chi2, n_like chi2__x
+ * (collection.py:154-159) */
 int32_t orc_row_width(const orc_model *m);
 int32_t orc_n_derived(const orc_model *m);
 
@@ -103,6 +111,9 @@ int32_t orc_n_derived(const orc_model *m);
  * (only if logprior is finite, else NaN) and derived[n_derived]. */
 double orc_logpost(const orc_model *m, const double *x, double *logprior,
                    double *loglikes, double *derived);
+/* the same with the prior components: pl[0] internal, pl[1..n_ext_prior] external (may be NULL) */
+double orc_logpost_ex(const orc_model *m, const double *x, double *logprior,
+                      double *loglikes, double *derived, double *pl);
 
 orc_chain *orc_chain_new(const orc_model *m, uint64_t seed, uint64_t chain_id,
                          const double *x0, int64_t burn_in);

@@ -55,6 +55,7 @@ class _Model(C.Structure):
         ("drag_interp_steps", C.c_int32),
         ("T", C.c_void_p), ("proposal_scale", C.c_double),
         ("temperature", C.c_double), ("max_tries", C.c_int64), ("output_thin", C.c_int32),
+        ("n_ext_prior", C.c_int32), ("ext_priors", C.c_void_p),
     ]
 
 
@@ -177,6 +178,18 @@ class OracleModel:
         m.temperature = fm.temperature
         m.max_tries = int(min(fm.max_tries, 2**59))  # x10 during burn-in must fit int64
         m.output_thin = int(fm.output_thin)
+        eps = list(getattr(fm, "ext_priors", []) or [])
+        if eps and fm.drag:
+            raise ValueError("external priors are not supported together with dragging")
+        ext = (_Like * max(1, len(eps)))()
+        for i, ep in enumerate(eps):
+            ext[i].kind = 3
+            ext[i].dim = ep.dim
+            ext[i].idx = _p(k(ep.idx, np.int32))
+            ext[i].fn = host_function(ep.source, ep.fn_name, keep=self._keep)
+        self._ext_priors = ext
+        m.n_ext_prior = len(eps)
+        m.ext_priors = C.cast(ext, C.c_void_p)
         self.c = m
 
     def _keepa(self, a, dtype=np.float64):

@@ -606,5 +606,18 @@ def test_external_functions_through_the_plugin_on_the_cpu_test_engine():
         info2["likelihood"]["banana"] = {"external": bad}
         with pytest.raises(LoggedError, match="disagrees"):
             run(info2)
+        # an external prior (own minuslogprior__ring column) through the same machinery
+        info9, _ = ext_functions.info_g9()
+        opts9 = dict(info9["sampler"]["mcmc"])
+        opts9.update(chains_per_gpu=5, max_samples=50, seed=4, Rminus1_stop=1e-9)
+        info9["sampler"] = {"cobaya_b200.plugin.MCMC": opts9}
+        _, smp9 = run(info9)
+        rows9 = smp9.products()["sample"]
+        a9, b9 = rows9["a"].to_numpy(), rows9["b"].to_numpy()
+        np.testing.assert_allclose(rows9["minuslogprior__ring"].to_numpy(),
+                                   -ext_functions.ring(a9, b9), rtol=1e-10, atol=1e-11)
+        np.testing.assert_allclose(rows9["minuslogprior"].to_numpy(),
+                                   rows9["minuslogprior__0"].to_numpy()
+                                   + rows9["minuslogprior__ring"].to_numpy(), rtol=1e-12)
     finally:
         plugin.MCMC._engine_factory = None
