@@ -519,6 +519,8 @@ def run_gpu_arm(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "dominant_kernel": dom,
+                     "binding_roof": "fp64 tensor pipe (DMMA m8n8k4; see roofline.fp64.frac), "
+                                     "not HBM: the HBM figures follow the contract's recipe",
                      "dominant_kernel_own": {"bytes_per_proposal": own_bytes[dom],
                                              "achieved": dom_achieved,
                                              "frac": dom_achieved / peak},
